@@ -1,0 +1,174 @@
+/* nkbk.h -- C ABI of libnkbk.so: the B200 (sm_100a) kernels behind the
+ * nkb-classification hot path.
+ *
+ * The reference (nkb-tech/nkb-classification) is 100 % Python and has no FFI
+ * of its own; its boundary for this path is the config-driven Python API
+ * (SURVEY.md section 8b).  Every entry point below therefore names the Python
+ * call sites it replaces; the Python mirror in nkb_classification_b200/ binds
+ * these symbols through ctypes and keeps the reference's signatures.
+ *
+ * Conventions
+ *   - extern "C", plain pointers / sizes / scalars, no torch types.
+ *   - Device pointers unless a parameter says "host".  The caller owns every
+ *     buffer; the library owns only its NCCL communicator.
+ *   - Every launch is asynchronous on `stream` (a cudaStream_t passed as
+ *     void*; NULL = the legacy default stream) and re-entrant per stream.
+ *   - Return value: 0 = NKBK_OK, negative = error; the message is available
+ *     from nkbk_last_error() (thread local).  Nothing throws across the ABI.
+ *   - There is no CPU fallback: without a CUDA device every compute entry
+ *     point returns NKBK_E_CUDA.
+ */
+#ifndef NKBK_H_
+#define NKBK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NKBK_ABI_VERSION 1
+
+enum {
+    NKBK_OK = 0,
+    NKBK_E_ARG = -1,          /* NULL / out-of-range argument            */
+    NKBK_E_SHAPE = -2,        /* unsupported size                         */
+    NKBK_E_CUDA = -3,         /* CUDA runtime error (message has detail)  */
+    NKBK_E_NCCL = -4,         /* NCCL error / communicator not initialised */
+    NKBK_E_UNSUPPORTED = -5   /* valid request this build cannot serve    */
+};
+
+enum { NKBK_F32 = 0, NKBK_BF16 = 1 };                    /* element types */
+enum { NKBK_MODE_STRETCH = 0, NKBK_MODE_LETTERBOX = 1 }; /* K1 geometry   */
+enum { NKBK_LOSS_CE = 0, NKBK_LOSS_FOCAL = 1 };          /* K2 loss kind  */
+
+int nkbk_abi_version(void);
+const char* nkbk_last_error(void);
+/* Number of kernels this library has launched in the calling process. */
+int64_t nkbk_launch_count(void);
+
+/* ------------------------------------------------------------------------
+ * K1  fused crop + cv2-INTER_LINEAR-exact uint8 resize + Normalize + HWC->NCHW
+ *
+ * Replaces, per sample: AnnotatedYOLODataset.__getitem__ slice
+ * (nkb_classification/dataset.py:398-409), Transforms.__call__ (:96-102) with
+ * the A.Resize | A.LongestMaxSize + A.PadIfNeeded(BORDER_CONSTANT), A.Normalize,
+ * ToTensorV2 pipeline of configs/singletask_config.py:203-219, default_collate
+ * + pin + fp32 H2D (dataset.py:608-629, engine.py:40,101) and the per-box loop
+ * of Evaluator.classify_crops (metrics/det_cls_val.py:228-244).
+ *
+ *   frames_base  uint8 source pixels, interleaved 3-channel rows
+ *   frame_desc   int64 [n_frames][4] = {byte offset from frames_base, height,
+ *                width, row pitch in bytes}; width >= 2
+ *   boxes        int32 [n][4] = x0, y0, x1, y1 (pixel, x1/y1 exclusive),
+ *                as produced by bbox_xywhn2xyxy (dataset.py:414-421)
+ *   frame_idx    int32 [n]
+ *   mode         NKBK_MODE_STRETCH   -> A.Resize(out_h, out_w)
+ *                NKBK_MODE_LETTERBOX -> A.LongestMaxSize(max_size) +
+ *                                       centred constant pad to out_h x out_w
+ *   pad_value    host uint8[3] (letterbox border, in OUTPUT channel order)
+ *   mean255      host float[3]  = f32(mean) * f32(max_pixel_value)
+ *   denom        host float[3]  = 1 / (f32(std) * f32(max_pixel_value))
+ *   channel_swap non-zero: source is BGR, emit RGB (cv2.cvtColor BGR2RGB)
+ *   out          [n][3][out_h][out_w] of out_dtype (NKBK_F32 | NKBK_BF16)
+ *   out_u8       optional [n][out_h][out_w][3] resized uint8 pixels (may be NULL)
+ *   bad_count    optional int32 counter, incremented once per crop whose box
+ *                is empty or leaves its frame (such crops are filled with the
+ *                normalised pad value)
+ * ---------------------------------------------------------------------- */
+int nkbk_preprocess_crops(const void* frames_base, const int64_t* frame_desc, int n_frames, const int32_t* boxes,
+                          const int32_t* frame_idx, int n, int mode, int out_h, int out_w, int max_size,
+                          const uint8_t* pad_value, const float* mean255, const float* denom, int channel_swap,
+                          void* out, int out_dtype, uint8_t* out_u8, int32_t* bad_count, void* stream);
+
+/* Host-only helper (no CUDA): the per-axis coefficient table K1 uses, for
+ * parity tests on machines without a GPU.  Writes dsize entries each. */
+int nkbk_debug_axis_table(int dsize, int ssize, int horizontal, int32_t* src_index, int32_t* coef0, int32_t* coef1);
+/* Host-only helper: letterbox geometry K1 uses. out4 = new_h, new_w, top, left. */
+int nkbk_debug_letterbox(int h, int w, int max_size, int out_h, int out_w, int32_t* out4);
+
+/* ------------------------------------------------------------------------
+ * K2  all task heads as one segmented GEMM + softmax + CE/focal loss + grads
+ *
+ * Replaces: the per-task nn.Linear of SingletaskClassifier / MultitaskClassifier
+ * (nkb_classification/model.py:41-43, :114-116), FocalLoss.forward
+ * (losses.py:59-94), nn.CrossEntropyLoss(weight) (losses.py:155-159),
+ * MultitaskCriterion.__call__ (losses.py:110-147), their autograd backward
+ * (engine.py:55-58) and the softmax of BaseLogger.log_iter (logging.py:270,279).
+ *
+ * Heads are concatenated: W_cat [NC][D], b_cat [NC], NC = seg_offsets[T];
+ * task t owns rows seg_offsets[t] .. seg_offsets[t+1].
+ *
+ * The "reduce buffer" is one contiguous fp32 array (size from
+ * nkbk_heads_reduce_buf_len):   [ dW_sum NC*D | db_sum NC | loss_sum T | denom T ]
+ * holding UNNORMALISED sums over the local rows, so that N ranks can all-reduce
+ * it once (K4) and then call nkbk_heads_finalize; 1 GPU calls finalize directly.
+ *
+ *   emb            [B][D] row-major, NKBK_F32 or NKBK_BF16
+ *   W_cat, b_cat   fp32
+ *   seg_offsets    host int32 [T+1]
+ *   labels         int64 [B][T]; ignore_index rows contribute nothing
+ *   class_weight   optional fp32 [NC] (CE `weight` / focal `alpha`), may be NULL
+ *   out_logits     optional fp32 [B][NC]
+ *   out_probs      optional fp32 [B][NC]   per-task softmax (fp32)
+ *   dlogits        fp32 [B][NC]  d(loss_sum)/d(logit) (required when grads wanted;
+ *                  may be NULL for a forward-only call -> reduce_buf then only
+ *                  receives loss_sum / denom and its dW/db parts are zeroed)
+ *   reduce_buf     fp32, see above
+ *   workspace      scratch, size >= nkbk_heads_workspace_bytes(B, D, NC, T)
+ * ---------------------------------------------------------------------- */
+int64_t nkbk_heads_reduce_buf_len(int D, int NC, int T);
+int64_t nkbk_heads_workspace_bytes(int B, int D, int NC, int T);
+
+int nkbk_heads_fwd_loss_bwd(const void* emb, int emb_dtype, int B, int D, const float* W_cat, const float* b_cat,
+                            const int32_t* seg_offsets, int T, const int64_t* labels, int loss_kind, float gamma,
+                            const float* class_weight, int64_t ignore_index, float* out_logits, float* out_probs,
+                            float* dlogits, float* reduce_buf, void* workspace, size_t workspace_bytes,
+                            void* stream);
+
+/* In place: dW, db <- sums / denom[task]; out_loss (fp32 [T+1]) <- per-task mean
+ * losses and their unweighted sum (losses.py:140-147).  denom == 0 -> 0. */
+int nkbk_heads_finalize(float* reduce_buf, int D, const int32_t* seg_offsets, int T, float* out_loss, void* stream);
+
+/* d(loss)/d(emb) [B][D] (emb_dtype) from dlogits and the (all-reduced,
+ * not yet finalised or finalised -- denom is untouched by finalize) reduce_buf. */
+int nkbk_heads_demb(const float* dlogits, const float* reduce_buf, const float* W_cat, const int32_t* seg_offsets,
+                    int T, int B, int D, void* out_demb, int out_dtype, void* stream);
+
+/* ------------------------------------------------------------------------
+ * K3  per-task argmax + confusion-matrix accumulation
+ *
+ * Replaces: argmax + D2H lists of BaseLogger.log_iter (logging.py:272-281),
+ * the confusion matrix inside sklearn balanced_accuracy_score
+ * (metrics.py:31) and inference()'s per-task argmax (inference.py:53,59).
+ *
+ *   logits   [B][ld] NKBK_F32 | NKBK_BF16, ld >= seg_offsets[T]
+ *   labels   optional int64 [B][T] (NULL -> predictions only)
+ *   out_pred optional int32 [B][T]
+ *   cm       optional int64, task t at offset sum_{s<t} C_s^2, row = gt,
+ *            col = pred; ACCUMULATES (caller zeroes at epoch start)
+ * Ties -> lowest index; NaN is maximal (torch.argmax semantics).
+ * ---------------------------------------------------------------------- */
+int nkbk_argmax_confusion(const void* logits, int dtype, int B, int ld, const int32_t* seg_offsets, int T,
+                          const int64_t* labels, int32_t* out_pred, int64_t* cm, void* stream);
+
+/* ------------------------------------------------------------------------
+ * K4  batch sharding: the only exchange step of the path
+ *
+ * The reference is single-GPU (no torch.distributed anywhere);
+ * this is the new data-parallel step: one all-reduce of the K2 reduce buffer
+ * and one of the int64 confusion counts, NCCL over NVLink/NVSwitch.
+ * ---------------------------------------------------------------------- */
+#define NKBK_UNIQUE_ID_BYTES 128
+int nkbk_comm_unique_id(void* out_id_host);               /* rank 0, host buffer of 128 bytes */
+int nkbk_comm_init(int rank, int world, const void* id_host, int device);
+int nkbk_comm_world(void);                                 /* 0 when not initialised */
+/* Sum-all-reduce both payloads in one NCCL group; either may be NULL / 0. */
+int nkbk_allreduce_heads(float* reduce_buf, int64_t n_f32, int64_t* cm, int64_t n_i64, void* stream);
+int nkbk_comm_shutdown(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NKBK_H_ */

@@ -1,0 +1,361 @@
+// K1: fused YOLO-box crop + cv2-INTER_LINEAR-exact uint8 resize + Normalize +
+// HWC->NCHW, one launch per batch.  See include/nkbk.h for the contract and
+// DESIGN.md section "K1" for the layout / roofline reasoning.
+//
+// Work decomposition (v1, "row walker"):
+//   grid  = (crop, band-of-rows block, column tile)       block = 4 warps
+//   warp  = one band of `rows_per_warp` consecutive output rows of one crop
+//   lane  = output columns  tile*32*JMAX + lane + 32*j,  j = 0..JMAX-1
+//           -> every store instruction of a warp writes one full 128-byte line
+//              of one channel plane (fp32), every source load instruction of a
+//              warp touches one contiguous ~32*scale*3-byte span of one row.
+// Per lane the horizontal tables (byte offset of the 2-pixel window, packed
+// 11-bit coefficient pair) live in registers for the whole band.  The warp
+// walks down its rows keeping the horizontally-filtered values (H >> 4, the
+// 15-bit quantity OpenCV feeds its vertical pass) of the two source rows in
+// registers, so a source row is fetched and filtered once per band even when
+// consecutive output rows share it (up-scaling) or it moves from the lower
+// to the upper tap (down-scaling by < 2).
+//
+// Integer pipeline per output sample (bit-exact with cv2):
+//   6 interleaved source bytes (2 pixels) are cut out of 2-3 aligned 32-bit
+//   words with two funnel shifts, one PRMT per channel pairs the two taps, one
+//   IDP.2A (16-bit x 8-bit dot product) yields H = a0*p0 + a1*p1, >> 4.
+//   Vertical: IMAD.HI with the coefficient pre-shifted by 16 gives
+//   (b*(H>>4))>>16 with the "+2" and the second tap folded into the addend,
+//   then >> 2, int->float, (v - mean255) * denom as two rounded fp32 ops.
+#include "nkbk_common.cuh"
+#include "k1_coef.h"
+
+namespace nkbk {
+
+constexpr int K1_WARPS = 4;
+
+struct K1Params {
+    const uint8_t* frames;
+    const int64_t* frame_desc;
+    const int32_t* boxes;
+    const int32_t* frame_idx;
+    int n, n_frames, mode, out_h, out_w, max_size;
+    float m[3], d[3];
+    float padf[3];       // normalised pad value per output channel
+    uint32_t padu[3];    // raw pad value per output channel
+    uint32_t sel[3];     // PRMT selectors per output channel (encode channel_swap)
+    void* out;
+    uint8_t* out_u8;
+    int32_t* bad_count;
+    int rows_per_warp;
+};
+
+template <typename OutT>
+__device__ __forceinline__ void store_out(OutT* p, float v);
+template <>
+__device__ __forceinline__ void store_out<float>(float* p, float v) {
+    __stcs(p, v);
+}
+template <>
+__device__ __forceinline__ void store_out<__nv_bfloat16>(__nv_bfloat16* p, float v) {
+    __stcs(reinterpret_cast<unsigned short*>(p), __bfloat16_as_ushort(__float2bfloat16_rn(v)));
+}
+
+// Horizontal pass of one source row for this lane's JMAX columns.
+template <int JMAX>
+__device__ __forceinline__ void hrow(uint32_t (&H)[JMAX][3], const uint8_t* __restrict__ rowp,
+                                     const uint32_t (&xo)[JMAX], const uint32_t (&cf)[JMAX], const uint32_t sel0,
+                                     const uint32_t sel1, const uint32_t sel2) {
+    uint32_t w0[JMAX], w1[JMAX], w2[JMAX], k8[JMAX];
+#pragma unroll
+    for (int j = 0; j < JMAX; ++j) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(rowp + xo[j]);
+        const uint32_t* al = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+        k8[j] = (uint32_t(a) & 3u) * 8u;
+        w0[j] = __ldg(al);
+        w1[j] = __ldg(al + 1);
+        w2[j] = 0u;
+        if (k8[j] == 24u) w2[j] = __ldg(al + 2);  // only then are bytes 8.. of the window needed
+    }
+#pragma unroll
+    for (int j = 0; j < JMAX; ++j) {
+        const uint32_t lo = __funnelshift_r(w0[j], w1[j], k8[j]);  // bytes o .. o+3
+        const uint32_t hi = __funnelshift_r(w1[j], w2[j], k8[j]);  // bytes o+4 .. o+7
+        H[j][0] = __dp2a_lo(cf[j], __byte_perm(lo, hi, sel0), 0u) >> 4;
+        H[j][1] = __dp2a_lo(cf[j], __byte_perm(lo, hi, sel1), 0u) >> 4;
+        H[j][2] = __dp2a_lo(cf[j], __byte_perm(lo, hi, sel2), 0u) >> 4;
+    }
+}
+
+template <int JMAX, typename OutT, bool WRITE_U8>
+__global__ void __launch_bounds__(K1_WARPS * 32) k1_crop_resize_normalize(const K1Params p) {
+    const int crop = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int band = blockIdx.y * K1_WARPS + warp;
+    const int y_begin = band * p.rows_per_warp;
+    if (y_begin >= p.out_h) return;
+    const int nrows = min(p.rows_per_warp, p.out_h - y_begin);
+    const int ox0 = blockIdx.z * (32 * JMAX) + lane;
+
+    // ---- crop geometry (warp-uniform) ----
+    const int bx0 = __ldg(p.boxes + 4 * (int64_t)crop + 0), by0 = __ldg(p.boxes + 4 * (int64_t)crop + 1);
+    const int bx1 = __ldg(p.boxes + 4 * (int64_t)crop + 2), by1 = __ldg(p.boxes + 4 * (int64_t)crop + 3);
+    const int fi = __ldg(p.frame_idx + crop);
+    bool ok = fi >= 0 && fi < p.n_frames;
+    int64_t f_off = 0, pitch = 0;
+    int fh = 0, fw = 0;
+    if (ok) {
+        const int64_t* fd = p.frame_desc + 4 * (int64_t)fi;
+        f_off = __ldg(fd + 0);
+        fh = (int)__ldg(fd + 1);
+        fw = (int)__ldg(fd + 2);
+        pitch = __ldg(fd + 3);
+    }
+    const int bw = bx1 - bx0, bh = by1 - by0;
+    ok = ok && bx0 >= 0 && by0 >= 0 && bx1 <= fw && by1 <= fh && bw >= 1 && bh >= 1 && fw >= 2;
+    int dw = p.out_w, dh = p.out_h, top = 0, left = 0;
+    if (ok && p.mode == NKBK_MODE_LETTERBOX)
+        ok = letterbox_geometry(bh, bw, p.max_size, p.out_h, p.out_w, dh, dw, top, left);
+
+    const int64_t plane = (int64_t)p.out_h * p.out_w;
+    OutT* const out_crop = reinterpret_cast<OutT*>(p.out) + (int64_t)crop * 3 * plane;
+    uint32_t wmask = 0;  // columns this lane writes at all
+#pragma unroll
+    for (int j = 0; j < JMAX; ++j) wmask |= uint32_t(ox0 + 32 * j < p.out_w) << j;
+
+    if (!ok) {
+        // empty / out-of-frame box: emit the normalised pad value, count it once per crop
+        if (p.bad_count != nullptr && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0)
+            atomicAdd(p.bad_count, 1);
+        for (int yy = 0; yy < nrows; ++yy) {
+            OutT* o = out_crop + (int64_t)(y_begin + yy) * p.out_w + ox0;
+#pragma unroll
+            for (int j = 0; j < JMAX; ++j)
+                if (wmask >> j & 1) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) store_out<OutT>(o + c * plane + 32 * j, p.padf[c]);
+                    if (WRITE_U8) {
+                        uint8_t* u = p.out_u8 + (((int64_t)crop * p.out_h + y_begin + yy) * p.out_w + ox0 + 32 * j) * 3;
+                        u[0] = (uint8_t)p.padu[0]; u[1] = (uint8_t)p.padu[1]; u[2] = (uint8_t)p.padu[2];
+                    }
+                }
+        }
+        return;
+    }
+
+    // ---- horizontal tables, one entry per (lane, j), kept in registers ----
+    uint32_t xo[JMAX], cf[JMAX];
+    uint32_t vmask = 0;  // columns that receive resized pixels (the rest of wmask is letterbox border)
+    {
+        const double sxs = axis_scale(dw, bw);
+#pragma unroll
+        for (int j = 0; j < JMAX; ++j) {
+            const int ox = ox0 + 32 * j;
+            const int dx = ox - left;
+            const bool v = ox < p.out_w && dx >= 0 && dx < dw;
+            int s = 0, c0 = 0, c1 = 0;
+            if (v) axis_coef(dx, sxs, bw, true, s, c0, c1);
+            int px = bx0 + s;
+            uint32_t c = uint32_t(c0) | (uint32_t(c1) << 16);
+            if (px + 1 >= fw) {  // window would leave the frame row: shift it left, weight moves to tap 1
+                px -= 1;
+                c = uint32_t(c0) << 16;
+            }
+            if (!v) { px = 0; c = 0u; }
+            xo[j] = uint32_t(px) * 3u;
+            cf[j] = c;
+            vmask |= uint32_t(v) << j;
+        }
+    }
+
+    // ---- vertical tables: lane l holds row y_begin + l of this band ----
+    int my_r0 = -1, my_r1 = -1;
+    uint32_t my_b0 = 0, my_b1 = 0;
+    if (lane < nrows) {
+        const int dy = y_begin + lane - top;
+        if (dy >= 0 && dy < dh) {
+            int s, c0, c1;
+            axis_coef(dy, axis_scale(dh, bh), bh, false, s, c0, c1);
+            my_r0 = min(max(s, 0), bh - 1);
+            my_r1 = min(max(s + 1, 0), bh - 1);
+            my_b0 = uint32_t(c0) << 16;  // pre-shifted: umulhi(b << 16, h) == (b * h) >> 16
+            my_b1 = uint32_t(c1) << 16;
+        }
+    }
+
+    const uint8_t* const src0 = p.frames + f_off + (int64_t)by0 * pitch;
+    const uint32_t sel0 = p.sel[0], sel1 = p.sel[1], sel2 = p.sel[2];
+    const float m0 = p.m[0], m1 = p.m[1], m2 = p.m[2];
+    const float d0 = p.d[0], d1 = p.d[1], d2 = p.d[2];
+
+    uint32_t Ha[JMAX][3], Hb[JMAX][3];
+    int ia = -1, ib = -1;
+#pragma unroll
+    for (int j = 0; j < JMAX; ++j)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) Ha[j][c] = Hb[j][c] = 0u;
+
+    for (int yy = 0; yy < nrows; ++yy) {
+        const int r0 = __shfl_sync(0xffffffffu, my_r0, yy);
+        const int r1 = __shfl_sync(0xffffffffu, my_r1, yy);
+        const uint32_t b0 = __shfl_sync(0xffffffffu, my_b0, yy);
+        const uint32_t b1 = __shfl_sync(0xffffffffu, my_b1, yy);
+        const int y = y_begin + yy;
+        OutT* o = out_crop + (int64_t)y * p.out_w + ox0;
+        uint8_t* u = WRITE_U8 ? p.out_u8 + (((int64_t)crop * p.out_h + y) * p.out_w + ox0) * 3 : nullptr;
+
+        if (r0 < 0) {  // letterbox border row
+#pragma unroll
+            for (int j = 0; j < JMAX; ++j)
+                if (wmask >> j & 1) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) store_out<OutT>(o + c * plane + 32 * j, p.padf[c]);
+                    if (WRITE_U8) {
+                        u[96 * j + 0] = (uint8_t)p.padu[0]; u[96 * j + 1] = (uint8_t)p.padu[1];
+                        u[96 * j + 2] = (uint8_t)p.padu[2];
+                    }
+                }
+            continue;
+        }
+
+        if (r0 != ia) {
+            if (r0 == ib) {
+#pragma unroll
+                for (int j = 0; j < JMAX; ++j)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) Ha[j][c] = Hb[j][c];
+            } else {
+                hrow<JMAX>(Ha, src0 + (int64_t)r0 * pitch, xo, cf, sel0, sel1, sel2);
+            }
+            ia = r0;
+        }
+        if (r1 != ib) {
+            if (r1 == ia) {
+#pragma unroll
+                for (int j = 0; j < JMAX; ++j)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) Hb[j][c] = Ha[j][c];
+            } else {
+                hrow<JMAX>(Hb, src0 + (int64_t)r1 * pitch, xo, cf, sel0, sel1, sel2);
+            }
+            ib = r1;
+        }
+
+#pragma unroll
+        for (int j = 0; j < JMAX; ++j) {
+            if (!(wmask >> j & 1)) continue;
+            const bool v = vmask >> j & 1;
+            uint32_t px[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                uint32_t t = __umulhi(b0, Ha[j][c]) + 2u;
+                t = __umulhi(b1, Hb[j][c]) + t;
+                px[c] = v ? (t >> 2) : p.padu[c];
+            }
+            store_out<OutT>(o + 32 * j, __fmul_rn(__fsub_rn((float)px[0], m0), d0));
+            store_out<OutT>(o + plane + 32 * j, __fmul_rn(__fsub_rn((float)px[1], m1), d1));
+            store_out<OutT>(o + 2 * plane + 32 * j, __fmul_rn(__fsub_rn((float)px[2], m2), d2));
+            if (WRITE_U8) {
+                u[96 * j + 0] = (uint8_t)px[0]; u[96 * j + 1] = (uint8_t)px[1]; u[96 * j + 2] = (uint8_t)px[2];
+            }
+        }
+    }
+}
+
+template <int JMAX, typename OutT>
+static void launch_k1(const K1Params& p, dim3 grid, cudaStream_t st) {
+    if (p.out_u8 != nullptr)
+        k1_crop_resize_normalize<JMAX, OutT, true><<<grid, K1_WARPS * 32, 0, st>>>(p);
+    else
+        k1_crop_resize_normalize<JMAX, OutT, false><<<grid, K1_WARPS * 32, 0, st>>>(p);
+}
+
+}  // namespace nkbk
+
+using namespace nkbk;
+
+extern "C" int nkbk_preprocess_crops(const void* frames_base, const int64_t* frame_desc, int n_frames,
+                                     const int32_t* boxes, const int32_t* frame_idx, int n, int mode, int out_h,
+                                     int out_w, int max_size, const uint8_t* pad_value, const float* mean255,
+                                     const float* denom, int channel_swap, void* out, int out_dtype, uint8_t* out_u8,
+                                     int32_t* bad_count, void* stream) {
+    NKBK_CHECK_ARG(n >= 0, "nkbk_preprocess_crops: n=%d < 0", n);
+    if (n == 0) return NKBK_OK;
+    NKBK_CHECK_ARG(frames_base && frame_desc && boxes && frame_idx && out, "nkbk_preprocess_crops: NULL pointer");
+    NKBK_CHECK_ARG(mean255 && denom, "nkbk_preprocess_crops: NULL mean255/denom");
+    NKBK_CHECK_ARG(n_frames >= 1, "nkbk_preprocess_crops: n_frames=%d", n_frames);
+    NKBK_CHECK_ARG(mode == NKBK_MODE_STRETCH || mode == NKBK_MODE_LETTERBOX, "nkbk_preprocess_crops: mode=%d", mode);
+    NKBK_CHECK_ARG(out_dtype == NKBK_F32 || out_dtype == NKBK_BF16, "nkbk_preprocess_crops: out_dtype=%d", out_dtype);
+    if (out_h < 1 || out_w < 1 || out_h > 16384 || out_w > 16384) {
+        set_error("nkbk_preprocess_crops: output %dx%d outside [1,16384]", out_h, out_w);
+        return NKBK_E_SHAPE;
+    }
+    if (mode == NKBK_MODE_LETTERBOX && (max_size < 1 || max_size > out_h || max_size > out_w)) {
+        set_error("nkbk_preprocess_crops: LongestMaxSize(%d) does not fit PadIfNeeded(%d,%d)", max_size, out_h, out_w);
+        return NKBK_E_UNSUPPORTED;
+    }
+
+    K1Params p;
+    p.frames = static_cast<const uint8_t*>(frames_base);
+    p.frame_desc = frame_desc;
+    p.boxes = boxes;
+    p.frame_idx = frame_idx;
+    p.n = n; p.n_frames = n_frames; p.mode = mode; p.out_h = out_h; p.out_w = out_w; p.max_size = max_size;
+    static const uint32_t kSel[3] = {0x0030u, 0x0041u, 0x0052u};  // (tap0, tap1) byte pairs of R, G, B
+    for (int c = 0; c < 3; ++c) {
+        p.m[c] = mean255[c];
+        p.d[c] = denom[c];
+        p.padu[c] = pad_value ? pad_value[c] : 0u;
+        volatile float t = (float)p.padu[c] - mean255[c];  // two rounded ops, like the kernel
+        p.padf[c] = t * denom[c];
+        p.sel[c] = kSel[channel_swap ? 2 - c : c];
+    }
+    p.out = out; p.out_u8 = out_u8; p.bad_count = bad_count;
+
+    // rows per warp: split the height into blocks of <= 64 rows, 4 warps each
+    const int nby = (out_h + 63) / 64;
+    p.rows_per_warp = (out_h + nby * K1_WARPS - 1) / (nby * K1_WARPS);
+    // column tile: 32*JMAX columns, JMAX in {4,7,8}; least padded wins, ties -> wider
+    int best_j = 8, best_cost = 1 << 30;
+    const int cands[3] = {8, 7, 4};
+    for (int i = 0; i < 3; ++i) {
+        const int w = 32 * cands[i];
+        const int cost = (out_w + w - 1) / w * w;
+        if (cost < best_cost) { best_cost = cost; best_j = cands[i]; }
+    }
+    const int ntx = (out_w + 32 * best_j - 1) / (32 * best_j);
+    if (nby > 65535 || ntx > 65535) {
+        set_error("nkbk_preprocess_crops: output %dx%d too large", out_h, out_w);
+        return NKBK_E_SHAPE;
+    }
+    dim3 grid((unsigned)n, (unsigned)nby, (unsigned)ntx);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool f32 = out_dtype == NKBK_F32;
+    switch (best_j) {
+        case 4: f32 ? launch_k1<4, float>(p, grid, st) : launch_k1<4, __nv_bfloat16>(p, grid, st); break;
+        case 7: f32 ? launch_k1<7, float>(p, grid, st) : launch_k1<7, __nv_bfloat16>(p, grid, st); break;
+        default: f32 ? launch_k1<8, float>(p, grid, st) : launch_k1<8, __nv_bfloat16>(p, grid, st); break;
+    }
+    NKBK_CHECK_LAUNCH("k1_crop_resize_normalize");
+    return NKBK_OK;
+}
+
+extern "C" int nkbk_debug_axis_table(int dsize, int ssize, int horizontal, int32_t* src_index, int32_t* coef0,
+                                     int32_t* coef1) {
+    NKBK_CHECK_ARG(dsize >= 1 && ssize >= 1 && src_index && coef0 && coef1, "nkbk_debug_axis_table: bad argument");
+    const double sc = axis_scale(dsize, ssize);
+    for (int d = 0; d < dsize; ++d) {
+        int s, c0, c1;
+        axis_coef(d, sc, ssize, horizontal != 0, s, c0, c1);
+        src_index[d] = s; coef0[d] = c0; coef1[d] = c1;
+    }
+    return NKBK_OK;
+}
+
+extern "C" int nkbk_debug_letterbox(int h, int w, int max_size, int out_h, int out_w, int32_t* out4) {
+    NKBK_CHECK_ARG(h >= 1 && w >= 1 && max_size >= 1 && out4, "nkbk_debug_letterbox: bad argument");
+    int nh, nw, top = 0, left = 0;
+    if (!letterbox_geometry(h, w, max_size, out_h, out_w, nh, nw, top, left)) {
+        set_error("nkbk_debug_letterbox: %dx%d at max_size %d does not fit %dx%d", h, w, max_size, out_h, out_w);
+        return NKBK_E_UNSUPPORTED;
+    }
+    out4[0] = nh; out4[1] = nw; out4[2] = top; out4[3] = left;
+    return NKBK_OK;
+}

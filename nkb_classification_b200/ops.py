@@ -1,0 +1,248 @@
+"""Thin torch-tensor wrappers over the C ABI (include/nkbk.h).
+
+PyTorch is plumbing here: it owns device memory and streams; every byte of
+arithmetic on the hot path happens inside libnkbk.so.  All functions require
+CUDA tensors and raise otherwise -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_float, c_int32, c_uint8
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, LOSS_CE, LOSS_FOCAL, check, lib
+from .transforms import PreprocessPlan
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _need_cuda(name: str, t: torch.Tensor):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: nkb_classification_b200 has no CPU path")
+
+
+def _seg_array(seg_offsets: Sequence[int]):
+    seg = [int(x) for x in seg_offsets]
+    return (c_int32 * len(seg))(*seg), len(seg) - 1, seg[-1]
+
+
+# --------------------------------------------------------------------------
+# K1
+# --------------------------------------------------------------------------
+def frame_descriptors(frames: torch.Tensor) -> torch.Tensor:
+    """int64 [F,4] = {byte offset, height, width, pitch} for a contiguous uint8 [F,H,W,3] batch."""
+    F, H, W, C = frames.shape
+    assert C == 3
+    d = torch.empty((F, 4), dtype=torch.int64)
+    d[:, 0] = torch.arange(F, dtype=torch.int64) * (H * W * 3)
+    d[:, 1] = H
+    d[:, 2] = W
+    d[:, 3] = W * 3
+    return d.to(frames.device, non_blocking=True)
+
+
+def preprocess_crops(
+    frames: torch.Tensor,              # uint8 CUDA [F,H,W,3] contiguous, or a flat uint8 buffer with `frame_desc`
+    boxes: torch.Tensor,               # int32 CUDA [n,4]  x0,y0,x1,y1
+    frame_idx: torch.Tensor,           # int32 CUDA [n]
+    plan: PreprocessPlan,
+    out_dtype: torch.dtype = torch.float32,
+    out: Optional[torch.Tensor] = None,
+    out_u8: Optional[torch.Tensor] = None,
+    frame_desc: Optional[torch.Tensor] = None,
+    bad_count: Optional[torch.Tensor] = None,
+) -> torch.Tensor:
+    """One K1 launch: [n,3,out_h,out_w] normalised crops (see nkbk_preprocess_crops)."""
+    _need_cuda("frames", frames)
+    _need_cuda("boxes", boxes)
+    _need_cuda("frame_idx", frame_idx)
+    if frames.dtype != torch.uint8 or not frames.is_contiguous():
+        raise ValueError("frames must be a contiguous uint8 tensor")
+    if boxes.dtype != torch.int32 or frame_idx.dtype != torch.int32:
+        raise ValueError("boxes and frame_idx must be int32")
+    if not boxes.is_contiguous() or not frame_idx.is_contiguous():
+        raise ValueError("boxes and frame_idx must be contiguous")
+    n = int(frame_idx.numel())
+    if boxes.numel() != 4 * n:
+        raise ValueError(f"boxes has {boxes.numel()} elements for {n} crops")
+    if frame_desc is None:
+        if frames.dim() != 4 or frames.shape[-1] != 3:
+            raise ValueError("frames must be [F,H,W,3] when frame_desc is not given")
+        if frames.shape[2] < 2:
+            raise ValueError("frames narrower than 2 pixels are not supported")
+        frame_desc = frame_descriptors(frames)
+    _need_cuda("frame_desc", frame_desc)
+    n_frames = int(frame_desc.shape[0])
+    if out_dtype not in _DT:
+        raise ValueError(f"out_dtype {out_dtype} not supported (float32 | bfloat16)")
+    if out is None:
+        out = torch.empty((n, 3, plan.out_h, plan.out_w), dtype=out_dtype, device=frames.device)
+    else:
+        if out.dtype != out_dtype or not out.is_contiguous() or out.numel() != n * 3 * plan.out_h * plan.out_w:
+            raise ValueError("out has the wrong dtype / shape / layout")
+    if out_u8 is not None:
+        if out_u8.dtype != torch.uint8 or not out_u8.is_contiguous() or out_u8.numel() != n * 3 * plan.out_h * plan.out_w:
+            raise ValueError("out_u8 must be contiguous uint8 [n,out_h,out_w,3]")
+    pad = (c_uint8 * 3)(*plan.pad_value)
+    m = (c_float * 3)(*plan.mean255)
+    d = (c_float * 3)(*plan.denom)
+    rc = lib().nkbk_preprocess_crops(
+        _ptr(frames), _ptr(frame_desc), n_frames, _ptr(boxes), _ptr(frame_idx), n, plan.mode, plan.out_h, plan.out_w,
+        plan.max_size, pad, m, d, int(plan.channel_swap), _ptr(out), _DT[out_dtype], _ptr(out_u8), _ptr(bad_count),
+        _stream(frames.device),
+    )
+    check(rc)
+    return out
+
+
+def debug_axis_table(dsize: int, ssize: int, horizontal: bool):
+    """Host-only: the coefficient table the kernel prologue computes (no GPU needed)."""
+    s = np.empty(dsize, dtype=np.int32)
+    c0 = np.empty(dsize, dtype=np.int32)
+    c1 = np.empty(dsize, dtype=np.int32)
+    check(lib().nkbk_debug_axis_table(dsize, ssize, int(horizontal), s.ctypes.data, c0.ctypes.data, c1.ctypes.data))
+    return s, c0, c1
+
+
+def debug_letterbox(h: int, w: int, max_size: int, out_h: int, out_w: int):
+    o = np.empty(4, dtype=np.int32)
+    check(lib().nkbk_debug_letterbox(h, w, max_size, out_h, out_w, o.ctypes.data))
+    return tuple(int(x) for x in o)
+
+
+# --------------------------------------------------------------------------
+# K2
+# --------------------------------------------------------------------------
+def heads_reduce_buf_len(D: int, NC: int, T: int) -> int:
+    return int(lib().nkbk_heads_reduce_buf_len(D, NC, T))
+
+
+class HeadsBuffers:
+    """Caller-owned scratch for K2, reused across steps (allocation-free steady state)."""
+
+    def __init__(self, B: int, D: int, seg_offsets: Sequence[int], device, want_logits=True, want_probs=True,
+                 want_grads=True):
+        self.B, self.D = B, D
+        self.seg = [int(x) for x in seg_offsets]
+        self.T, self.NC = len(self.seg) - 1, self.seg[-1]
+        f32 = dict(dtype=torch.float32, device=device)
+        self.logits = torch.empty((B, self.NC), **f32) if want_logits else None
+        self.probs = torch.empty((B, self.NC), **f32) if want_probs else None
+        self.dlogits = torch.empty((B, self.NC), **f32) if want_grads else None
+        self.reduce_buf = torch.empty(heads_reduce_buf_len(D, self.NC, self.T), **f32)
+        ws = int(lib().nkbk_heads_workspace_bytes(B, D, self.NC, self.T))
+        self.workspace = torch.empty(max(ws, 16), dtype=torch.uint8, device=device)
+        self.loss = torch.empty(self.T + 1, **f32)
+
+    # views into the reduce buffer
+    def dW(self) -> torch.Tensor:
+        return self.reduce_buf[: self.NC * self.D].view(self.NC, self.D)
+
+    def db(self) -> torch.Tensor:
+        return self.reduce_buf[self.NC * self.D : self.NC * self.D + self.NC]
+
+    def loss_sum(self) -> torch.Tensor:
+        o = self.NC * self.D + self.NC
+        return self.reduce_buf[o : o + self.T]
+
+    def denom(self) -> torch.Tensor:
+        o = self.NC * self.D + self.NC + self.T
+        return self.reduce_buf[o : o + self.T]
+
+
+def heads_fwd_loss_bwd(
+    emb: torch.Tensor, W_cat: torch.Tensor, b_cat: torch.Tensor, labels: Optional[torch.Tensor], bufs: HeadsBuffers,
+    loss_kind: int = LOSS_FOCAL, gamma: float = 2.0, class_weight: Optional[torch.Tensor] = None,
+    ignore_index: int = -100,
+) -> HeadsBuffers:
+    """Forward + loss terms + dlogits + unnormalised dW/db into ``bufs`` (see nkbk_heads_fwd_loss_bwd)."""
+    _need_cuda("emb", emb)
+    _need_cuda("W_cat", W_cat)
+    if emb.dtype not in _DT:
+        raise ValueError(f"emb dtype {emb.dtype} not supported (float32 | bfloat16)")
+    if not emb.is_contiguous() or emb.dim() != 2:
+        raise ValueError("emb must be contiguous [B,D]")
+    B, D = emb.shape
+    if (B, D) != (bufs.B, bufs.D):
+        raise ValueError(f"emb {tuple(emb.shape)} does not match buffers ({bufs.B},{bufs.D})")
+    if W_cat.dtype != torch.float32 or b_cat.dtype != torch.float32:
+        raise ValueError("W_cat / b_cat must be float32")
+    if tuple(W_cat.shape) != (bufs.NC, D) or b_cat.numel() != bufs.NC or not W_cat.is_contiguous():
+        raise ValueError("W_cat must be contiguous [NC,D] and b_cat [NC]")
+    if labels is not None:
+        _need_cuda("labels", labels)
+        if labels.dtype != torch.int64 or not labels.is_contiguous() or labels.numel() != B * bufs.T:
+            raise ValueError("labels must be contiguous int64 [B,T]")
+    if class_weight is not None:
+        if class_weight.dtype != torch.float32 or class_weight.numel() != bufs.NC or not class_weight.is_cuda:
+            raise ValueError("class_weight must be CUDA float32 [NC]")
+    seg, T, _ = _seg_array(bufs.seg)
+    rc = lib().nkbk_heads_fwd_loss_bwd(
+        _ptr(emb), _DT[emb.dtype], B, D, _ptr(W_cat), _ptr(b_cat), seg, T, _ptr(labels), int(loss_kind), float(gamma),
+        _ptr(class_weight), int(ignore_index), _ptr(bufs.logits), _ptr(bufs.probs), _ptr(bufs.dlogits),
+        _ptr(bufs.reduce_buf), _ptr(bufs.workspace), bufs.workspace.numel(), _stream(emb.device),
+    )
+    check(rc)
+    return bufs
+
+
+def heads_finalize(bufs: HeadsBuffers) -> torch.Tensor:
+    """reduce_buf sums -> mean gradients in place; returns fp32 [T+1] = per-task losses + total."""
+    seg, T, _ = _seg_array(bufs.seg)
+    check(lib().nkbk_heads_finalize(_ptr(bufs.reduce_buf), bufs.D, seg, T, _ptr(bufs.loss),
+                                    _stream(bufs.reduce_buf.device)))
+    return bufs.loss
+
+
+def heads_demb(bufs: HeadsBuffers, W_cat: torch.Tensor, out_dtype: torch.dtype = torch.float32,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if bufs.dlogits is None:
+        raise ValueError("buffers were created without gradients")
+    if out is None:
+        out = torch.empty((bufs.B, bufs.D), dtype=out_dtype, device=W_cat.device)
+    seg, T, _ = _seg_array(bufs.seg)
+    check(lib().nkbk_heads_demb(_ptr(bufs.dlogits), _ptr(bufs.reduce_buf), _ptr(W_cat), seg, T, bufs.B, bufs.D,
+                                _ptr(out), _DT[out_dtype], _stream(W_cat.device)))
+    return out
+
+
+# --------------------------------------------------------------------------
+# K3
+# --------------------------------------------------------------------------
+def confusion_len(seg_offsets: Sequence[int]) -> int:
+    return int(sum((b - a) ** 2 for a, b in zip(seg_offsets[:-1], seg_offsets[1:])))
+
+
+def argmax_confusion(logits: torch.Tensor, seg_offsets: Sequence[int], labels: Optional[torch.Tensor] = None,
+                     cm: Optional[torch.Tensor] = None, out_pred: Optional[torch.Tensor] = None,
+                     want_pred: bool = True) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """Per-task argmax (+ accumulate int64 confusion counts into ``cm``)."""
+    _need_cuda("logits", logits)
+    if logits.dtype not in _DT or logits.dim() != 2 or logits.stride(1) != 1:
+        raise ValueError("logits must be [B,ld] float32 | bfloat16 with unit inner stride")
+    B, ld = logits.shape[0], logits.stride(0) if logits.shape[0] > 1 else logits.shape[1]
+    seg, T, NC = _seg_array(seg_offsets)
+    if labels is not None:
+        _need_cuda("labels", labels)
+        if labels.dtype != torch.int64 or not labels.is_contiguous() or labels.numel() != B * T:
+            raise ValueError("labels must be contiguous int64 [B,T]")
+    if cm is not None:
+        if cm.dtype != torch.int64 or not cm.is_cuda or cm.numel() != confusion_len(seg_offsets):
+            raise ValueError("cm must be CUDA int64 with sum(C_t^2) entries")
+    if want_pred and out_pred is None:
+        out_pred = torch.empty((B, T), dtype=torch.int32, device=logits.device)
+    check(lib().nkbk_argmax_confusion(_ptr(logits), _DT[logits.dtype], B, ld, seg, T, _ptr(labels), _ptr(out_pred),
+                                      _ptr(cm), _stream(logits.device)))
+    return out_pred, cm
