@@ -128,8 +128,12 @@ int nkbk_heads_fwd_loss_bwd(const void* emb, int emb_dtype, int B, int D, const 
                             void* stream);
 
 /* In place: dW, db <- sums / denom[task]; out_loss (fp32 [T+1]) <- per-task mean
- * losses and their unweighted sum (losses.py:140-147).  denom == 0 -> 0. */
-int nkbk_heads_finalize(float* reduce_buf, int D, const int32_t* seg_offsets, int T, float* out_loss, void* stream);
+ * losses and their unweighted sum (losses.py:140-147).  denom == 0 -> 0.
+ * Optionally folds the (all-reduced) per-step confusion counts into the epoch
+ * totals in the same launch: cm_total[i] += cm_step[i]; cm_step[i] = 0
+ * (both NULL / n_cm = 0 to skip). */
+int nkbk_heads_finalize(float* reduce_buf, int D, const int32_t* seg_offsets, int T, float* out_loss,
+                        int64_t* cm_total, int64_t* cm_step, int64_t n_cm, void* stream);
 
 /* d(loss)/d(emb) [B][D] (emb_dtype) from dlogits and the (all-reduced,
  * not yet finalised or finalised -- denom is untouched by finalize) reduce_buf. */

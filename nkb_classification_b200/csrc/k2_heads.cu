@@ -289,7 +289,8 @@ __global__ void __launch_bounds__(256) k2_heads_reduce(const float* __restrict__
 }
 
 __global__ void __launch_bounds__(256) k2_heads_finalize(float* __restrict__ reduce_buf, int NC, int D, const K2Seg seg,
-                                                         float* __restrict__ out_loss) {
+                                                         float* __restrict__ out_loss, int64_t* __restrict__ cm_total,
+                                                         int64_t* __restrict__ cm_step, int64_t n_cm) {
     const int T = seg.T;
     const int64_t nW = (int64_t)NC * D;
     const float* loss_sum = reduce_buf + nW + NC;
@@ -300,6 +301,10 @@ __global__ void __launch_bounds__(256) k2_heads_finalize(float* __restrict__ red
         while (t + 1 < T && c >= seg.off[t + 1]) ++t;
         const float dn = denom[t];
         reduce_buf[i] = dn > 0.f ? __fdiv_rn(reduce_buf[i], dn) : 0.f;
+    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cm; i += (int64_t)gridDim.x * blockDim.x) {
+        cm_total[i] += cm_step[i];
+        cm_step[i] = 0;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0 && out_loss != nullptr) {
         float total = 0.f;
@@ -460,7 +465,7 @@ extern "C" int nkbk_heads_fwd_loss_bwd(const void* emb, int emb_dtype, int B, in
 }
 
 extern "C" int nkbk_heads_finalize(float* reduce_buf, int D, const int32_t* seg_offsets, int T, float* out_loss,
-                                   void* stream) {
+                                   int64_t* cm_total, int64_t* cm_step, int64_t n_cm, void* stream) {
     K2Seg seg;
     int rc = fill_seg(seg, seg_offsets, T, "nkbk_heads_finalize");
     if (rc) return rc;
@@ -469,7 +474,9 @@ extern "C" int nkbk_heads_finalize(float* reduce_buf, int D, const int32_t* seg_
     const int64_t n = (int64_t)NC * D + NC;
     int blocks = (int)((n + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    k2_heads_finalize<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(reduce_buf, NC, D, seg, out_loss);
+    NKBK_CHECK_ARG(n_cm >= 0 && (n_cm == 0 || (cm_total && cm_step)), "nkbk_heads_finalize: bad confusion buffers");
+    k2_heads_finalize<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(reduce_buf, NC, D, seg, out_loss, cm_total,
+                                                                             cm_step, n_cm);
     NKBK_CHECK_LAUNCH("k2_heads_finalize");
     return NKBK_OK;
 }

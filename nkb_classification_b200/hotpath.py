@@ -1,0 +1,105 @@
+"""The fused hot path as one object: K1 -> (backbone, external) -> K2 -> K3 -> K4.
+
+This is the call a user (or engine.py's train/val loop) makes per batch; it
+owns the reusable device buffers so a steady-state step allocates nothing.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import LOSS_CE, LOSS_FOCAL
+from .parallel import Communicator
+from .transforms import PreprocessPlan
+
+LOSS_KINDS = {"CrossEntropyLoss": LOSS_CE, "FocalLoss": LOSS_FOCAL}
+
+
+class HotPath:
+    def __init__(self, plan: PreprocessPlan, classes_per_task: Sequence[int], emb_dim: int, loss_type: str = "FocalLoss",
+                 gamma: float = 2.0, class_weight: Optional[torch.Tensor] = None, ignore_index: int = -100,
+                 device="cuda:0", comm: Optional[Communicator] = None, out_dtype: torch.dtype = torch.float32):
+        if loss_type not in LOSS_KINDS:
+            raise NotImplementedError(f"Unknown loss type in config: {loss_type}")  # losses.py:171
+        self.plan = plan
+        self.device = torch.device(device)
+        self.seg = np.concatenate([[0], np.cumsum(list(classes_per_task))]).astype(int).tolist()
+        self.T, self.NC, self.D = len(classes_per_task), self.seg[-1], int(emb_dim)
+        self.loss_kind, self.gamma, self.ignore_index = LOSS_KINDS[loss_type], float(gamma), int(ignore_index)
+        self.class_weight = None if class_weight is None else class_weight.to(self.device, torch.float32).contiguous()
+        self.comm = comm or Communicator()
+        self.out_dtype = out_dtype
+        self.cm = torch.zeros(ops.confusion_len(self.seg), dtype=torch.int64, device=self.device)       # epoch totals
+        self.cm_step = torch.zeros_like(self.cm)   # this step's counts: K3 -> all-reduce -> folded into cm by finalize
+        self._bufs: Dict[tuple, ops.HeadsBuffers] = {}
+        self._images: Dict[int, torch.Tensor] = {}
+        self._pred: Dict[int, torch.Tensor] = {}
+        self._desc = None
+
+    # ---- K1 ----
+    def preprocess(self, frames: torch.Tensor, boxes: torch.Tensor, frame_idx: torch.Tensor,
+                   frame_desc: Optional[torch.Tensor] = None) -> torch.Tensor:
+        n = int(frame_idx.numel())
+        out = self._images.get(n)
+        if out is None:
+            out = torch.empty((n, 3, self.plan.out_h, self.plan.out_w), dtype=self.out_dtype, device=self.device)
+            self._images = {n: out}
+        if frame_desc is None:
+            key = (tuple(frames.shape), frames.data_ptr())
+            if self._desc is None or self._desc[0] != key[0]:
+                self._desc = (key[0], ops.frame_descriptors(frames))
+            frame_desc = self._desc[1]
+        return ops.preprocess_crops(frames, boxes, frame_idx, self.plan, self.out_dtype, out=out, frame_desc=frame_desc)
+
+    # ---- K2 + K3 + K4 ----
+    def _buffers(self, B: int, train: bool, want_probs: bool) -> ops.HeadsBuffers:
+        key = (B, train, want_probs)
+        b = self._bufs.get(key)
+        if b is None:
+            b = ops.HeadsBuffers(B, self.D, self.seg, self.device, want_logits=True, want_probs=want_probs,
+                                 want_grads=train)
+            self._bufs[key] = b
+        return b
+
+    def heads_step(self, emb: torch.Tensor, W_cat: torch.Tensor, b_cat: torch.Tensor,
+                   labels: Optional[torch.Tensor], train: bool = True, want_probs: bool = False,
+                   want_pred: bool = True, update_confusion: bool = True):
+        """One step of K2 + K3 + K4.  Returns the HeadsBuffers holding (after finalize) the global-mean
+        dW/db, logits, probs, ``.loss`` [T+1] and ``.pred`` [B,T]; the epoch confusion totals are in ``self.cm``
+        (already summed over ranks)."""
+        B = emb.shape[0]
+        bufs = self._buffers(B, train, want_probs)
+        ops.heads_fwd_loss_bwd(emb, W_cat, b_cat, labels, bufs, self.loss_kind, self.gamma, self.class_weight,
+                               self.ignore_index)
+        do_cm = update_confusion and labels is not None
+        pred = None
+        if want_pred or do_cm:
+            pred = self._pred.get(B)
+            if pred is None:
+                pred = torch.empty((B, self.T), dtype=torch.int32, device=self.device)
+                self._pred = {B: pred}
+            ops.argmax_confusion(bufs.logits, self.seg, labels if do_cm else None, self.cm_step if do_cm else None,
+                                 out_pred=pred)
+        self.comm.allreduce_heads(bufs.reduce_buf, self.cm_step if do_cm else None)
+        if do_cm:
+            ops.heads_finalize(bufs, self.cm, self.cm_step)
+        else:
+            ops.heads_finalize(bufs)
+        bufs.pred = pred
+        return bufs
+
+    def reset_confusion(self):
+        self.cm.zero_()
+
+    def confusion_matrices(self):
+        """Per-task int64 [C_t, C_t] numpy matrices (one D2H)."""
+        flat = self.cm.cpu().numpy()
+        out, off = [], 0
+        for t in range(self.T):
+            C = self.seg[t + 1] - self.seg[t]
+            out.append(flat[off: off + C * C].reshape(C, C).copy())
+            off += C * C
+        return out

@@ -198,11 +198,19 @@ def heads_fwd_loss_bwd(
     return bufs
 
 
-def heads_finalize(bufs: HeadsBuffers) -> torch.Tensor:
-    """reduce_buf sums -> mean gradients in place; returns fp32 [T+1] = per-task losses + total."""
+def heads_finalize(bufs: HeadsBuffers, cm_total: Optional[torch.Tensor] = None,
+                   cm_step: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """reduce_buf sums -> mean gradients in place; returns fp32 [T+1] = per-task losses + total.
+    With ``cm_total`` / ``cm_step``: cm_total += cm_step; cm_step = 0 in the same launch."""
     seg, T, _ = _seg_array(bufs.seg)
-    check(lib().nkbk_heads_finalize(_ptr(bufs.reduce_buf), bufs.D, seg, T, _ptr(bufs.loss),
-                                    _stream(bufs.reduce_buf.device)))
+    n_cm = 0
+    if cm_total is not None or cm_step is not None:
+        if cm_total is None or cm_step is None or cm_total.numel() != cm_step.numel() \
+                or cm_total.dtype != torch.int64 or cm_step.dtype != torch.int64:
+            raise ValueError("cm_total / cm_step must both be int64 of equal length")
+        n_cm = cm_total.numel()
+    check(lib().nkbk_heads_finalize(_ptr(bufs.reduce_buf), bufs.D, seg, T, _ptr(bufs.loss), _ptr(cm_total),
+                                    _ptr(cm_step), n_cm, _stream(bufs.reduce_buf.device)))
     return bufs.loss
 
 

@@ -1,0 +1,216 @@
+"""K1 parity on the GPU: CUDA (through the C ABI) vs the CPU oracle.
+uint8 pixels bit-exact, fp32 tensors bit-exact (0 ulp; the bar is <= 1 ulp),
+bf16 = RNE of the fp32 value."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import preprocess as opre
+from oracle.cref import preprocess_batch_c
+
+pytestmark = pytest.mark.gpu
+
+MEAN, STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+
+
+def make_plan(T, mode="stretch", out_h=224, out_w=224, max_size=None, pad=0, swap=False):
+    if mode == "stretch":
+        ops = [T.Resize(out_h, out_w)]
+    else:
+        ops = [T.LongestMaxSize(max_size or min(out_h, out_w)), T.PadIfNeeded(out_h, out_w, border_mode=0, value=pad)]
+    return T.compile_pipeline(ops + [T.Normalize(MEAN, STD), T.ToTensorV2()], channel_swap=swap)
+
+
+def oracle_plan(plan):
+    return opre.Plan(mode=plan.mode, out_h=plan.out_h, out_w=plan.out_w, max_size=plan.max_size,
+                     pad_value=plan.pad_value, mean=MEAN, std=STD, channel_swap=plan.channel_swap)
+
+
+def run_k1(dev, frames, boxes, fidx, plan, dtype=torch.float32, want_u8=True, **kw):
+    from nkb_classification_b200 import ops
+    fr = torch.from_numpy(frames).to(dev) if isinstance(frames, np.ndarray) else frames
+    bx = torch.from_numpy(np.ascontiguousarray(boxes, dtype=np.int32)).to(dev)
+    fi = torch.from_numpy(np.ascontiguousarray(fidx, dtype=np.int32)).to(dev)
+    n = len(fidx)
+    u8 = torch.full((n, plan.out_h, plan.out_w, 3), 99, dtype=torch.uint8, device=dev) if want_u8 else None
+    out = ops.preprocess_crops(fr, bx, fi, plan, out_dtype=dtype, out_u8=u8, **kw)
+    torch.cuda.synchronize()
+    return out, u8
+
+
+def assert_same_f32(got: torch.Tensor, exp: np.ndarray):
+    g = got.cpu().numpy()
+    assert g.shape == exp.shape
+    assert np.array_equal(g.view(np.uint32), exp.view(np.uint32)), f"max abs diff {np.abs(g - exp).max()}"
+
+
+@pytest.mark.parametrize("tag,kw", [
+    ("stretch32x48", dict(out_h=32, out_w=48)),
+    ("letterbox40", dict(mode="letterbox", out_h=40, out_w=40)),
+    ("letterbox48x56pad", dict(mode="letterbox", out_h=48, out_w=56, max_size=44, pad=(7, 200, 33))),
+    ("stretch64", dict(out_h=64, out_w=64)),
+])
+def test_k1_matches_cv2_golden(cuda_device, golden_dir, tag, kw):
+    from nkb_classification_b200 import transforms as T
+    g = np.load(golden_dir / "pixels_golden.npz")
+    idx = g[f"{tag}.idx"]
+    plan = make_plan(T, **kw)
+    out, u8 = run_k1(cuda_device, g["frames"], g["boxes"][idx], g["frame_idx"][idx], plan)
+    assert np.array_equal(u8.cpu().numpy(), g[f"{tag}.u8"])
+    assert_same_f32(out, g[f"{tag}.f32"])
+
+
+def _random_boxes(rng, n, H, W, wmin=1, wmax=None, hmax=None):
+    wmax, hmax = wmax or W, hmax or H
+    boxes = []
+    for _ in range(n):
+        w, h = int(rng.integers(wmin, wmax + 1)), int(rng.integers(wmin, hmax + 1))
+        x0, y0 = int(rng.integers(0, W - w + 1)), int(rng.integers(0, H - h + 1))
+        boxes.append((x0, y0, x0 + w, y0 + h))
+    return boxes
+
+
+@pytest.mark.parametrize("kw", [
+    dict(out_h=224, out_w=224),
+    dict(out_h=224, out_w=224, swap=True),
+    dict(out_h=128, out_w=128),
+    dict(out_h=256, out_w=256),
+    dict(out_h=100, out_w=60),
+    dict(out_h=40, out_w=384),
+    dict(mode="letterbox", out_h=224, out_w=224),
+    dict(mode="letterbox", out_h=128, out_w=128, swap=True, pad=(1, 2, 250)),
+    dict(mode="letterbox", out_h=96, out_w=160, max_size=90),
+])
+def test_k1_random_boxes_vs_oracle(cuda_device, kw):
+    from nkb_classification_b200 import transforms as T
+    rng = np.random.default_rng(11)
+    frames = rng.integers(0, 256, (3, 270, 480, 3), dtype=np.uint8)
+    boxes = _random_boxes(rng, 96, 270, 480, wmin=3 if kw.get("mode") == "letterbox" else 1)
+    if kw.get("mode") == "letterbox":  # drop boxes whose letterboxed side rounds to 0 (the reference asserts there)
+        ms = kw.get("max_size") or min(kw["out_h"], kw["out_w"])
+        boxes = [b for b in boxes if min(opre.letterbox_geometry(b[3] - b[1], b[2] - b[0], ms, kw["out_h"], kw["out_w"])[:2]) >= 1]
+    boxes += [(0, 0, 480, 270), (479, 269, 480, 270) if kw.get("mode") != "letterbox" else (470, 260, 480, 270),
+              (0, 0, 2, 270), (470, 0, 480, 270), (0, 265, 480, 270)]
+    fidx = [i % 3 for i in range(len(boxes))]
+    plan = make_plan(T, **kw)
+    out, u8 = run_k1(cuda_device, frames, boxes, fidx, plan)
+    eu8, ef32 = preprocess_batch_c(frames, boxes, fidx, oracle_plan(plan))
+    assert np.array_equal(u8.cpu().numpy(), eu8)
+    assert_same_f32(out, ef32)
+    # bf16 output is the RNE rounding of the same fp32 values
+    outb, _ = run_k1(cuda_device, frames, boxes, fidx, plan, dtype=torch.bfloat16, want_u8=False)
+    got_bits = outb.view(torch.int16).cpu().numpy().view(np.uint16)
+    assert np.array_equal(got_bits, opre.f32_to_bf16_bits(ef32).reshape(ef32.shape))
+
+
+def test_k1_edge_boxes_1080p(cuda_device):
+    """SURVEY 8d edge set: 5x5, 5x1080, full frame, x1 = W, exact 2x, identity, 223x225."""
+    from nkb_classification_b200 import transforms as T
+    rng = np.random.default_rng(12)
+    frames = rng.integers(0, 256, (2, 1080, 1920, 3), dtype=np.uint8)
+    yy, xx = np.mgrid[0:1080, 0:1920]
+    frames[1, :, :, 0] = (xx + 2 * yy) % 256
+    boxes = [(100, 100, 105, 105), (7, 0, 12, 1080), (0, 0, 1920, 1080), (1500, 300, 1920, 700), (10, 20, 458, 468),
+             (33, 44, 257, 268), (1, 1, 224, 226), (0, 1075, 1920, 1080), (1915, 0, 1920, 1080), (640, 360, 1120, 840),
+             (1919, 1079, 1920, 1080)]
+    fidx = [i % 2 for i in range(len(boxes))]
+    plan = make_plan(T)
+    out, u8 = run_k1(cuda_device, frames, boxes, fidx, plan)
+    eu8, ef32 = preprocess_batch_c(frames, boxes, fidx, oracle_plan(plan))
+    assert np.array_equal(u8.cpu().numpy(), eu8)
+    assert_same_f32(out, ef32)
+    # identity crop: the resized pixels are the source pixels
+    assert np.array_equal(u8[5].cpu().numpy(), frames[1][44:268, 33:257])
+
+
+def test_k1_bad_boxes_are_counted_and_padded(cuda_device):
+    from nkb_classification_b200 import transforms as T
+    rng = np.random.default_rng(13)
+    frames = rng.integers(0, 256, (1, 64, 64, 3), dtype=np.uint8)
+    boxes = [(0, 0, 10, 10), (5, 5, 5, 20), (10, 10, 70, 20), (-1, 0, 10, 10), (3, 9, 2, 12), (20, 20, 40, 40)]
+    fidx = [0, 0, 0, 0, 0, 7]
+    plan = make_plan(T, out_h=32, out_w=32)
+    bad = torch.zeros(1, dtype=torch.int32, device=cuda_device)
+    out, u8 = run_k1(cuda_device, frames, boxes, fidx, plan, bad_count=bad)
+    assert int(bad.item()) == 5
+    eu8, ef32 = preprocess_batch_c(frames, boxes[:1], fidx[:1], oracle_plan(plan))
+    assert np.array_equal(u8[0].cpu().numpy(), eu8[0])
+    m, d = opre.normalize_constants(MEAN, STD)
+    pad = ((np.zeros(3, np.float32) - m) * d).astype(np.float32)
+    for i in range(1, 6):
+        assert np.array_equal(out[i].cpu().numpy(), np.broadcast_to(pad[:, None, None], (3, 32, 32)))
+
+
+def test_k1_ragged_frames_with_pitch(cuda_device):
+    """Frames of different sizes in one buffer, rows padded to an odd pitch (unaligned 3-byte pixels)."""
+    from nkb_classification_b200 import ops, transforms as T
+    rng = np.random.default_rng(14)
+    shapes = [(50, 67, 211), (33, 90, 275), (80, 41, 130)]  # (H, W, pitch) -- pitches not multiples of 4
+    bufs, desc, off, frames = [], [], 3, []                  # start at an odd offset
+    flat = np.zeros(3 + sum(h * p for h, w, p in shapes) + 16, dtype=np.uint8)
+    for h, w, p in shapes:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        frames.append(img)
+        view = flat[off: off + h * p].reshape(h, p)
+        view[:, : w * 3] = img.reshape(h, w * 3)
+        desc.append((off, h, w, p))
+        off += h * p
+    boxes, fidx = [], []
+    for fi, (h, w, p) in enumerate(shapes):
+        for b in _random_boxes(rng, 12, h, w) + [(0, 0, w, h), (w - 1, 0, w, h), (w - 2, h - 2, w, h)]:
+            boxes.append(b)
+            fidx.append(fi)
+    plan = make_plan(T, out_h=48, out_w=72)
+    dev = cuda_device
+    out_u8 = torch.empty((len(boxes), 48, 72, 3), dtype=torch.uint8, device=dev)
+    out = ops.preprocess_crops(torch.from_numpy(flat).to(dev), torch.tensor(boxes, dtype=torch.int32, device=dev),
+                               torch.tensor(fidx, dtype=torch.int32, device=dev), plan, out_u8=out_u8,
+                               frame_desc=torch.tensor(desc, dtype=torch.int64, device=dev))
+    torch.cuda.synchronize()
+    op = oracle_plan(plan)
+    for i, (b, fi) in enumerate(zip(boxes, fidx)):
+        eu8, ef = opre.preprocess_crop(frames[fi], b, op, "int")
+        assert np.array_equal(out_u8[i].cpu().numpy(), eu8), (i, b, fi)
+        assert np.array_equal(out[i].cpu().numpy().view(np.uint32), ef.view(np.uint32))
+
+
+def test_k1_full_size_batch_properties(cuda_device):
+    """BASELINE config 5 shape: 64 x 1080p frames, 64 boxes each -> 4096 crops of 224^2.
+    Spot-check 96 crops against the oracle; determinism; identity-crop property on all frames."""
+    from nkb_classification_b200 import transforms as T
+    dev = cuda_device
+    g = torch.Generator(device="cpu").manual_seed(1234)
+    frames = torch.randint(0, 256, (64, 1080, 1920, 3), dtype=torch.uint8, generator=g)
+    rng = np.random.default_rng(4321)
+    boxes, fidx = [], []
+    for f in range(64):
+        for k in range(64):
+            w, h = int(rng.integers(48, 481)), int(rng.integers(48, 481))
+            x0, y0 = int(rng.integers(0, 1920 - w + 1)), int(rng.integers(0, 1080 - h + 1))
+            if k == 0:
+                w = h = 224  # identity crop in every frame
+                x0, y0 = min(x0, 1920 - 224), min(y0, 1080 - 224)
+            boxes.append((x0, y0, x0 + w, y0 + h))
+            fidx.append(f)
+    plan = make_plan(T)
+    fr = frames.to(dev)
+    out1, u8 = run_k1(dev, fr, boxes, fidx, plan)
+    out2, _ = run_k1(dev, fr, boxes, fidx, plan, want_u8=False)
+    assert torch.equal(out1, out2)
+    pick = sorted(set(rng.integers(0, 4096, 96).tolist()) | {0, 4095})
+    fn = frames.numpy()
+    eu8, ef32 = preprocess_batch_c(fn, [boxes[i] for i in pick], [fidx[i] for i in pick], oracle_plan(plan))
+    assert np.array_equal(u8[pick].cpu().numpy(), eu8)
+    assert_same_f32(out1[pick], ef32)
+    for f in range(0, 64, 7):
+        x0, y0, x1, y1 = boxes[f * 64]
+        assert np.array_equal(u8[f * 64].cpu().numpy(), fn[f][y0:y1, x0:x1])
+
+
+def test_k1_empty_batch(cuda_device):
+    from nkb_classification_b200 import ops, transforms as T
+    plan = make_plan(T, out_h=16, out_w=16)
+    out = ops.preprocess_crops(torch.zeros((1, 8, 8, 3), dtype=torch.uint8, device=cuda_device),
+                               torch.zeros((0, 4), dtype=torch.int32, device=cuda_device),
+                               torch.zeros((0,), dtype=torch.int32, device=cuda_device), plan)
+    assert tuple(out.shape) == (0, 3, 16, 16)

@@ -1,0 +1,222 @@
+"""K2 (heads + loss + gradients) and K3 (argmax + confusion) parity on the GPU.
+Tolerances (BASELINE.json): losses / gradients <= 1e-5 relative in fp32,
+<= 1e-2 in bf16; predictions and confusion matrices bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import heads as oh
+from oracle import metrics as om
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "focal_g1": (oh.LOSS_FOCAL, 1.0, False),
+    "focal_g2": (oh.LOSS_FOCAL, 2.0, False),
+    "focal_g0p5_alpha": (oh.LOSS_FOCAL, 0.5, True),
+    "focal_g2_alpha": (oh.LOSS_FOCAL, 2.0, True),
+    "ce": (oh.LOSS_CE, 0.0, False),
+    "ce_weight": (oh.LOSS_CE, 0.0, True),
+}
+
+
+def rel_err(got, exp):
+    got, exp = np.asarray(got, dtype=np.float64), np.asarray(exp, dtype=np.float64)
+    scale = max(np.abs(exp).max(), 1e-30)
+    return np.abs(got - exp).max() / scale
+
+
+def run_k2(dev, emb, Ws, bs, labels, kind, gamma, cws=None, ignore_index=-100, emb_dtype=torch.float32, demb=True):
+    from nkb_classification_b200 import ops
+    seg = np.concatenate([[0], np.cumsum([w.shape[0] for w in Ws])]).tolist()
+    W_cat = torch.cat([w.float() for w in Ws]).contiguous().to(dev)
+    b_cat = torch.cat([b.float() for b in bs]).contiguous().to(dev)
+    cw = torch.cat([c.float() for c in cws]).to(dev) if cws is not None else None
+    e = emb.to(dev).to(emb_dtype).contiguous()
+    B, D = e.shape
+    bufs = ops.HeadsBuffers(B, D, seg, dev)
+    ops.heads_fwd_loss_bwd(e, W_cat, b_cat, labels.to(dev).contiguous(), bufs, kind, gamma, cw, ignore_index)
+    loss = ops.heads_finalize(bufs)
+    de = ops.heads_demb(bufs, W_cat, out_dtype=emb_dtype) if demb else None
+    torch.cuda.synchronize()
+    T = len(Ws)
+    dW = [bufs.dW()[seg[t]:seg[t + 1]].cpu().numpy() for t in range(T)]
+    db = [bufs.db()[seg[t]:seg[t + 1]].cpu().numpy() for t in range(T)]
+    logits = [bufs.logits[:, seg[t]:seg[t + 1]].cpu().numpy() for t in range(T)]
+    probs = [bufs.probs[:, seg[t]:seg[t + 1]].cpu().numpy() for t in range(T)]
+    return dict(loss=loss.cpu().numpy(), dW=dW, db=db, logits=logits, probs=probs,
+                demb=None if de is None else de.float().cpu().numpy(), bufs=bufs, seg=seg)
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_k2_matches_reference_golden_fp32(cuda_device, golden_dir, case):
+    g = np.load(golden_dir / "heads_golden.npz")
+    T = 3
+    emb = torch.from_numpy(g["emb"])
+    Ws = [torch.from_numpy(g[f"W{t}"]) for t in range(T)]
+    bs = [torch.from_numpy(g[f"b{t}"]) for t in range(T)]
+    alphas = [torch.from_numpy(g[f"alpha{t}"]) for t in range(T)]
+    labels = torch.from_numpy(g["labels"])
+    kind, gamma, weighted = CASES[case]
+    r = run_k2(cuda_device, emb, Ws, bs, labels, kind, gamma, alphas if weighted else None)
+    tol = 1e-5
+    assert rel_err(r["loss"], g[f"{case}.f64.loss"]) <= tol
+    for t in range(T):
+        assert rel_err(r["logits"][t], g[f"{case}.f64.logits{t}"]) <= tol
+        assert rel_err(r["dW"][t], g[f"{case}.f64.dW{t}"]) <= tol, (case, t)
+        assert rel_err(r["db"][t], g[f"{case}.f64.db{t}"]) <= tol
+    assert rel_err(r["demb"], g[f"{case}.f64.demb"]) <= tol
+
+
+@pytest.mark.parametrize("B,D,classes,kind,gamma", [
+    (256, 1280, (4, 7, 2), oh.LOSS_FOCAL, 1.0),           # BASELINE config 2
+    (1024, 768, (2, 3, 4, 7, 14), oh.LOSS_FOCAL, 1.0),    # BASELINE config 4 (fp32 leg)
+    (1024, 768, (2, 3, 4, 7, 14), oh.LOSS_CE, 0.0),
+    (32, 512, (10,), oh.LOSS_CE, 0.0),                    # BASELINE config 1
+    (517, 2048, (10,), oh.LOSS_CE, 0.0),                  # config 5 width, ragged B
+    (130, 260, (3, 70, 2, 5), oh.LOSS_FOCAL, 2.0),        # > 64 classes: two dW passes, ragged D
+    (5, 64, (2,) * 9, oh.LOSS_FOCAL, 2.0),                # more than 8 tasks per row group
+])
+def test_k2_vs_oracle_fp32(cuda_device, B, D, classes, kind, gamma):
+    g = torch.Generator().manual_seed(7)
+    emb = torch.randn(B, D, generator=g)
+    Ws = [torch.randn(c, D, generator=g) * (2.0 / D) ** 0.5 for c in classes]
+    bs = [torch.randn(c, generator=g) * 0.05 for c in classes]
+    labels = torch.stack([torch.randint(0, c, (B,), generator=g) for c in classes], 1)
+    labels[::17, 0] = -100
+    exp = oh.heads_loss_fwd_bwd(emb, Ws, bs, labels, kind, gamma, dtype=torch.float64)
+    r = run_k2(cuda_device, emb, Ws, bs, labels, kind, gamma)
+    tol = 1e-5
+    assert rel_err(r["loss"][:-1], [float(x) for x in exp["loss"]]) <= tol
+    assert rel_err(r["loss"][-1], float(exp["total"])) <= tol
+    for t in range(len(classes)):
+        assert rel_err(r["logits"][t], exp["logits"][t].numpy()) <= tol
+        assert rel_err(r["probs"][t], exp["probs"][t].numpy()) <= tol
+        assert rel_err(r["dW"][t], exp["dW"][t].numpy()) <= tol, t
+        assert rel_err(r["db"][t], exp["db"][t].numpy()) <= tol, t
+    assert rel_err(r["demb"], exp["demb"].numpy()) <= tol
+
+
+def test_k2_bf16_embeddings(cuda_device):
+    """BASELINE config 4: bf16 embeddings [1024,768], 5 heads -- tolerance 1e-2."""
+    g = torch.Generator().manual_seed(7)
+    B, D, classes = 1024, 768, (2, 3, 4, 7, 14)
+    emb = torch.randn(B, D, generator=g).to(torch.bfloat16)
+    Ws = [torch.randn(c, D, generator=g) * (2.0 / D) ** 0.5 for c in classes]
+    bs = [torch.zeros(c) for c in classes]
+    labels = torch.stack([torch.randint(0, c, (B,), generator=g) for c in classes], 1)
+    for kind, gamma in ((oh.LOSS_FOCAL, 1.0), (oh.LOSS_CE, 0.0)):
+        exp = oh.heads_loss_fwd_bwd(emb.double(), Ws, bs, labels, kind, gamma, dtype=torch.float64)
+        r = run_k2(cuda_device, emb, Ws, bs, labels, kind, gamma, emb_dtype=torch.bfloat16)
+        assert rel_err(r["loss"][-1], float(exp["total"])) <= 1e-2
+        for t in range(len(classes)):
+            assert rel_err(r["dW"][t], exp["dW"][t].numpy()) <= 1e-2
+        assert rel_err(r["demb"], exp["demb"].numpy()) <= 1e-2
+
+
+def test_k2_all_ignored_and_forward_only(cuda_device):
+    from nkb_classification_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    B, D, classes = 64, 128, (3, 4)
+    emb = torch.randn(B, D, generator=g)
+    Ws = [torch.randn(c, D, generator=g) * 0.1 for c in classes]
+    bs = [torch.zeros(c) for c in classes]
+    labels = torch.stack([torch.full((B,), -100), torch.randint(0, 4, (B,), generator=g)], 1)
+    r = run_k2(cuda_device, emb, Ws, bs, labels, oh.LOSS_FOCAL, 1.0)
+    assert r["loss"][0] == 0.0 and np.all(r["dW"][0] == 0) and np.all(r["db"][0] == 0)
+    exp = oh.heads_loss_fwd_bwd(emb, Ws, bs, labels, oh.LOSS_FOCAL, 1.0)
+    assert rel_err(r["loss"][1], float(exp["loss"][1])) <= 1e-5
+    # forward-only buffers (val / inference): no dlogits, grads zeroed, loss still produced
+    dev = cuda_device
+    seg = [0, 3, 7]
+    bufs = ops.HeadsBuffers(B, D, seg, dev, want_grads=False)
+    W_cat = torch.cat(Ws).to(dev)
+    ops.heads_fwd_loss_bwd(emb.to(dev), W_cat, torch.zeros(7, device=dev), labels.to(dev), bufs, oh.LOSS_FOCAL, 1.0)
+    loss = ops.heads_finalize(bufs).cpu().numpy()
+    assert rel_err(loss[1], float(exp["loss"][1])) <= 1e-5
+    assert float(bufs.dW().abs().max()) == 0.0
+
+
+def test_k2_is_deterministic(cuda_device):
+    g = torch.Generator().manual_seed(5)
+    B, D, classes = 1000, 768, (4, 7, 2)
+    emb = torch.randn(B, D, generator=g)
+    Ws = [torch.randn(c, D, generator=g) * 0.05 for c in classes]
+    bs = [torch.zeros(c) for c in classes]
+    labels = torch.stack([torch.randint(0, c, (B,), generator=g) for c in classes], 1)
+    a = run_k2(cuda_device, emb, Ws, bs, labels, oh.LOSS_FOCAL, 1.0)
+    b = run_k2(cuda_device, emb, Ws, bs, labels, oh.LOSS_FOCAL, 1.0)
+    assert np.array_equal(a["loss"], b["loss"])
+    assert all(np.array_equal(x, y) for x, y in zip(a["dW"], b["dW"]))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_k3_argmax_confusion_exact(cuda_device, dtype):
+    from nkb_classification_b200 import ops
+    dev = cuda_device
+    rng = np.random.default_rng(21)
+    classes = (2, 3, 4, 7, 14)
+    seg = np.concatenate([[0], np.cumsum(classes)]).tolist()
+    B = 5000
+    # integer-valued logits: plenty of exact ties, representable in bf16
+    z = rng.integers(-3, 4, (B, seg[-1])).astype(np.float32)
+    z[5, 0:2] = np.nan
+    z[6, 3] = np.nan
+    z[7, 5:9] = -np.inf
+    labels = np.stack([rng.integers(0, c, B) for c in classes], 1).astype(np.int64)
+    labels[::13, 2] = -100
+    zt = torch.from_numpy(z).to(dev).to(dtype)
+    cm = torch.zeros(ops.confusion_len(seg), dtype=torch.int64, device=dev)
+    lab = torch.from_numpy(labels).to(dev)
+    pred, _ = ops.argmax_confusion(zt, seg, lab, cm)
+    ops.argmax_confusion(zt, seg, lab, cm, want_pred=False)   # accumulates: second pass doubles the counts
+    torch.cuda.synchronize()
+    pred = pred.cpu().numpy()
+    off = 0
+    for t, C in enumerate(classes):
+        zt_t = z[:, seg[t]:seg[t + 1]]
+        exp_pred = torch.from_numpy(zt_t).argmax(-1).numpy()
+        assert np.array_equal(exp_pred, om.argmax_first(zt_t))
+        assert np.array_equal(pred[:, t], exp_pred)
+        exp_cm = om.confusion_matrix(labels[:, t], exp_pred, C)
+        got = cm[off: off + C * C].view(C, C).cpu().numpy()
+        assert np.array_equal(got, 2 * exp_cm)
+        assert om.balanced_accuracy_from_cm(got) == om.balanced_accuracy_from_cm(exp_cm)
+        off += C * C
+
+
+def test_k3_large_class_count_uses_global_atomics(cuda_device):
+    from nkb_classification_b200 import ops
+    dev = cuda_device
+    rng = np.random.default_rng(22)
+    C, B = 120, 3000   # 14400 bins > shared-memory histogram capacity
+    z = rng.normal(size=(B, C)).astype(np.float32)
+    labels = rng.integers(0, C, (B, 1)).astype(np.int64)
+    cm = torch.zeros(C * C, dtype=torch.int64, device=dev)
+    pred, _ = ops.argmax_confusion(torch.from_numpy(z).to(dev), [0, C], torch.from_numpy(labels).to(dev), cm)
+    exp_pred = z.argmax(1)
+    assert np.array_equal(pred.cpu().numpy()[:, 0], exp_pred)
+    assert np.array_equal(cm.view(C, C).cpu().numpy(), om.confusion_matrix(labels[:, 0], exp_pred, C))
+
+
+def test_k2_k3_end_to_end_metrics_match_reference_golden(cuda_device, golden_dir):
+    """Confusion matrix from K3 -> balanced accuracy equals the reference's sklearn value bit for bit."""
+    from nkb_classification_b200 import ops
+    g = np.load(golden_dir / "metrics_golden.npz")
+    dev = cuda_device
+    names = ["a_color", "b_size", "c_kind"]
+    zs = [g[f"{n}.logits"] for n in names]
+    seg = np.concatenate([[0], np.cumsum([z.shape[1] for z in zs])]).tolist()
+    z = torch.from_numpy(np.concatenate(zs, 1)).to(dev)
+    labels = torch.from_numpy(np.stack([g[f"{n}.gt"] for n in names], 1).astype(np.int64)).to(dev)
+    cm = torch.zeros(ops.confusion_len(seg), dtype=torch.int64, device=dev)
+    ops.argmax_confusion(z, seg, labels, cm)
+    off = 0
+    accs = []
+    for n, zt in zip(names, zs):
+        C = zt.shape[1]
+        acc = om.balanced_accuracy_from_cm(cm[off: off + C * C].view(C, C).cpu().numpy())
+        assert acc == float(g[f"{n}.epoch_acc"])
+        accs.append(acc)
+        off += C * C
+    assert float(np.mean(accs)) == float(g["epoch_acc"])
