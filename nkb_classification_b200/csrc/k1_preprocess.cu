@@ -58,34 +58,58 @@ __device__ __forceinline__ void store_out<__nv_bfloat16>(__nv_bfloat16* p, float
     __stcs(reinterpret_cast<unsigned short*>(p), __bfloat16_as_ushort(__float2bfloat16_rn(v)));
 }
 
-// Horizontal pass of one source row for this lane's JMAX columns.
+// Raw words of one source row for this lane's JMAX two-pixel windows, loaded one
+// row ahead of use so the DRAM/L2 latency hides behind the vertical pass.
 template <int JMAX>
-__device__ __forceinline__ void hrow(uint32_t (&H)[JMAX][3], const uint8_t* __restrict__ rowp,
-                                     const uint32_t (&xo)[JMAX], const uint32_t (&cf)[JMAX], const uint32_t sel0,
-                                     const uint32_t sel1, const uint32_t sel2) {
-    uint32_t w0[JMAX], w1[JMAX], w2[JMAX], k8[JMAX];
+struct RawRow {
+    uint32_t w0[JMAX], w1[JMAX], w2[JMAX];
+    uint32_t mis;  // (row address & 3): byte misalignment of the row the words came from
+    int row;       // source row held, -1 = none
+};
+
+// Issue the loads of source row `rowp` (pointer to the crop's first byte of that row).
+// Every word read contains at least one byte of the row's pixels, so aligned 32-bit
+// loads never leave the mapped frame; the third word is fetched only when the
+// 6-byte window straddles into it ((offset & 3) == 3).
+template <int JMAX>
+__device__ __forceinline__ void issue_row(RawRow<JMAX>& R, const uint8_t* __restrict__ rowp,
+                                          const uint32_t (&xo)[JMAX], int row) {
+    const uint32_t mis = uint32_t(reinterpret_cast<uintptr_t>(rowp)) & 3u;
+    const uint8_t* base = rowp - mis;
 #pragma unroll
     for (int j = 0; j < JMAX; ++j) {
-        const uintptr_t a = reinterpret_cast<uintptr_t>(rowp + xo[j]);
-        const uint32_t* al = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
-        k8[j] = (uint32_t(a) & 3u) * 8u;
-        w0[j] = __ldg(al);
-        w1[j] = __ldg(al + 1);
-        w2[j] = 0u;
-        if (k8[j] == 24u) w2[j] = __ldg(al + 2);  // only then are bytes 8.. of the window needed
+        const uint32_t p = xo[j] + mis;
+        const uint32_t* al = reinterpret_cast<const uint32_t*>(base + (p & ~3u));
+        R.w0[j] = __ldg(al);
+        R.w1[j] = __ldg(al + 1);
+        R.w2[j] = 0u;
+        if ((p & 3u) == 3u) R.w2[j] = __ldg(al + 2);
     }
+    R.mis = mis;
+    R.row = row;
+}
+
+// Horizontal pass: raw words -> H >> 4 (the 15-bit values OpenCV's vertical pass consumes).
+template <int JMAX>
+__device__ __forceinline__ void convert_row(uint32_t (&H)[JMAX][3], const RawRow<JMAX>& R, const uint32_t (&xo)[JMAX],
+                                            const uint32_t (&cf)[JMAX], const uint32_t sel0, const uint32_t sel1,
+                                            const uint32_t sel2) {
 #pragma unroll
     for (int j = 0; j < JMAX; ++j) {
-        const uint32_t lo = __funnelshift_r(w0[j], w1[j], k8[j]);  // bytes o .. o+3
-        const uint32_t hi = __funnelshift_r(w1[j], w2[j], k8[j]);  // bytes o+4 .. o+7
+        const uint32_t k8 = (xo[j] + R.mis) << 3;                    // shf.wrap uses the low 5 bits: (offset & 3) * 8
+        const uint32_t lo = __funnelshift_r(R.w0[j], R.w1[j], k8);   // bytes o .. o+3
+        const uint32_t hi = __funnelshift_r(R.w1[j], R.w2[j], k8);   // bytes o+4 .. o+7
         H[j][0] = __dp2a_lo(cf[j], __byte_perm(lo, hi, sel0), 0u) >> 4;
         H[j][1] = __dp2a_lo(cf[j], __byte_perm(lo, hi, sel1), 0u) >> 4;
         H[j][2] = __dp2a_lo(cf[j], __byte_perm(lo, hi, sel2), 0u) >> 4;
     }
 }
 
-template <int JMAX, typename OutT, bool WRITE_U8>
+// GENERAL = false: stretch mode and out_w a multiple of the 32*JMAX column tile -> every lane
+// writes every column, no border handling, no uint8 side output.  GENERAL = true: everything.
+template <int JMAX, typename OutT, bool GENERAL, bool WRITE_U8>
 __global__ void __launch_bounds__(K1_WARPS * 32) k1_crop_resize_normalize(const K1Params p) {
+    static_assert(GENERAL || !WRITE_U8, "uint8 side output only in the general variant");
     const int crop = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int band = blockIdx.y * K1_WARPS + warp;
@@ -111,14 +135,17 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_crop_resize_normalize(const 
     const int bw = bx1 - bx0, bh = by1 - by0;
     ok = ok && bx0 >= 0 && by0 >= 0 && bx1 <= fw && by1 <= fh && bw >= 1 && bh >= 1 && fw >= 2;
     int dw = p.out_w, dh = p.out_h, top = 0, left = 0;
-    if (ok && p.mode == NKBK_MODE_LETTERBOX)
+    if (GENERAL && ok && p.mode == NKBK_MODE_LETTERBOX)
         ok = letterbox_geometry(bh, bw, p.max_size, p.out_h, p.out_w, dh, dw, top, left);
 
     const int64_t plane = (int64_t)p.out_h * p.out_w;
     OutT* const out_crop = reinterpret_cast<OutT*>(p.out) + (int64_t)crop * 3 * plane;
-    uint32_t wmask = 0;  // columns this lane writes at all
+    uint32_t wmask = (1u << JMAX) - 1u;  // columns this lane writes at all
+    if (GENERAL) {
+        wmask = 0;
 #pragma unroll
-    for (int j = 0; j < JMAX; ++j) wmask |= uint32_t(ox0 + 32 * j < p.out_w) << j;
+        for (int j = 0; j < JMAX; ++j) wmask |= uint32_t(ox0 + 32 * j < p.out_w) << j;
+    }
 
     if (!ok) {
         // empty / out-of-frame box: emit the normalised pad value, count it once per crop
@@ -142,14 +169,15 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_crop_resize_normalize(const 
 
     // ---- horizontal tables, one entry per (lane, j), kept in registers ----
     uint32_t xo[JMAX], cf[JMAX];
-    uint32_t vmask = 0;  // columns that receive resized pixels (the rest of wmask is letterbox border)
+    uint32_t vmask = (1u << JMAX) - 1u;  // columns that receive resized pixels (the rest of wmask is border)
     {
+        if (GENERAL) vmask = 0;
         const double sxs = axis_scale(dw, bw);
 #pragma unroll
         for (int j = 0; j < JMAX; ++j) {
             const int ox = ox0 + 32 * j;
             const int dx = ox - left;
-            const bool v = ox < p.out_w && dx >= 0 && dx < dw;
+            const bool v = !GENERAL || (ox < p.out_w && dx >= 0 && dx < dw);
             int s = 0, c0 = 0, c1 = 0;
             if (v) axis_coef(dx, sxs, bw, true, s, c0, c1);
             int px = bx0 + s;
@@ -161,7 +189,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_crop_resize_normalize(const 
             if (!v) { px = 0; c = 0u; }
             xo[j] = uint32_t(px) * 3u;
             cf[j] = c;
-            vmask |= uint32_t(v) << j;
+            if (GENERAL) vmask |= uint32_t(v) << j;
         }
     }
 
@@ -192,6 +220,31 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_crop_resize_normalize(const 
 #pragma unroll
         for (int c = 0; c < 3; ++c) Ha[j][c] = Hb[j][c] = 0u;
 
+    // ---- source-row stream with one row of look-ahead ----
+    // The rows a band needs form a strictly increasing sequence (r0, r1 of each output row that
+    // are not already held).  `fetch_next` scans the (row, tap) candidates in order of need and
+    // issues the loads of the next unseen row; it is called right after the previous row has
+    // been converted, i.e. a whole vertical pass before the data is consumed.
+    RawRow<JMAX> pf;
+    pf.row = -1;
+    pf.mis = 0;
+#pragma unroll
+    for (int j = 0; j < JMAX; ++j) pf.w0[j] = pf.w1[j] = pf.w2[j] = 0u;
+    int kq = 0, fetched_max = -1;
+    auto fetch_next = [&]() {
+        pf.row = -1;
+        while (kq < 2 * nrows) {
+            const int rc = __shfl_sync(0xffffffffu, (kq & 1) ? my_r1 : my_r0, kq >> 1);
+            ++kq;
+            if (rc > fetched_max) {
+                fetched_max = rc;
+                issue_row<JMAX>(pf, src0 + (int64_t)rc * pitch, xo, rc);
+                break;
+            }
+        }
+    };
+    fetch_next();
+
     for (int yy = 0; yy < nrows; ++yy) {
         const int r0 = __shfl_sync(0xffffffffu, my_r0, yy);
         const int r1 = __shfl_sync(0xffffffffu, my_r1, yy);
@@ -201,7 +254,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_crop_resize_normalize(const 
         OutT* o = out_crop + (int64_t)y * p.out_w + ox0;
         uint8_t* u = WRITE_U8 ? p.out_u8 + (((int64_t)crop * p.out_h + y) * p.out_w + ox0) * 3 : nullptr;
 
-        if (r0 < 0) {  // letterbox border row
+        if (GENERAL && r0 < 0) {  // letterbox border row
 #pragma unroll
             for (int j = 0; j < JMAX; ++j)
                 if (wmask >> j & 1) {
@@ -221,8 +274,9 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_crop_resize_normalize(const 
                 for (int j = 0; j < JMAX; ++j)
 #pragma unroll
                     for (int c = 0; c < 3; ++c) Ha[j][c] = Hb[j][c];
-            } else {
-                hrow<JMAX>(Ha, src0 + (int64_t)r0 * pitch, xo, cf, sel0, sel1, sel2);
+            } else {  // pf.row == r0 by construction of the stream
+                convert_row<JMAX>(Ha, pf, xo, cf, sel0, sel1, sel2);
+                fetch_next();
             }
             ia = r0;
         }
@@ -233,38 +287,45 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_crop_resize_normalize(const 
 #pragma unroll
                     for (int c = 0; c < 3; ++c) Hb[j][c] = Ha[j][c];
             } else {
-                hrow<JMAX>(Hb, src0 + (int64_t)r1 * pitch, xo, cf, sel0, sel1, sel2);
+                convert_row<JMAX>(Hb, pf, xo, cf, sel0, sel1, sel2);
+                fetch_next();
             }
             ib = r1;
         }
 
 #pragma unroll
         for (int j = 0; j < JMAX; ++j) {
-            if (!(wmask >> j & 1)) continue;
-            const bool v = vmask >> j & 1;
             uint32_t px[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                uint32_t t = __umulhi(b0, Ha[j][c]) + 2u;
-                t = __umulhi(b1, Hb[j][c]) + t;
-                px[c] = v ? (t >> 2) : p.padu[c];
+                const uint32_t t0 = __umulhi(b0, Ha[j][c]);
+                const uint32_t t1 = __umulhi(b1, Hb[j][c]);
+                px[c] = (t0 + t1 + 2u) >> 2;
+                if (GENERAL && !(vmask >> j & 1)) px[c] = p.padu[c];
             }
-            store_out<OutT>(o + 32 * j, __fmul_rn(__fsub_rn((float)px[0], m0), d0));
-            store_out<OutT>(o + plane + 32 * j, __fmul_rn(__fsub_rn((float)px[1], m1), d1));
-            store_out<OutT>(o + 2 * plane + 32 * j, __fmul_rn(__fsub_rn((float)px[2], m2), d2));
-            if (WRITE_U8) {
-                u[96 * j + 0] = (uint8_t)px[0]; u[96 * j + 1] = (uint8_t)px[1]; u[96 * j + 2] = (uint8_t)px[2];
+            const float f0 = __fmul_rn(__fsub_rn((float)px[0], m0), d0);
+            const float f1 = __fmul_rn(__fsub_rn((float)px[1], m1), d1);
+            const float f2 = __fmul_rn(__fsub_rn((float)px[2], m2), d2);
+            if (!GENERAL || (wmask >> j & 1)) {
+                store_out<OutT>(o + 32 * j, f0);
+                store_out<OutT>(o + plane + 32 * j, f1);
+                store_out<OutT>(o + 2 * plane + 32 * j, f2);
+                if (WRITE_U8) {
+                    u[96 * j + 0] = (uint8_t)px[0]; u[96 * j + 1] = (uint8_t)px[1]; u[96 * j + 2] = (uint8_t)px[2];
+                }
             }
         }
     }
 }
 
 template <int JMAX, typename OutT>
-static void launch_k1(const K1Params& p, dim3 grid, cudaStream_t st) {
+static void launch_k1(const K1Params& p, dim3 grid, cudaStream_t st, bool general) {
     if (p.out_u8 != nullptr)
-        k1_crop_resize_normalize<JMAX, OutT, true><<<grid, K1_WARPS * 32, 0, st>>>(p);
+        k1_crop_resize_normalize<JMAX, OutT, true, true><<<grid, K1_WARPS * 32, 0, st>>>(p);
+    else if (general)
+        k1_crop_resize_normalize<JMAX, OutT, true, false><<<grid, K1_WARPS * 32, 0, st>>>(p);
     else
-        k1_crop_resize_normalize<JMAX, OutT, false><<<grid, K1_WARPS * 32, 0, st>>>(p);
+        k1_crop_resize_normalize<JMAX, OutT, false, false><<<grid, K1_WARPS * 32, 0, st>>>(p);
 }
 
 }  // namespace nkbk
@@ -328,10 +389,11 @@ extern "C" int nkbk_preprocess_crops(const void* frames_base, const int64_t* fra
     dim3 grid((unsigned)n, (unsigned)nby, (unsigned)ntx);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool f32 = out_dtype == NKBK_F32;
+    const bool general = mode != NKBK_MODE_STRETCH || out_w % (32 * best_j) != 0;
     switch (best_j) {
-        case 4: f32 ? launch_k1<4, float>(p, grid, st) : launch_k1<4, __nv_bfloat16>(p, grid, st); break;
-        case 7: f32 ? launch_k1<7, float>(p, grid, st) : launch_k1<7, __nv_bfloat16>(p, grid, st); break;
-        default: f32 ? launch_k1<8, float>(p, grid, st) : launch_k1<8, __nv_bfloat16>(p, grid, st); break;
+        case 4: f32 ? launch_k1<4, float>(p, grid, st, general) : launch_k1<4, __nv_bfloat16>(p, grid, st, general); break;
+        case 7: f32 ? launch_k1<7, float>(p, grid, st, general) : launch_k1<7, __nv_bfloat16>(p, grid, st, general); break;
+        default: f32 ? launch_k1<8, float>(p, grid, st, general) : launch_k1<8, __nv_bfloat16>(p, grid, st, general); break;
     }
     NKBK_CHECK_LAUNCH("k1_crop_resize_normalize");
     return NKBK_OK;
