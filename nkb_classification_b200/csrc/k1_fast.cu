@@ -1,0 +1,223 @@
+// K1 fast path: stretch mode (A.Resize), full 32*JMAX column tiles, 16-byte
+// aligned frame rows.  Same arithmetic as k1_general.cu (bit-exact with cv2),
+// different data movement:
+//
+//   * every warp owns a band of output rows and a private shared-memory ring of
+//     source-row slots; one elected lane streams the rows the band needs with
+//     cp.async.bulk (TMA bulk copy, SASS UBLKCP) completing on per-slot mbarriers,
+//     up to `nslot` rows ahead of the arithmetic -> DRAM latency is hidden by the
+//     copy engine instead of by occupancy, and no registers are tied up;
+//   * the list of rows to fetch (strictly increasing, <= 2 * rows_per_warp <= 32
+//     entries) is built once per band with two ballots and lives one entry per lane;
+//   * the two vertically-adjacent filtered rows are kept in two register arrays
+//     whose roles flip instead of being copied when the lower tap becomes the
+//     upper one;
+//   * all per-(lane, j) constants (smem byte offset of the 2-pixel window, funnel
+//     shift, packed 11-bit coefficients) are loop invariant, so one source row
+//     costs 3 LDS + 2 SHF + 3 PRMT + 3 IDP.2A + 3 SHF per (lane, j).
+#include "k1_common.cuh"
+
+namespace nkbk {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "NKBK_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra NKBK_DONE_%=;\n\t"
+        "bra NKBK_WAIT_%=;\n\t"
+        "NKBK_DONE_%=:\n\t"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+
+template <int JMAX, typename OutT>
+__global__ void __launch_bounds__(K1_WARPS * 32) k1_crop_resize_normalize_tma(const K1Params p) {
+    __shared__ __align__(128) uint8_t ring[K1_WARPS][K1F_RING_BYTES];
+    __shared__ __align__(8) uint64_t bars[K1_WARPS][K1F_MAX_SLOTS];
+    __shared__ int fetch_rows[K1_WARPS][32];
+
+    const int crop = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int band = blockIdx.y * K1_WARPS + warp;
+    const int y_begin = band * p.rows_per_warp;
+    if (y_begin >= p.out_h) return;
+    const int nrows = min(p.rows_per_warp, p.out_h - y_begin);
+    const int ox0 = blockIdx.z * (32 * JMAX) + lane;
+
+    const CropGeom g = load_geom(p, crop);
+    uint32_t seg_start, seg_bytes, slot_stride;
+    int nslot;
+    if (!fast_path_qualifies(p, g, seg_start, seg_bytes, slot_stride, nslot)) return;  // left to the general kernel
+    const int dw = p.out_w, dh = p.out_h;
+
+    // ---- per-warp barriers ----
+    const uint32_t bar0 = smem_u32(&bars[warp][0]);
+    const uint32_t ring0 = smem_u32(&ring[warp][0]);
+    if (lane == 0) {
+        for (int s = 0; s < nslot; ++s) mbar_init(bar0 + 8u * s, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+
+    // ---- horizontal tables: smem byte offset of the window, funnel shift, packed coefficients ----
+    uint32_t soa[JMAX], sk8[JMAX], cf[JMAX];
+    {
+        const double sxs = axis_scale(dw, g.bw);
+#pragma unroll
+        for (int j = 0; j < JMAX; ++j) {
+            int s, c0, c1;
+            axis_coef(ox0 + 32 * j, sxs, g.bw, true, s, c0, c1);
+            int px = g.bx0 + s;
+            uint32_t c = uint32_t(c0) | (uint32_t(c1) << 16);
+            if (px + 1 >= g.fw) {  // window would leave the frame row: shift it left, weight moves to tap 1
+                px -= 1;
+                c = uint32_t(c0) << 16;
+            }
+            const uint32_t so = uint32_t(px) * 3u - seg_start;
+            soa[j] = so & ~3u;
+            sk8[j] = (so & 3u) * 8u;
+            cf[j] = c;
+        }
+    }
+
+    // ---- vertical tables: lane l holds output row y_begin + l ----
+    int my_r0 = -1, my_r1 = -1;
+    uint32_t my_b0 = 0, my_b1 = 0;
+    if (lane < nrows) {
+        int s, c0, c1;
+        axis_coef(y_begin + lane, axis_scale(dh, g.bh), g.bh, false, s, c0, c1);
+        my_r0 = min(max(s, 0), g.bh - 1);
+        my_r1 = min(max(s + 1, 0), g.bh - 1);
+        my_b0 = uint32_t(c0) << 16;  // pre-shifted: umulhi(b << 16, h) == (b * h) >> 16
+        my_b1 = uint32_t(c1) << 16;
+    }
+
+    // ---- fetch list: the strictly increasing sequence of source rows this band consumes ----
+    int nfetch;
+    {
+        int prev_r1 = __shfl_up_sync(0xffffffffu, my_r1, 1);
+        if (lane == 0) prev_r1 = -1;
+        const bool new0 = lane < nrows && my_r0 > prev_r1;
+        const bool new1 = lane < nrows && my_r1 > my_r0 && my_r1 > prev_r1;
+        const uint32_t m0 = __ballot_sync(0xffffffffu, new0), m1 = __ballot_sync(0xffffffffu, new1);
+        const uint32_t lt = (1u << lane) - 1u;
+        const int pos0 = __popc(m0 & lt) + __popc(m1 & lt);
+        if (new0) fetch_rows[warp][pos0] = my_r0;
+        if (new1) fetch_rows[warp][pos0 + (new0 ? 1 : 0)] = my_r1;
+        nfetch = __popc(m0) + __popc(m1);
+    }
+    __syncwarp();
+
+    const uint8_t* const src_seg = p.frames + g.f_off + (int64_t)g.by0 * g.pitch + seg_start;
+    auto issue = [&](int k) {  // lane 0: start the bulk copy of fetch number k into slot k % nslot
+        const int s = k % nslot;
+        const int row = fetch_rows[warp][k];
+        mbar_expect_tx(bar0 + 8u * s, seg_bytes);
+        bulk_g2s(ring0 + slot_stride * s, src_seg + (int64_t)row * g.pitch, seg_bytes, bar0 + 8u * s);
+    };
+    if (lane == 0) {
+        const int pre = min(nslot, nfetch);
+        for (int k = 0; k < pre; ++k) issue(k);
+    }
+
+    const uint32_t sel0 = p.sel[0], sel1 = p.sel[1], sel2 = p.sel[2];
+    const float m0f = p.m[0], m1f = p.m[1], m2f = p.m[2];
+    const float d0f = p.d[0], d1f = p.d[1], d2f = p.d[2];
+    const int64_t plane = (int64_t)p.out_h * p.out_w;
+    OutT* const out_crop = reinterpret_cast<OutT*>(p.out) + (int64_t)crop * 3 * plane;
+
+    uint32_t HA[JMAX][3], HB[JMAX][3];
+    int iA = -1, iB = -1;
+    int consumed = 0, cslot = 0;
+    uint32_t cparity = 0;
+
+    // wait for the next staged row, run the horizontal pass into H, refill the slot
+    auto consume_into = [&](uint32_t (&H)[JMAX][3]) {
+        mbar_wait(bar0 + 8u * cslot, cparity);
+        const uint8_t* slot = &ring[warp][0] + slot_stride * cslot;
+#pragma unroll
+        for (int j = 0; j < JMAX; ++j) {
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(slot + soa[j]);
+            const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+            const uint32_t lo = __funnelshift_r(w0, w1, sk8[j]);  // bytes o .. o+3
+            const uint32_t hi = __funnelshift_r(w1, w2, sk8[j]);  // bytes o+4 .. o+7
+            H[j][0] = __dp2a_lo(cf[j], __byte_perm(lo, hi, sel0), 0u) >> 4;
+            H[j][1] = __dp2a_lo(cf[j], __byte_perm(lo, hi, sel1), 0u) >> 4;
+            H[j][2] = __dp2a_lo(cf[j], __byte_perm(lo, hi, sel2), 0u) >> 4;
+        }
+        __syncwarp();  // every lane has read the slot before it is overwritten
+        if (lane == 0 && consumed + nslot < nfetch) issue(consumed + nslot);
+        ++consumed;
+        if (++cslot == nslot) { cslot = 0; cparity ^= 1u; }
+    };
+
+    for (int yy = 0; yy < nrows; ++yy) {
+        const int r0 = __shfl_sync(0xffffffffu, my_r0, yy);
+        const int r1 = __shfl_sync(0xffffffffu, my_r1, yy);
+        const uint32_t b0 = __shfl_sync(0xffffffffu, my_b0, yy);
+        const uint32_t b1 = __shfl_sync(0xffffffffu, my_b1, yy);
+        OutT* o = out_crop + (int64_t)(y_begin + yy) * p.out_w + ox0;
+
+        auto vertical = [&](const uint32_t (&Ht)[JMAX][3], const uint32_t (&Hb)[JMAX][3]) {
+#pragma unroll
+            for (int j = 0; j < JMAX; ++j) {
+                const uint32_t v0 = (__umulhi(b0, Ht[j][0]) + __umulhi(b1, Hb[j][0]) + 2u) >> 2;
+                const uint32_t v1 = (__umulhi(b0, Ht[j][1]) + __umulhi(b1, Hb[j][1]) + 2u) >> 2;
+                const uint32_t v2 = (__umulhi(b0, Ht[j][2]) + __umulhi(b1, Hb[j][2]) + 2u) >> 2;
+                store_out<OutT>(o + 32 * j, __fmul_rn(__fsub_rn((float)v0, m0f), d0f));
+                store_out<OutT>(o + plane + 32 * j, __fmul_rn(__fsub_rn((float)v1, m1f), d1f));
+                store_out<OutT>(o + 2 * plane + 32 * j, __fmul_rn(__fsub_rn((float)v2, m2f), d2f));
+            }
+        };
+        // Ht must hold source row r0, Hb row r1 (r1 == r0 only when the tap is clamped at an edge)
+        auto row_step = [&](uint32_t (&Ht)[JMAX][3], uint32_t (&Hb)[JMAX][3], int& it, int& ib) {
+            if (r0 != it) { consume_into(Ht); it = r0; }
+            if (r1 != r0) {
+                if (r1 != ib) { consume_into(Hb); ib = r1; }
+                vertical(Ht, Hb);
+            } else {
+                vertical(Ht, Ht);
+            }
+        };
+        // roles flip (no register copies) when the lower tap of the previous row is this row's upper tap
+        const bool a_is_top = (r0 == iA) || (r0 != iB);
+        if (a_is_top) row_step(HA, HB, iA, iB);
+        else row_step(HB, HA, iB, iA);
+    }
+}
+
+template <int JMAX>
+static void launch_fast_j(const K1Params& p, dim3 grid, cudaStream_t st, bool f32) {
+    if (f32) k1_crop_resize_normalize_tma<JMAX, float><<<grid, K1_WARPS * 32, 0, st>>>(p);
+    else k1_crop_resize_normalize_tma<JMAX, __nv_bfloat16><<<grid, K1_WARPS * 32, 0, st>>>(p);
+}
+
+// Returns false when no fast instantiation exists for this column-tile width.
+bool launch_k1_fast(const K1Params& p, int jmax, dim3 grid, cudaStream_t st, bool f32) {
+    switch (jmax) {
+        case 4: launch_fast_j<4>(p, grid, st, f32); return true;
+        case 5: launch_fast_j<5>(p, grid, st, f32); return true;
+        case 6: launch_fast_j<6>(p, grid, st, f32); return true;
+        case 7: launch_fast_j<7>(p, grid, st, f32); return true;
+        case 8: launch_fast_j<8>(p, grid, st, f32); return true;
+        default: return false;
+    }
+}
+
+}  // namespace nkbk

@@ -24,39 +24,11 @@
 //   Vertical: IMAD.HI with the coefficient pre-shifted by 16 gives
 //   (b*(H>>4))>>16 with the "+2" and the second tap folded into the addend,
 //   then >> 2, int->float, (v - mean255) * denom as two rounded fp32 ops.
-#include "nkbk_common.cuh"
-#include "k1_coef.h"
+#include "k1_common.cuh"
 
 namespace nkbk {
 
-constexpr int K1_WARPS = 4;
-
-struct K1Params {
-    const uint8_t* frames;
-    const int64_t* frame_desc;
-    const int32_t* boxes;
-    const int32_t* frame_idx;
-    int n, n_frames, mode, out_h, out_w, max_size;
-    float m[3], d[3];
-    float padf[3];       // normalised pad value per output channel
-    uint32_t padu[3];    // raw pad value per output channel
-    uint32_t sel[3];     // PRMT selectors per output channel (encode channel_swap)
-    void* out;
-    uint8_t* out_u8;
-    int32_t* bad_count;
-    int rows_per_warp;
-};
-
-template <typename OutT>
-__device__ __forceinline__ void store_out(OutT* p, float v);
-template <>
-__device__ __forceinline__ void store_out<float>(float* p, float v) {
-    __stcs(p, v);
-}
-template <>
-__device__ __forceinline__ void store_out<__nv_bfloat16>(__nv_bfloat16* p, float v) {
-    __stcs(reinterpret_cast<unsigned short*>(p), __bfloat16_as_ushort(__float2bfloat16_rn(v)));
-}
+bool launch_k1_fast(const K1Params& p, int jmax, dim3 grid, cudaStream_t st, bool f32);  // k1_fast.cu
 
 // Raw words of one source row for this lane's JMAX two-pixel windows, loaded one
 // row ahead of use so the DRAM/L2 latency hides behind the vertical pass.
@@ -108,9 +80,8 @@ __device__ __forceinline__ void convert_row(uint32_t (&H)[JMAX][3], const RawRow
 // GENERAL = false: stretch mode and out_w a multiple of the 32*JMAX column tile -> every lane
 // writes every column, no border handling, no uint8 side output.  GENERAL = true: everything.
 template <int JMAX, typename OutT, bool GENERAL, bool WRITE_U8>
-__global__ void __launch_bounds__(K1_WARPS * 32) k1_crop_resize_normalize(const K1Params p) {
+__device__ __forceinline__ void k1_process_crop(const K1Params& p, const int crop) {
     static_assert(GENERAL || !WRITE_U8, "uint8 side output only in the general variant");
-    const int crop = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int band = blockIdx.y * K1_WARPS + warp;
     const int y_begin = band * p.rows_per_warp;
@@ -119,21 +90,15 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_crop_resize_normalize(const 
     const int ox0 = blockIdx.z * (32 * JMAX) + lane;
 
     // ---- crop geometry (warp-uniform) ----
-    const int bx0 = __ldg(p.boxes + 4 * (int64_t)crop + 0), by0 = __ldg(p.boxes + 4 * (int64_t)crop + 1);
-    const int bx1 = __ldg(p.boxes + 4 * (int64_t)crop + 2), by1 = __ldg(p.boxes + 4 * (int64_t)crop + 3);
-    const int fi = __ldg(p.frame_idx + crop);
-    bool ok = fi >= 0 && fi < p.n_frames;
-    int64_t f_off = 0, pitch = 0;
-    int fh = 0, fw = 0;
-    if (ok) {
-        const int64_t* fd = p.frame_desc + 4 * (int64_t)fi;
-        f_off = __ldg(fd + 0);
-        fh = (int)__ldg(fd + 1);
-        fw = (int)__ldg(fd + 2);
-        pitch = __ldg(fd + 3);
+    const CropGeom g = load_geom(p, crop);
+    if (p.skip_fast) {  // the TMA kernel produced this crop already
+        uint32_t a, b, c;
+        int d;
+        if (fast_path_qualifies(p, g, a, b, c, d)) return;
     }
-    const int bw = bx1 - bx0, bh = by1 - by0;
-    ok = ok && bx0 >= 0 && by0 >= 0 && bx1 <= fw && by1 <= fh && bw >= 1 && bh >= 1 && fw >= 2;
+    const int bx0 = g.bx0, by0 = g.by0, bw = g.bw, bh = g.bh, fw = g.fw;
+    const int64_t f_off = g.f_off, pitch = g.pitch;
+    bool ok = g.ok;
     int dw = p.out_w, dh = p.out_h, top = 0, left = 0;
     if (GENERAL && ok && p.mode == NKBK_MODE_LETTERBOX)
         ok = letterbox_geometry(bh, bw, p.max_size, p.out_h, p.out_w, dh, dw, top, left);
@@ -318,14 +283,19 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_crop_resize_normalize(const 
     }
 }
 
+// grid.x strides over crops so the same kernel serves as the (small-grid) fix-up pass behind the TMA kernel
+template <int JMAX, typename OutT, bool GENERAL, bool WRITE_U8>
+__global__ void __launch_bounds__(K1_WARPS * 32) k1_crop_resize_normalize(const K1Params p) {
+    for (int crop = blockIdx.x; crop < p.n; crop += gridDim.x) k1_process_crop<JMAX, OutT, GENERAL, WRITE_U8>(p, crop);
+}
+
 template <int JMAX, typename OutT>
 static void launch_k1(const K1Params& p, dim3 grid, cudaStream_t st, bool general) {
+    (void)general;
     if (p.out_u8 != nullptr)
         k1_crop_resize_normalize<JMAX, OutT, true, true><<<grid, K1_WARPS * 32, 0, st>>>(p);
-    else if (general)
-        k1_crop_resize_normalize<JMAX, OutT, true, false><<<grid, K1_WARPS * 32, 0, st>>>(p);
     else
-        k1_crop_resize_normalize<JMAX, OutT, false, false><<<grid, K1_WARPS * 32, 0, st>>>(p);
+        k1_crop_resize_normalize<JMAX, OutT, true, false><<<grid, K1_WARPS * 32, 0, st>>>(p);
 }
 
 }  // namespace nkbk
@@ -373,6 +343,28 @@ extern "C" int nkbk_preprocess_crops(const void* frames_base, const int64_t* fra
     // rows per warp: split the height into blocks of <= 64 rows, 4 warps each
     const int nby = (out_h + 63) / 64;
     p.rows_per_warp = (out_h + nby * K1_WARPS - 1) / (nby * K1_WARPS);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool f32 = out_dtype == NKBK_F32;
+    p.skip_fast = 0;
+
+    // ---- fast path: A.Resize, output width a whole number of 32*J column tiles, no uint8 side output ----
+    // Crops whose frame rows are not 16-byte aligned or whose boxes are too wide for the shared-memory ring are
+    // left untouched by the TMA kernel and produced by the general kernel in a small-grid fix-up pass.
+    if (mode == NKBK_MODE_STRETCH && out_u8 == nullptr && out_w % 32 == 0) {
+        const int cols = out_w / 32;
+        int fj = 0;
+        for (int j = 8; j >= 4; --j)
+            if (cols % j == 0) { fj = j; break; }
+        if (fj != 0 && cols / fj <= 65535 && nby <= 65535) {
+            dim3 fgrid((unsigned)n, (unsigned)nby, (unsigned)(cols / fj));
+            if (launch_k1_fast(p, fj, fgrid, st, f32)) {
+                NKBK_CHECK_LAUNCH("k1_crop_resize_normalize_tma");
+                p.skip_fast = 1;
+            }
+        }
+    }
+
+    // ---- general path (everything), or the fix-up pass behind the fast kernel ----
     // column tile: 32*JMAX columns, JMAX in {4,7,8}; least padded wins, ties -> wider
     int best_j = 8, best_cost = 1 << 30;
     const int cands[3] = {8, 7, 4};
@@ -386,10 +378,9 @@ extern "C" int nkbk_preprocess_crops(const void* frames_base, const int64_t* fra
         set_error("nkbk_preprocess_crops: output %dx%d too large", out_h, out_w);
         return NKBK_E_SHAPE;
     }
-    dim3 grid((unsigned)n, (unsigned)nby, (unsigned)ntx);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const bool f32 = out_dtype == NKBK_F32;
-    const bool general = mode != NKBK_MODE_STRETCH || out_w % (32 * best_j) != 0;
+    const int gx = p.skip_fast ? (n < 148 ? n : 148) : n;
+    dim3 grid((unsigned)gx, (unsigned)nby, (unsigned)ntx);
+    const bool general = true;
     switch (best_j) {
         case 4: f32 ? launch_k1<4, float>(p, grid, st, general) : launch_k1<4, __nv_bfloat16>(p, grid, st, general); break;
         case 7: f32 ? launch_k1<7, float>(p, grid, st, general) : launch_k1<7, __nv_bfloat16>(p, grid, st, general); break;

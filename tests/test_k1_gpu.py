@@ -97,6 +97,9 @@ def test_k1_random_boxes_vs_oracle(cuda_device, kw):
     eu8, ef32 = preprocess_batch_c(frames, boxes, fidx, oracle_plan(plan))
     assert np.array_equal(u8.cpu().numpy(), eu8)
     assert_same_f32(out, ef32)
+    # without the uint8 side output the TMA fast path runs where it applies: same bits
+    out_fast, _ = run_k1(cuda_device, frames, boxes, fidx, plan, want_u8=False)
+    assert_same_f32(out_fast, ef32)
     # bf16 output is the RNE rounding of the same fp32 values
     outb, _ = run_k1(cuda_device, frames, boxes, fidx, plan, dtype=torch.bfloat16, want_u8=False)
     got_bits = outb.view(torch.int16).cpu().numpy().view(np.uint16)
@@ -119,6 +122,8 @@ def test_k1_edge_boxes_1080p(cuda_device):
     eu8, ef32 = preprocess_batch_c(frames, boxes, fidx, oracle_plan(plan))
     assert np.array_equal(u8.cpu().numpy(), eu8)
     assert_same_f32(out, ef32)
+    out_fast, _ = run_k1(cuda_device, frames, boxes, fidx, plan, want_u8=False)  # fast path + fix-up for wide boxes
+    assert_same_f32(out_fast, ef32)
     # identity crop: the resized pixels are the source pixels
     assert np.array_equal(u8[5].cpu().numpy(), frames[1][44:268, 33:257])
 
@@ -167,11 +172,52 @@ def test_k1_ragged_frames_with_pitch(cuda_device):
                                torch.tensor(fidx, dtype=torch.int32, device=dev), plan, out_u8=out_u8,
                                frame_desc=torch.tensor(desc, dtype=torch.int64, device=dev))
     torch.cuda.synchronize()
+    # same call without the side output: frames are not 16-byte aligned, so the fix-up pass produces every crop
+    out2 = ops.preprocess_crops(torch.from_numpy(flat).to(dev), torch.tensor(boxes, dtype=torch.int32, device=dev),
+                                torch.tensor(fidx, dtype=torch.int32, device=dev), plan,
+                                frame_desc=torch.tensor(desc, dtype=torch.int64, device=dev))
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)
     op = oracle_plan(plan)
     for i, (b, fi) in enumerate(zip(boxes, fidx)):
         eu8, ef = opre.preprocess_crop(frames[fi], b, op, "int")
         assert np.array_equal(out_u8[i].cpu().numpy(), eu8), (i, b, fi)
         assert np.array_equal(out[i].cpu().numpy().view(np.uint32), ef.view(np.uint32))
+
+
+def test_k1_fast_path_mixed_alignment_and_widths(cuda_device):
+    """One launch mixing crops the TMA kernel takes (aligned frames, narrow boxes) with crops it must leave to
+    the fix-up pass (frame with a 16-byte-misaligned pitch, boxes wider than the ring): every crop exactly once."""
+    from nkb_classification_b200 import ops, transforms as T
+    rng = np.random.default_rng(15)
+    dev = cuda_device
+    shapes = [(300, 1600, 4800), (200, 333, 1000), (120, 640, 1920 + 16)]   # (H, W, pitch): aligned / misaligned / aligned+padded
+    total = sum(h * p for h, w, p in shapes)
+    flat = np.zeros(total, dtype=np.uint8)
+    frames, desc, off = [], [], 0
+    for h, w, p in shapes:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        frames.append(img)
+        flat[off: off + h * p].reshape(h, p)[:, : w * 3] = img.reshape(h, w * 3)
+        desc.append((off, h, w, p))
+        off += h * p
+    boxes, fidx = [], []
+    for fi, (h, w, p) in enumerate(shapes):
+        for b in _random_boxes(rng, 40, h, w, wmin=1) + [(0, 0, w, h), (w - 1, 0, w, h), (0, 0, min(w, 1500), h),
+                                                         (max(0, w - 500), 0, w, h), (3, 3, 4, 4)]:
+            boxes.append(b)
+            fidx.append(fi)
+    for kw in (dict(out_h=224, out_w=224), dict(out_h=64, out_w=160), dict(out_h=96, out_w=384)):
+        plan = make_plan(T, **kw)
+        args = (torch.from_numpy(flat).to(dev), torch.tensor(boxes, dtype=torch.int32, device=dev),
+                torch.tensor(fidx, dtype=torch.int32, device=dev), plan)
+        out = torch.full((len(boxes), 3, plan.out_h, plan.out_w), float("nan"), device=dev)
+        ops.preprocess_crops(*args, out=out, frame_desc=torch.tensor(desc, dtype=torch.int64, device=dev))
+        torch.cuda.synchronize()
+        op = oracle_plan(plan)
+        for i, (b, fi) in enumerate(zip(boxes, fidx)):
+            _, ef = opre.preprocess_crop(frames[fi], b, op, "int")
+            assert np.array_equal(out[i].cpu().numpy().view(np.uint32), ef.view(np.uint32)), (kw, i, b, fi)
 
 
 def test_k1_full_size_batch_properties(cuda_device):
