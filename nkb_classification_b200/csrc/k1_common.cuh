@@ -81,6 +81,7 @@ __device__ __forceinline__ bool fast_path_qualifies(const K1Params& p, const Cro
     seg_bytes = e - s;
     slot_stride = (seg_bytes + 16u + 127u) & ~127u;  // +16: the unconditional third-word read may run past the span
     nslot = min(K1F_MAX_SLOTS, (int)(K1F_RING_BYTES / slot_stride));
+    if ((int64_t)g.bh * g.pitch >= (int64_t(1) << 31)) return false;  // row offsets are kept in 32 bits
     return nslot >= 2;
 }
 

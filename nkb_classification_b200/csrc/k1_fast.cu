@@ -125,36 +125,41 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_crop_resize_normalize_tma(co
     __syncwarp();
 
     const uint8_t* const src_seg = p.frames + g.f_off + (int64_t)g.by0 * g.pitch + seg_start;
-    auto issue = [&](int k) {  // lane 0: start the bulk copy of fetch number k into slot k % nslot
-        const int s = k % nslot;
-        const int row = fetch_rows[warp][k];
-        mbar_expect_tx(bar0 + 8u * s, seg_bytes);
-        bulk_g2s(ring0 + slot_stride * s, src_seg + (int64_t)row * g.pitch, seg_bytes, bar0 + 8u * s);
+    const uint32_t pitch32 = (uint32_t)g.pitch;  // qualifying crops have bh * pitch < 2^31 (fast_path_qualifies)
+    // lane 0: start the bulk copy of fetch number k into the slot at (slot_addr, bar_addr)
+    auto issue = [&](int k, uint32_t slot_addr, uint32_t bar_addr) {
+        const uint32_t row = (uint32_t)fetch_rows[warp][k];
+        mbar_expect_tx(bar_addr, seg_bytes);
+        bulk_g2s(slot_addr, src_seg + row * pitch32, seg_bytes, bar_addr);
     };
     if (lane == 0) {
         const int pre = min(nslot, nfetch);
-        for (int k = 0; k < pre; ++k) issue(k);
+        for (int k = 0; k < pre; ++k) issue(k, ring0 + slot_stride * k, bar0 + 8u * k);
     }
 
     const uint32_t sel0 = p.sel[0], sel1 = p.sel[1], sel2 = p.sel[2];
     const float m0f = p.m[0], m1f = p.m[1], m2f = p.m[2];
     const float d0f = p.d[0], d1f = p.d[1], d2f = p.d[2];
     const int64_t plane = (int64_t)p.out_h * p.out_w;
-    OutT* const out_crop = reinterpret_cast<OutT*>(p.out) + (int64_t)crop * 3 * plane;
+    OutT* o = reinterpret_cast<OutT*>(p.out) + (int64_t)crop * 3 * plane + (int64_t)y_begin * p.out_w + ox0;
+    const int out_w = p.out_w;
 
     uint32_t HA[JMAX][3], HB[JMAX][3];
     int iA = -1, iB = -1;
-    int consumed = 0, cslot = 0;
-    uint32_t cparity = 0;
+    int consumed = 0;
+    uint32_t cslot = 0, cparity = 0, cur_slot = ring0, cur_bar = bar0;
+    const uint32_t ring_end = ring0 + slot_stride * (uint32_t)nslot;
 
     // wait for the next staged row, run the horizontal pass into H, refill the slot
     auto consume_into = [&](uint32_t (&H)[JMAX][3]) {
-        mbar_wait(bar0 + 8u * cslot, cparity);
-        const uint8_t* slot = &ring[warp][0] + slot_stride * cslot;
+        mbar_wait(cur_bar, cparity);
 #pragma unroll
         for (int j = 0; j < JMAX; ++j) {
-            const uint32_t* w = reinterpret_cast<const uint32_t*>(slot + soa[j]);
-            const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+            const uint32_t a = cur_slot + soa[j];
+            uint32_t w0, w1, w2;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(a));
+            asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(a));
+            asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(w2) : "r"(a));
             const uint32_t lo = __funnelshift_r(w0, w1, sk8[j]);  // bytes o .. o+3
             const uint32_t hi = __funnelshift_r(w1, w2, sk8[j]);  // bytes o+4 .. o+7
             H[j][0] = __dp2a_lo(cf[j], __byte_perm(lo, hi, sel0), 0u) >> 4;
@@ -162,18 +167,19 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_crop_resize_normalize_tma(co
             H[j][2] = __dp2a_lo(cf[j], __byte_perm(lo, hi, sel2), 0u) >> 4;
         }
         __syncwarp();  // every lane has read the slot before it is overwritten
-        if (lane == 0 && consumed + nslot < nfetch) issue(consumed + nslot);
+        if (lane == 0 && consumed + nslot < nfetch) issue(consumed + nslot, cur_slot, cur_bar);
         ++consumed;
-        if (++cslot == nslot) { cslot = 0; cparity ^= 1u; }
+        cur_slot += slot_stride;
+        cur_bar += 8u;
+        if (cur_slot == ring_end) { cur_slot = ring0; cur_bar = bar0; cparity ^= 1u; }
     };
+    (void)cslot;
 
     for (int yy = 0; yy < nrows; ++yy) {
         const int r0 = __shfl_sync(0xffffffffu, my_r0, yy);
         const int r1 = __shfl_sync(0xffffffffu, my_r1, yy);
         const uint32_t b0 = __shfl_sync(0xffffffffu, my_b0, yy);
         const uint32_t b1 = __shfl_sync(0xffffffffu, my_b1, yy);
-        OutT* o = out_crop + (int64_t)(y_begin + yy) * p.out_w + ox0;
-
         auto vertical = [&](const uint32_t (&Ht)[JMAX][3], const uint32_t (&Hb)[JMAX][3]) {
 #pragma unroll
             for (int j = 0; j < JMAX; ++j) {
@@ -199,6 +205,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_crop_resize_normalize_tma(co
         const bool a_is_top = (r0 == iA) || (r0 != iB);
         if (a_is_top) row_step(HA, HB, iA, iB);
         else row_step(HB, HA, iB, iA);
+        o += out_w;
     }
 }
 

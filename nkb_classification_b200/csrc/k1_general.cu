@@ -91,11 +91,6 @@ __device__ __forceinline__ void k1_process_crop(const K1Params& p, const int cro
 
     // ---- crop geometry (warp-uniform) ----
     const CropGeom g = load_geom(p, crop);
-    if (p.skip_fast) {  // the TMA kernel produced this crop already
-        uint32_t a, b, c;
-        int d;
-        if (fast_path_qualifies(p, g, a, b, c, d)) return;
-    }
     const int bx0 = g.bx0, by0 = g.by0, bw = g.bw, bh = g.bh, fw = g.fw;
     const int64_t f_off = g.f_off, pitch = g.pitch;
     bool ok = g.ok;
@@ -283,10 +278,33 @@ __device__ __forceinline__ void k1_process_crop(const K1Params& p, const int cro
     }
 }
 
-// grid.x strides over crops so the same kernel serves as the (small-grid) fix-up pass behind the TMA kernel
+// Normal mode: one crop per blockIdx.x.  Fix-up mode (skip_fast, small grid behind the TMA kernel): the
+// block's threads test 128 crops at a time against the fast-path predicate in parallel and the block then
+// produces only the crops the TMA kernel left out -- a few microseconds when there are none.
 template <int JMAX, typename OutT, bool GENERAL, bool WRITE_U8>
 __global__ void __launch_bounds__(K1_WARPS * 32) k1_crop_resize_normalize(const K1Params p) {
-    for (int crop = blockIdx.x; crop < p.n; crop += gridDim.x) k1_process_crop<JMAX, OutT, GENERAL, WRITE_U8>(p, crop);
+    if (!p.skip_fast) {
+        for (int crop = blockIdx.x; crop < p.n; crop += gridDim.x)
+            k1_process_crop<JMAX, OutT, GENERAL, WRITE_U8>(p, crop);
+        return;
+    }
+    __shared__ int todo[K1_WARPS * 32];
+    __shared__ int ntodo;
+    for (int base = blockIdx.x * (K1_WARPS * 32); base < p.n; base += gridDim.x * (K1_WARPS * 32)) {
+        if (threadIdx.x == 0) ntodo = 0;
+        __syncthreads();
+        const int crop = base + threadIdx.x;
+        if (crop < p.n) {
+            const CropGeom g = load_geom(p, crop);
+            uint32_t a, b, c;
+            int d;
+            if (!fast_path_qualifies(p, g, a, b, c, d)) todo[atomicAdd(&ntodo, 1)] = crop;
+        }
+        __syncthreads();
+        const int nt = ntodo;
+        for (int i = 0; i < nt; ++i) k1_process_crop<JMAX, OutT, GENERAL, WRITE_U8>(p, todo[i]);
+        __syncthreads();
+    }
 }
 
 template <int JMAX, typename OutT>
@@ -378,7 +396,7 @@ extern "C" int nkbk_preprocess_crops(const void* frames_base, const int64_t* fra
         set_error("nkbk_preprocess_crops: output %dx%d too large", out_h, out_w);
         return NKBK_E_SHAPE;
     }
-    const int gx = p.skip_fast ? (n < 148 ? n : 148) : n;
+    const int gx = p.skip_fast ? ((n + 127) / 128 < 148 ? (n + 127) / 128 : 148) : n;
     dim3 grid((unsigned)gx, (unsigned)nby, (unsigned)ntx);
     const bool general = true;
     switch (best_j) {
