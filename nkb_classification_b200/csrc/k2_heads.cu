@@ -5,15 +5,19 @@
 //
 // This file is the exact-fp32 path (FFMA accumulate; TF32/bf16 tensor cores
 // would break the 1e-5 fp32 parity bar).  bf16 embeddings are widened on load.
+// Everything is deterministic: partial sums are combined in a fixed order.
 //
-//   k2_heads_forward   warp = 4 rows x 16 classes per pass, lanes split K with
-//                      128-bit loads; a 31-shuffle transposing reduction leaves
-//                      logit (row, class) = lane; per-(row, task) lanes then do
-//                      softmax / loss / dlogits in registers.
-//   k2_heads_dw        thread = one (or two, bf16) embedding columns, all NC
-//                      accumulators in registers, dlogits chunk broadcast from
-//                      shared memory; per-row-chunk partials (deterministic).
-//   k2_heads_reduce    fixed-order sum of the partials into the reduce buffer.
+//   k2_heads_forward   CTA = 4 rows; its 4 warps split K (chunks of 128 columns,
+//                      round-robin) with all embedding loads of a round issued
+//                      up front; 16 classes per pass; a 31-shuffle transposing
+//                      reduction + a fixed-order cross-warp sum leave the logits
+//                      in shared memory; per-(row, task) lanes then do softmax /
+//                      loss / dlogits.
+//   k2_heads_dw        CTA = 256 rows x 128 columns, 8 warps x 32 rows, thread =
+//                      4 columns x NCP classes in registers, dlogits broadcast
+//                      from shared memory; fixed-order cross-warp tree; the last
+//                      CTA to finish a column block sums the per-chunk partials
+//                      (again in fixed order) straight into the reduce buffer.
 //   k2_heads_finalize  divide by the (all-reduced) denominators, emit losses.
 //   k2_heads_demb      d(loss)/d(emb) for an unfrozen backbone.
 #include "nkbk_common.cuh"
@@ -23,10 +27,13 @@ namespace nkbk {
 constexpr int K2_MAX_TASKS = 64;
 constexpr int K2_MAX_NC = 1024;
 constexpr int K2_FWD_WARPS = 4;
-constexpr int K2_FWD_ROWS = 4;    // rows per warp
-constexpr int K2_FWD_NCB = 16;    // classes per pass
-constexpr int K2_DW_THREADS = 128;
-constexpr int K2_DW_ROWS = 128;   // rows per dW chunk
+constexpr int K2_FWD_ROWS = 4;     // rows per CTA
+constexpr int K2_FWD_NCB = 16;     // classes per pass
+constexpr int K2_FWD_ROUND = 4;    // K chunks per warp whose loads are issued together
+constexpr int K2_DW_WARPS = 8;
+constexpr int K2_DW_ROWS = 256;    // rows per dW chunk (32 per warp)
+constexpr int K2_DW_COLS = 128;    // columns per dW CTA (4 per lane)
+constexpr int K2_DW_NCB = 16;      // classes per dW pass
 
 struct K2Seg {
     int T;
@@ -34,25 +41,25 @@ struct K2Seg {
 };
 
 struct K2Layout {  // workspace carve-up, in floats
-    int fwd_blocks, fwd_warps_total;
-    int dw_chunks;
-    int64_t loss_part;  // [fwd_warps_total][2T]
+    int fwd_blocks, dw_chunks, dw_xblocks, dw_passes;
+    int64_t loss_part;  // [fwd_blocks][2T]
     int64_t dw_part;    // [dw_chunks][NC][D]
     int64_t db_part;    // [dw_chunks][NC]
+    int64_t counters;   // uint32 [dw_passes * dw_xblocks]
     int64_t total;
 };
 
 static K2Layout k2_layout(int B, int D, int NC, int T) {
     K2Layout L;
-    const int rows_per_block = K2_FWD_WARPS * K2_FWD_ROWS;
-    L.fwd_blocks = (B + rows_per_block - 1) / rows_per_block;
-    L.fwd_warps_total = L.fwd_blocks * K2_FWD_WARPS;
+    L.fwd_blocks = (B + K2_FWD_ROWS - 1) / K2_FWD_ROWS;
     L.dw_chunks = (B + K2_DW_ROWS - 1) / K2_DW_ROWS;
+    L.dw_xblocks = (D + K2_DW_COLS - 1) / K2_DW_COLS;
+    L.dw_passes = (NC + K2_DW_NCB - 1) / K2_DW_NCB;
     L.loss_part = 0;
-    L.dw_part = L.loss_part + (int64_t)L.fwd_warps_total * 2 * T;
-    L.dw_part = (L.dw_part + 3) & ~int64_t(3);
+    L.dw_part = (L.loss_part + (int64_t)L.fwd_blocks * 2 * T + 3) & ~int64_t(3);
     L.db_part = L.dw_part + (int64_t)L.dw_chunks * NC * D;
-    L.total = L.db_part + (int64_t)L.dw_chunks * NC;
+    L.counters = (L.db_part + (int64_t)L.dw_chunks * NC + 3) & ~int64_t(3);
+    L.total = L.counters + (int64_t)L.dw_passes * L.dw_xblocks;
     return L;
 }
 
@@ -93,7 +100,9 @@ struct K2FwdParams {
     float* out_logits;
     float* out_probs;
     float* dlogits;
-    float* loss_part;  // [warps_total][2T]
+    float* loss_part;      // [fwd_blocks][2T]
+    unsigned int* counters;  // zeroed here for the dW kernel that follows
+    int n_counters;
     int B, D, NC;
     int loss_kind;
     float gamma;
@@ -106,35 +115,48 @@ __global__ void __launch_bounds__(K2_FWD_WARPS * 32) k2_heads_forward(const K2Fw
     extern __shared__ float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = p.seg.T, NC = p.NC, D = p.D;
-    float* zs = smem + (size_t)warp * (K2_FWD_ROWS * NC + K2_FWD_ROWS * 2 * T);  // [ROWS][NC] logits
-    float* ls = zs + K2_FWD_ROWS * NC;                                          // [ROWS][2T] loss / denom terms
-    const int row0 = (blockIdx.x * K2_FWD_WARPS + warp) * K2_FWD_ROWS;
+    float* zs = smem;                                   // [ROWS][NC] logits
+    float* ls = zs + K2_FWD_ROWS * NC;                  // [ROWS][2T] loss / denominator terms
+    float* part = ls + K2_FWD_ROWS * 2 * T;             // [WARPS][64] per-warp partial logits
+    const int row0 = blockIdx.x * K2_FWD_ROWS;
     const ET* emb = static_cast<const ET*>(p.emb);
+    if (blockIdx.x == 0)
+        for (int i = threadIdx.x; i < p.n_counters; i += blockDim.x) p.counters[i] = 0u;
 
-    // ---- logits: passes of 16 classes, K split across lanes ----
+    const int nchunks = (D + 127) / 128;
     for (int cb = 0; cb < NC; cb += K2_FWD_NCB) {
         float acc[K2_FWD_ROWS * K2_FWD_NCB];
 #pragma unroll
         for (int i = 0; i < K2_FWD_ROWS * K2_FWD_NCB; ++i) acc[i] = 0.f;
-        for (int k = lane * 4; k < D; k += 128) {
-            float4 e[K2_FWD_ROWS];
+        for (int c0 = warp; c0 < nchunks; c0 += K2_FWD_WARPS * K2_FWD_ROUND) {
+            float4 e[K2_FWD_ROUND][K2_FWD_ROWS];
 #pragma unroll
-            for (int r = 0; r < K2_FWD_ROWS; ++r) {
-                const int row = min(row0 + r, p.B - 1);  // tail rows recompute the last row, never stored
-                e[r] = ld4(emb + (int64_t)row * D + k);
-            }
-#pragma unroll
-            for (int c = 0; c < K2_FWD_NCB; ++c) {
-                const int cls = min(cb + c, NC - 1);
-                const float4 w = ld4(p.W + (int64_t)cls * D + k);
+            for (int u = 0; u < K2_FWD_ROUND; ++u) {
+                const int k = (c0 + u * K2_FWD_WARPS) * 128 + lane * 4;
 #pragma unroll
                 for (int r = 0; r < K2_FWD_ROWS; ++r) {
-                    float a = acc[r * K2_FWD_NCB + c];
-                    a = fmaf(e[r].x, w.x, a);
-                    a = fmaf(e[r].y, w.y, a);
-                    a = fmaf(e[r].z, w.z, a);
-                    a = fmaf(e[r].w, w.w, a);
-                    acc[r * K2_FWD_NCB + c] = a;
+                    const int row = min(row0 + r, p.B - 1);  // tail rows recompute the last row, never stored
+                    e[u][r] = k < D ? ld4(emb + (int64_t)row * D + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < K2_FWD_ROUND; ++u) {
+                const int k = (c0 + u * K2_FWD_WARPS) * 128 + lane * 4;
+                if (k < D) {
+#pragma unroll
+                    for (int c = 0; c < K2_FWD_NCB; ++c) {
+                        const int cls = min(cb + c, NC - 1);
+                        const float4 w = ld4(p.W + (int64_t)cls * D + k);
+#pragma unroll
+                        for (int r = 0; r < K2_FWD_ROWS; ++r) {
+                            float a = acc[r * K2_FWD_NCB + c];
+                            a = fmaf(e[u][r].x, w.x, a);
+                            a = fmaf(e[u][r].y, w.y, a);
+                            a = fmaf(e[u][r].z, w.z, a);
+                            a = fmaf(e[u][r].w, w.w, a);
+                            acc[r * K2_FWD_NCB + c] = a;
+                        }
+                    }
                 }
             }
         }
@@ -142,18 +164,23 @@ __global__ void __launch_bounds__(K2_FWD_WARPS * 32) k2_heads_forward(const K2Fw
         float lo[32], hi[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) { lo[i] = acc[i]; hi[i] = acc[32 + i]; }
-        const float s0 = warp_reduce_scatter32(lo, lane);
-        const float s1 = warp_reduce_scatter32(hi, lane);
-        const int c = cb + (lane & 15);
-        if (c < NC) {
-            const float b = __ldg(p.bias + c);
-            zs[(lane >> 4) * NC + c] = s0 + b;
-            zs[(2 + (lane >> 4)) * NC + c] = s1 + b;
+        part[warp * 64 + lane] = warp_reduce_scatter32(lo, lane);
+        part[warp * 64 + 32 + lane] = warp_reduce_scatter32(hi, lane);
+        __syncthreads();
+        if (threadIdx.x < 64) {
+            const int c = cb + (threadIdx.x & 15), r = threadIdx.x >> 4;
+            if (c < NC) {
+                float sum = part[threadIdx.x];
+#pragma unroll
+                for (int w = 1; w < K2_FWD_WARPS; ++w) sum += part[w * 64 + threadIdx.x];  // fixed order
+                zs[r * NC + c] = sum + __ldg(p.bias + c);
+            }
         }
+        __syncthreads();
     }
-    __syncwarp();
+    if (warp != 0) return;
 
-    // ---- per (row, task): softmax, loss term, dlogits ----
+    // ---- per (row, task): softmax, loss term, dlogits (warp 0) ----
     for (int i = lane; i < K2_FWD_ROWS * 2 * T; i += 32) ls[i] = 0.f;
     __syncwarp();
     for (int idx = lane; idx < K2_FWD_ROWS * T; idx += 32) {
@@ -208,83 +235,143 @@ __global__ void __launch_bounds__(K2_FWD_WARPS * 32) k2_heads_forward(const K2Fw
         }
     }
     __syncwarp();
-    // fixed-order per-warp partial: sum over this warp's rows
-    float* part = p.loss_part + (int64_t)(blockIdx.x * K2_FWD_WARPS + warp) * 2 * T;
+    // fixed-order per-CTA partial: sum over this CTA's rows
+    float* lp = p.loss_part + (int64_t)blockIdx.x * 2 * T;
     for (int i = lane; i < 2 * T; i += 32) {
         float s = 0.f;
 #pragma unroll
         for (int r = 0; r < K2_FWD_ROWS; ++r) s += ls[r * 2 * T + i];
-        part[i] = s;
+        lp[i] = s;
     }
 }
 
-// ---- dW / db partials ------------------------------------------------------
-// VEC = embedding columns per thread (1 for fp32, 2 for bf16 pairs)
+// Sum `n` floats spaced `stride` apart in a fixed order with one warp (lane-strided partial sums, xor tree).
+__device__ __forceinline__ float warp_fixed_sum(const float* base, int n, int64_t stride, int lane) {
+    float s = 0.f;
+    for (int i = lane; i < n; i += 32) s += __ldcg(base + (int64_t)i * stride);
+    return warp_sum(s);
+}
+
+// ---- dW / db ---------------------------------------------------------------
 template <typename ET, int NCP>
-__global__ void __launch_bounds__(K2_DW_THREADS) k2_heads_dw(const ET* __restrict__ emb,
-                                                            const float* __restrict__ dlogits, int B, int D, int NC,
-                                                            int cls0, float* __restrict__ dw_part,
-                                                            float* __restrict__ db_part) {
-    __shared__ __align__(16) float dl[K2_DW_ROWS][NCP];
-    const int chunk = blockIdx.y;
+__global__ void __launch_bounds__(K2_DW_WARPS * 32) k2_heads_dw(
+    const ET* __restrict__ emb, const float* __restrict__ dlogits, int B, int D, int NC, int T, int cls0, int pass,
+    float* __restrict__ dw_part, float* __restrict__ db_part, const float* __restrict__ loss_part, int fwd_blocks,
+    unsigned int* __restrict__ counters, float* __restrict__ reduce_buf) {
+    // dl [256][NCP] while accumulating, then the cross-warp reduction buffer [4][NCP][128] (aliased)
+    __shared__ __align__(16) float sm[4 * NCP * K2_DW_COLS > K2_DW_ROWS * NCP ? 4 * NCP * K2_DW_COLS : K2_DW_ROWS * NCP];
+    __shared__ int is_last;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int chunk = blockIdx.y, chunks = gridDim.y;
     const int rbeg = chunk * K2_DW_ROWS, rows = min(K2_DW_ROWS, B - rbeg);
     const int ncls = min(NCP, NC - cls0);
+    float (*dl)[NCP] = reinterpret_cast<float (*)[NCP]>(sm);
     for (int i = threadIdx.x; i < K2_DW_ROWS * NCP; i += blockDim.x) {
         const int r = i / NCP, c = i - r * NCP;
         dl[r][c] = (r < rows && c < ncls) ? __ldg(dlogits + (int64_t)(rbeg + r) * NC + cls0 + c) : 0.f;
     }
     __syncthreads();
-    const int k = blockIdx.x * K2_DW_THREADS + threadIdx.x;
-    if (k < D) {
-        float acc[NCP];
+
+    const int k0 = blockIdx.x * K2_DW_COLS + lane * 4;
+    float acc[NCP][4];
 #pragma unroll
-        for (int c = 0; c < NCP; ++c) acc[c] = 0.f;
-        const ET* ep = emb + (int64_t)rbeg * D + k;
-#pragma unroll 4
-        for (int r = 0; r < rows; ++r) {
-            const float e = load_as_float(ep + (int64_t)r * D);
+    for (int c = 0; c < NCP; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f;
+    if (k0 < D) {
+        const int r_lo = warp * 32, r_hi = min(r_lo + 32, rows);
+        const ET* ep = emb + (int64_t)(rbeg + r_lo) * D + k0;
+#pragma unroll 8
+        for (int r = r_lo; r < r_hi; ++r, ep += D) {
+            const float4 e = ld4(ep);
 #pragma unroll
             for (int c4 = 0; c4 < NCP; c4 += 4) {
                 const float4 g = *reinterpret_cast<const float4*>(&dl[r][c4]);
-                acc[c4 + 0] = fmaf(g.x, e, acc[c4 + 0]);
-                acc[c4 + 1] = fmaf(g.y, e, acc[c4 + 1]);
-                acc[c4 + 2] = fmaf(g.z, e, acc[c4 + 2]);
-                acc[c4 + 3] = fmaf(g.w, e, acc[c4 + 3]);
+                const float gg[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    acc[c4 + q][0] = fmaf(gg[q], e.x, acc[c4 + q][0]);
+                    acc[c4 + q][1] = fmaf(gg[q], e.y, acc[c4 + q][1]);
+                    acc[c4 + q][2] = fmaf(gg[q], e.z, acc[c4 + q][2]);
+                    acc[c4 + q][3] = fmaf(gg[q], e.w, acc[c4 + q][3]);
+                }
             }
         }
-        float* o = dw_part + ((int64_t)chunk * NC + cls0) * D + k;
-#pragma unroll
-        for (int c = 0; c < NCP; ++c)
-            if (c < ncls) o[(int64_t)c * D] = acc[c];
     }
+    // db partial of this chunk (column block 0 only), before dl is overwritten
     if (blockIdx.x == 0 && threadIdx.x < ncls) {
         float s = 0.f;
         for (int r = 0; r < rows; ++r) s += dl[r][threadIdx.x];
         db_part[(int64_t)chunk * NC + cls0 + threadIdx.x] = s;
     }
+    __syncthreads();
+
+    // fixed-order cross-warp tree: (0+4) (1+5) (2+6) (3+7) -> (0+2) (1+3) -> (0+1)
+    float4 (*red)[NCP][32] = reinterpret_cast<float4 (*)[NCP][32]>(sm);  // [slot][class][lane]
+#pragma unroll
+    for (int half = K2_DW_WARPS / 2; half >= 1; half >>= 1) {
+        if (warp >= half && warp < 2 * half) {
+#pragma unroll
+            for (int c = 0; c < NCP; ++c)
+                red[warp - half][c][lane] = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+        }
+        __syncthreads();
+        if (warp < half) {
+#pragma unroll
+            for (int c = 0; c < NCP; ++c) {
+                const float4 v = red[warp][c][lane];
+                acc[c][0] += v.x; acc[c][1] += v.y; acc[c][2] += v.z; acc[c][3] += v.w;
+            }
+        }
+        __syncthreads();
+    }
+    const int64_t nW = (int64_t)NC * D;
+    if (warp == 0 && k0 < D) {
+        float* o = dw_part + ((int64_t)chunk * NC + cls0) * D + k0;
+#pragma unroll
+        for (int c = 0; c < NCP; ++c)
+            if (c < ncls)
+                *reinterpret_cast<float4*>(o + (int64_t)c * D) = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+    }
+
+    // ---- the last CTA of this column block sums the per-chunk partials into the reduce buffer ----
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(&counters[pass * gridDim.x + blockIdx.x], 1u);
+        is_last = (prev == (unsigned int)chunks - 1u);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const int cols = min(K2_DW_COLS, D - blockIdx.x * K2_DW_COLS);
+    for (int i = threadIdx.x; i < ncls * cols; i += blockDim.x) {
+        const int c = i / cols, col = i - c * cols;
+        const int64_t e = (int64_t)(cls0 + c) * D + blockIdx.x * K2_DW_COLS + col;
+        float s = 0.f;
+        for (int ch = 0; ch < chunks; ++ch) s += __ldcg(dw_part + (int64_t)ch * nW + e);
+        reduce_buf[e] = s;
+    }
+    if (blockIdx.x == 0) {
+        for (int c = threadIdx.x; c < ncls; c += blockDim.x) {
+            float s = 0.f;
+            for (int ch = 0; ch < chunks; ++ch) s += __ldcg(db_part + (int64_t)ch * NC + cls0 + c);
+            reduce_buf[nW + cls0 + c] = s;
+        }
+        if (pass == 0)  // loss sums / denominators: one warp per entry, fixed order
+            for (int j = warp; j < 2 * T; j += K2_DW_WARPS) {
+                const float s = warp_fixed_sum(loss_part + j, fwd_blocks, 2 * T, lane);
+                if (lane == 0) reduce_buf[nW + NC + j] = s;
+            }
+    }
+    if (threadIdx.x == 0) counters[pass * gridDim.x + blockIdx.x] = 0u;
 }
 
-// reduce_buf = [dW NC*D | db NC | loss_sum T | denom T]
-__global__ void __launch_bounds__(256) k2_heads_reduce(const float* __restrict__ dw_part,
-                                                       const float* __restrict__ db_part,
-                                                       const float* __restrict__ loss_part, int chunks,
-                                                       int warps_total, int NC, int D, int T, int have_grads,
-                                                       float* __restrict__ reduce_buf) {
-    const int64_t nW = (int64_t)NC * D;
-    const int64_t n = nW + NC + 2 * T;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        float s = 0.f;
-        if (i < nW) {
-            if (have_grads)
-                for (int ch = 0; ch < chunks; ++ch) s += dw_part[(int64_t)ch * nW + i];
-        } else if (i < nW + NC) {
-            if (have_grads)
-                for (int ch = 0; ch < chunks; ++ch) s += db_part[(int64_t)ch * NC + (i - nW)];
-        } else {
-            const int j = (int)(i - nW - NC);
-            for (int w = 0; w < warps_total; ++w) s += loss_part[(int64_t)w * 2 * T + j];
-        }
-        reduce_buf[i] = s;
+// forward-only calls: loss sums / denominators into the reduce buffer (gradients are zeroed by a memset)
+__global__ void __launch_bounds__(256) k2_heads_reduce_loss(const float* __restrict__ loss_part, int fwd_blocks, int T,
+                                                            float* __restrict__ out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int j = warp; j < 2 * T; j += 8) {
+        const float s = warp_fixed_sum(loss_part + j, fwd_blocks, 2 * T, lane);
+        if (lane == 0) out[j] = s;
     }
 }
 
@@ -415,9 +502,11 @@ extern "C" int nkbk_heads_fwd_loss_bwd(const void* emb, int emb_dtype, int B, in
     p.emb = emb; p.W = W_cat; p.bias = b_cat; p.labels = labels; p.class_weight = class_weight;
     p.out_logits = out_logits; p.out_probs = out_probs; p.dlogits = dlogits;
     p.loss_part = ws + L.loss_part;
+    p.counters = reinterpret_cast<unsigned int*>(ws + L.counters);
+    p.n_counters = L.dw_passes * L.dw_xblocks;
     p.B = B; p.D = D; p.NC = NC; p.loss_kind = loss_kind; p.gamma = gamma; p.ignore_index = ignore_index;
     p.seg = seg;
-    const size_t smem = (size_t)K2_FWD_WARPS * (K2_FWD_ROWS * NC + K2_FWD_ROWS * 2 * T) * sizeof(float);
+    const size_t smem = (size_t)(K2_FWD_ROWS * NC + K2_FWD_ROWS * 2 * T + K2_FWD_WARPS * 64) * sizeof(float);
     if (emb_dtype == NKBK_F32) {
         if (smem > 48 * 1024)
             NKBK_CHECK_CUDA(cudaFuncSetAttribute(k2_heads_forward<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -431,35 +520,35 @@ extern "C" int nkbk_heads_fwd_loss_bwd(const void* emb, int emb_dtype, int B, in
     }
     NKBK_CHECK_LAUNCH("k2_heads_forward");
 
-    const int have_grads = dlogits != nullptr;
-    if (have_grads) {
-        dim3 grid((D + K2_DW_THREADS - 1) / K2_DW_THREADS, L.dw_chunks);
-        for (int cls0 = 0; cls0 < NC; cls0 += 64) {
+    if (dlogits != nullptr) {
+        dim3 grid(L.dw_xblocks, L.dw_chunks);
+        float* dwp = ws + L.dw_part;
+        float* dbp = ws + L.db_part;
+        for (int pass = 0; pass < L.dw_passes; ++pass) {
+            const int cls0 = pass * K2_DW_NCB;
             const int rem = NC - cls0;
-            float* dwp = ws + L.dw_part;
-            float* dbp = ws + L.db_part;
-#define NKBK_DW(ET, NCP)                                                                                       \
-    k2_heads_dw<ET, NCP><<<grid, K2_DW_THREADS, 0, st>>>(static_cast<const ET*>(emb), dlogits, B, D, NC, cls0, \
-                                                         dwp, dbp)
+#define NKBK_DW(ET, NCP)                                                                                          \
+    k2_heads_dw<ET, NCP><<<grid, K2_DW_WARPS * 32, 0, st>>>(static_cast<const ET*>(emb), dlogits, B, D, NC, T, cls0, \
+                                                            pass, dwp, dbp, ws + L.loss_part, L.fwd_blocks,        \
+                                                            p.counters, reduce_buf)
             if (emb_dtype == NKBK_F32) {
-                if (rem <= 16) NKBK_DW(float, 16);
-                else if (rem <= 32) NKBK_DW(float, 32);
-                else NKBK_DW(float, 64);
+                if (rem <= 4) NKBK_DW(float, 4);
+                else if (rem <= 8) NKBK_DW(float, 8);
+                else if (rem <= 12) NKBK_DW(float, 12);
+                else NKBK_DW(float, 16);
             } else {
-                if (rem <= 16) NKBK_DW(__nv_bfloat16, 16);
-                else if (rem <= 32) NKBK_DW(__nv_bfloat16, 32);
-                else NKBK_DW(__nv_bfloat16, 64);
+                if (rem <= 4) NKBK_DW(__nv_bfloat16, 4);
+                else if (rem <= 8) NKBK_DW(__nv_bfloat16, 8);
+                else if (rem <= 12) NKBK_DW(__nv_bfloat16, 12);
+                else NKBK_DW(__nv_bfloat16, 16);
             }
 #undef NKBK_DW
             NKBK_CHECK_LAUNCH("k2_heads_dw");
         }
-    }
-    {
-        int blocks = (int)((nbuf + 255) / 256);
-        if (blocks > 148 * 8) blocks = 148 * 8;
-        k2_heads_reduce<<<blocks, 256, 0, st>>>(ws + L.dw_part, ws + L.db_part, ws + L.loss_part, L.dw_chunks,
-                                                L.fwd_warps_total, NC, D, T, have_grads, reduce_buf);
-        NKBK_CHECK_LAUNCH("k2_heads_reduce");
+    } else {
+        NKBK_CHECK_CUDA(cudaMemsetAsync(reduce_buf, 0, ((int64_t)NC * D + NC) * sizeof(float), st));
+        k2_heads_reduce_loss<<<1, 256, 0, st>>>(ws + L.loss_part, L.fwd_blocks, T, reduce_buf + (int64_t)NC * D + NC);
+        NKBK_CHECK_LAUNCH("k2_heads_reduce_loss");
     }
     return NKBK_OK;
 }
