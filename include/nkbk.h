@@ -135,10 +135,24 @@ int nkbk_heads_fwd_loss_bwd(const void* emb, int emb_dtype, int B, int D, const 
 int nkbk_heads_finalize(float* reduce_buf, int D, const int32_t* seg_offsets, int T, float* out_loss,
                         int64_t* cm_total, int64_t* cm_step, int64_t n_cm, void* stream);
 
-/* d(loss)/d(emb) [B][D] (emb_dtype) from dlogits and the (all-reduced,
- * not yet finalised or finalised -- denom is untouched by finalize) reduce_buf. */
+/* d(sum_t task_scale[t] * loss_t)/d(emb) [B][D] (out_dtype) from dlogits and the (all-reduced, finalised or not
+ * -- finalize leaves denom untouched) reduce_buf.  task_scale: optional device fp32 [T] (NULL = all ones, i.e. the
+ * gradient of the summed loss that MultitaskCriterion returns). */
 int nkbk_heads_demb(const float* dlogits, const float* reduce_buf, const float* W_cat, const int32_t* seg_offsets,
-                    int T, int B, int D, void* out_demb, int out_dtype, void* stream);
+                    int T, int B, int D, const float* task_scale, void* out_demb, int out_dtype, void* stream);
+
+/* Loss on already-computed logits: the reference's `criterion(pred, true)` call
+ * (FocalLoss.forward losses.py:59-94, nn.CrossEntropyLoss losses.py:155-159,
+ * MultitaskCriterion losses.py:110-147) when the heads were evaluated elsewhere.
+ *   logits    [B][ld] NKBK_F32 | NKBK_BF16, task t in columns seg_offsets[t]..
+ *   out_probs optional fp32 [B][NC]; dlogits optional fp32 [B][NC] = d(total loss)/d(logit)
+ *   out_loss  fp32 [T+1] per-task mean losses and their sum
+ *   workspace >= nkbk_loss_workspace_bytes(B, T) */
+int64_t nkbk_loss_workspace_bytes(int B, int T);
+int nkbk_loss_fwd_bwd(const void* logits, int dtype, int B, int ld, const int32_t* seg_offsets, int T,
+                      const int64_t* labels, int loss_kind, float gamma, const float* class_weight,
+                      int64_t ignore_index, float* out_probs, float* dlogits, float* out_loss, void* workspace,
+                      size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------
  * K3  per-task argmax + confusion-matrix accumulation

@@ -110,6 +110,73 @@ struct K2FwdParams {
     K2Seg seg;
 };
 
+// Per (row, task) softmax, loss term and dlogits for the K2_FWD_ROWS rows whose logits sit in shared
+// memory `zs` [ROWS][NC]; executed by one warp.  Writes this CTA's fixed-order loss / denominator partial.
+__device__ __forceinline__ void heads_row_epilogue(const K2FwdParams& p, const float* zs, float* ls, int row0, int lane,
+                                                   float* lp) {
+    const int T = p.seg.T, NC = p.NC;
+    for (int i = lane; i < K2_FWD_ROWS * 2 * T; i += 32) ls[i] = 0.f;
+    __syncwarp();
+    for (int idx = lane; idx < K2_FWD_ROWS * T; idx += 32) {
+        const int r = idx / T, t = idx - r * T;
+        const int row = row0 + r;
+        if (row >= p.B) continue;
+        const int c0 = p.seg.off[t], C = p.seg.off[t + 1] - c0;
+        const float* z = zs + r * NC + c0;
+        float mx = z[0];
+        for (int j = 1; j < C; ++j) mx = fmaxf(mx, z[j]);
+        float se = 0.f;
+        for (int j = 0; j < C; ++j) se += expf(z[j] - mx);
+        const float lse = mx + logf(se);
+        const int64_t y = p.labels ? p.labels[(int64_t)row * T + t] : p.ignore_index;
+        const bool keep = p.labels != nullptr && y != p.ignore_index && y >= 0 && y < C;
+        float q = 0.f;  // dlogit_j = q * (delta_jy - p_j)
+        if (keep) {
+            const float logpt = z[y] - lse;
+            const float a = p.class_weight ? __ldg(p.class_weight + c0 + (int)y) : 1.f;
+            float loss_i, den_i;
+            if (p.loss_kind == NKBK_LOSS_FOCAL) {
+                const float pt = expf(logpt);
+                const float om = 1.f - pt;
+                const float g = p.gamma;
+                float ft, dterm;  // ft = om^g ; dterm = g * pt * om^(g-1) * logpt
+                if (g == 0.f) { ft = 1.f; dterm = 0.f; }
+                else {
+                    const float pw1 = (g == 1.f) ? 1.f : ((g == 2.f) ? om : powf(om, g - 1.f));
+                    ft = pw1 * om;
+                    dterm = g * pt * pw1 * logpt;
+                }
+                loss_i = -a * ft * logpt;
+                q = a * (dterm - ft);
+                den_i = 1.f;
+            } else {
+                loss_i = -a * logpt;
+                q = -a;
+                den_i = a;
+            }
+            ls[r * 2 * T + t] = loss_i;
+            ls[r * 2 * T + T + t] = den_i;
+        }
+        float* zo = p.out_logits ? p.out_logits + (int64_t)row * NC + c0 : nullptr;
+        float* po = p.out_probs ? p.out_probs + (int64_t)row * NC + c0 : nullptr;
+        float* go = p.dlogits ? p.dlogits + (int64_t)row * NC + c0 : nullptr;
+        for (int j = 0; j < C; ++j) {
+            const float zj = z[j];
+            const float pj = expf(zj - lse);
+            if (zo) zo[j] = zj;
+            if (po) po[j] = pj;
+            if (go) go[j] = keep ? q * ((j == (int)y ? 1.f : 0.f) - pj) : 0.f;
+        }
+    }
+    __syncwarp();
+    for (int i = lane; i < 2 * T; i += 32) {  // fixed order over this CTA's rows
+        float s = 0.f;
+#pragma unroll
+        for (int r = 0; r < K2_FWD_ROWS; ++r) s += ls[r * 2 * T + i];
+        lp[i] = s;
+    }
+}
+
 template <typename ET>
 __global__ void __launch_bounds__(K2_FWD_WARPS * 32) k2_heads_forward(const K2FwdParams p) {
     extern __shared__ float smem[];
@@ -180,69 +247,7 @@ __global__ void __launch_bounds__(K2_FWD_WARPS * 32) k2_heads_forward(const K2Fw
     }
     if (warp != 0) return;
 
-    // ---- per (row, task): softmax, loss term, dlogits (warp 0) ----
-    for (int i = lane; i < K2_FWD_ROWS * 2 * T; i += 32) ls[i] = 0.f;
-    __syncwarp();
-    for (int idx = lane; idx < K2_FWD_ROWS * T; idx += 32) {
-        const int r = idx / T, t = idx - r * T;
-        const int row = row0 + r;
-        if (row >= p.B) continue;
-        const int c0 = p.seg.off[t], C = p.seg.off[t + 1] - c0;
-        const float* z = zs + r * NC + c0;
-        float mx = z[0];
-        for (int j = 1; j < C; ++j) mx = fmaxf(mx, z[j]);
-        float se = 0.f;
-        for (int j = 0; j < C; ++j) se += expf(z[j] - mx);
-        const float lse = mx + logf(se);
-        const int64_t y = p.labels ? p.labels[(int64_t)row * T + t] : p.ignore_index;
-        const bool keep = p.labels != nullptr && y != p.ignore_index && y >= 0 && y < C;
-        float q = 0.f;  // dlogit_j = q * (delta_jy - p_j)
-        if (keep) {
-            const float logpt = z[y] - lse;
-            const float a = p.class_weight ? __ldg(p.class_weight + c0 + (int)y) : 1.f;
-            float loss_i, den_i;
-            if (p.loss_kind == NKBK_LOSS_FOCAL) {
-                const float pt = expf(logpt);
-                const float om = 1.f - pt;
-                const float g = p.gamma;
-                float ft, dterm;  // ft = om^g ; dterm = g * pt * om^(g-1) * logpt
-                if (g == 0.f) { ft = 1.f; dterm = 0.f; }
-                else {
-                    const float pw1 = (g == 1.f) ? 1.f : ((g == 2.f) ? om : powf(om, g - 1.f));
-                    ft = pw1 * om;
-                    dterm = g * pt * pw1 * logpt;
-                }
-                loss_i = -a * ft * logpt;
-                q = a * (dterm - ft);
-                den_i = 1.f;
-            } else {
-                loss_i = -a * logpt;
-                q = -a;
-                den_i = a;
-            }
-            ls[r * 2 * T + t] = loss_i;
-            ls[r * 2 * T + T + t] = den_i;
-        }
-        float* zo = p.out_logits ? p.out_logits + (int64_t)row * NC + c0 : nullptr;
-        float* po = p.out_probs ? p.out_probs + (int64_t)row * NC + c0 : nullptr;
-        float* go = p.dlogits ? p.dlogits + (int64_t)row * NC + c0 : nullptr;
-        for (int j = 0; j < C; ++j) {
-            const float zj = z[j];
-            const float pj = expf(zj - lse);
-            if (zo) zo[j] = zj;
-            if (po) po[j] = pj;
-            if (go) go[j] = keep ? q * ((j == (int)y ? 1.f : 0.f) - pj) : 0.f;
-        }
-    }
-    __syncwarp();
-    // fixed-order per-CTA partial: sum over this CTA's rows
-    float* lp = p.loss_part + (int64_t)blockIdx.x * 2 * T;
-    for (int i = lane; i < 2 * T; i += 32) {
-        float s = 0.f;
-#pragma unroll
-        for (int r = 0; r < K2_FWD_ROWS; ++r) s += ls[r * 2 * T + i];
-        lp[i] = s;
-    }
+    heads_row_epilogue(p, zs, ls, row0, lane, p.loss_part + (int64_t)blockIdx.x * 2 * T);
 }
 
 // Sum `n` floats spaced `stride` apart in a fixed order with one warp (lane-strided partial sums, xor tree).
@@ -375,6 +380,47 @@ __global__ void __launch_bounds__(256) k2_heads_reduce_loss(const float* __restr
     }
 }
 
+// Loss on given logits (criterion(pred, true) of the reference API): one warp per 4 rows.
+template <typename LT>
+__global__ void __launch_bounds__(32) k2_loss_on_logits(const K2FwdParams p, const LT* __restrict__ logits, int ld) {
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x, NC = p.NC, T = p.seg.T;
+    float* zs = smem;
+    float* ls = zs + K2_FWD_ROWS * NC;
+    const int row0 = blockIdx.x * K2_FWD_ROWS;
+    for (int i = lane; i < K2_FWD_ROWS * NC; i += 32) {
+        const int r = i / NC, c = i - r * NC;
+        const int row = min(row0 + r, p.B - 1);
+        zs[i] = load_as_float(logits + (int64_t)row * ld + c);
+    }
+    __syncwarp();
+    heads_row_epilogue(p, zs, ls, row0, lane, p.loss_part + (int64_t)blockIdx.x * 2 * T);
+}
+
+// sums[2T] (loss sums, denominators) -> out_loss[T+1]; dlogits /= denom[task]
+__global__ void __launch_bounds__(256) k2_loss_normalise(float* __restrict__ dlogits, int B, int NC, const K2Seg seg,
+                                                         const float* __restrict__ sums, float* __restrict__ out_loss) {
+    const int T = seg.T;
+    if (dlogits != nullptr)
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)B * NC;
+             i += (int64_t)gridDim.x * blockDim.x) {
+            const int c = (int)(i % NC);
+            int t = 0;
+            while (t + 1 < T && c >= seg.off[t + 1]) ++t;
+            const float dn = sums[T + t];
+            dlogits[i] = dn > 0.f ? __fdiv_rn(dlogits[i], dn) : 0.f;
+        }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        float total = 0.f;
+        for (int t = 0; t < T; ++t) {
+            const float l = sums[T + t] > 0.f ? __fdiv_rn(sums[t], sums[T + t]) : 0.f;
+            out_loss[t] = l;
+            total += l;
+        }
+        out_loss[T] = total;
+    }
+}
+
 __global__ void __launch_bounds__(256) k2_heads_finalize(float* __restrict__ reduce_buf, int NC, int D, const K2Seg seg,
                                                          float* __restrict__ out_loss, int64_t* __restrict__ cm_total,
                                                          int64_t* __restrict__ cm_step, int64_t n_cm) {
@@ -419,6 +465,7 @@ __device__ __forceinline__ void st4<__nv_bfloat16>(__nv_bfloat16* p, float4 v) {
 
 template <typename OT>
 __global__ void __launch_bounds__(256) k2_heads_demb(const float* __restrict__ dlogits, const float* __restrict__ denom,
+                                                     const float* __restrict__ task_scale,
                                                      const float* __restrict__ W, const K2Seg seg, int NC, int D,
                                                      OT* __restrict__ out) {
     extern __shared__ float g[];  // [NC] normalised dlogits of this row
@@ -427,7 +474,9 @@ __global__ void __launch_bounds__(256) k2_heads_demb(const float* __restrict__ d
         int t = 0;
         while (t + 1 < seg.T && c >= seg.off[t + 1]) ++t;
         const float dn = denom[t];
-        g[c] = dn > 0.f ? __fdiv_rn(__ldg(dlogits + (int64_t)row * NC + c), dn) : 0.f;
+        float v = dn > 0.f ? __fdiv_rn(__ldg(dlogits + (int64_t)row * NC + c), dn) : 0.f;
+        if (task_scale != nullptr) v *= task_scale[t];
+        g[c] = v;
     }
     __syncthreads();
     for (int k = threadIdx.x * 4; k < D; k += blockDim.x * 4) {
@@ -553,6 +602,54 @@ extern "C" int nkbk_heads_fwd_loss_bwd(const void* emb, int emb_dtype, int B, in
     return NKBK_OK;
 }
 
+extern "C" int64_t nkbk_loss_workspace_bytes(int B, int T) {
+    if (B < 1) B = 1;
+    return ((int64_t)((B + K2_FWD_ROWS - 1) / K2_FWD_ROWS) * 2 * T + 2 * T) * (int64_t)sizeof(float);
+}
+
+extern "C" int nkbk_loss_fwd_bwd(const void* logits, int dtype, int B, int ld, const int32_t* seg_offsets, int T,
+                                 const int64_t* labels, int loss_kind, float gamma, const float* class_weight,
+                                 int64_t ignore_index, float* out_probs, float* dlogits, float* out_loss,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+    K2Seg seg;
+    int rc = fill_seg(seg, seg_offsets, T, "nkbk_loss_fwd_bwd");
+    if (rc) return rc;
+    const int NC = seg.off[T];
+    NKBK_CHECK_ARG(B >= 0 && ld >= NC, "nkbk_loss_fwd_bwd: B=%d ld=%d NC=%d", B, ld, NC);
+    NKBK_CHECK_ARG(dtype == NKBK_F32 || dtype == NKBK_BF16, "nkbk_loss_fwd_bwd: dtype=%d", dtype);
+    NKBK_CHECK_ARG(loss_kind == NKBK_LOSS_CE || loss_kind == NKBK_LOSS_FOCAL, "nkbk_loss_fwd_bwd: loss_kind=%d", loss_kind);
+    NKBK_CHECK_ARG(out_loss && workspace && labels, "nkbk_loss_fwd_bwd: NULL out_loss/workspace/labels");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (B == 0) {
+        NKBK_CHECK_CUDA(cudaMemsetAsync(out_loss, 0, (T + 1) * sizeof(float), st));
+        return NKBK_OK;
+    }
+    NKBK_CHECK_ARG(logits != nullptr, "nkbk_loss_fwd_bwd: NULL logits");
+    if ((int64_t)workspace_bytes < nkbk_loss_workspace_bytes(B, T)) {
+        set_error("nkbk_loss_fwd_bwd: workspace %zu < %lld bytes", workspace_bytes, (long long)nkbk_loss_workspace_bytes(B, T));
+        return NKBK_E_ARG;
+    }
+    const int blocks = (B + K2_FWD_ROWS - 1) / K2_FWD_ROWS;
+    float* ws = static_cast<float*>(workspace);
+    float* sums = ws + (int64_t)blocks * 2 * T;
+    K2FwdParams p;
+    p.emb = nullptr; p.W = nullptr; p.bias = nullptr; p.labels = labels; p.class_weight = class_weight;
+    p.out_logits = nullptr; p.out_probs = out_probs; p.dlogits = dlogits; p.loss_part = ws;
+    p.counters = nullptr; p.n_counters = 0;
+    p.B = B; p.D = 0; p.NC = NC; p.loss_kind = loss_kind; p.gamma = gamma; p.ignore_index = ignore_index; p.seg = seg;
+    const size_t smem = (size_t)(K2_FWD_ROWS * NC + K2_FWD_ROWS * 2 * T) * sizeof(float);
+    if (dtype == NKBK_F32) k2_loss_on_logits<float><<<blocks, 32, smem, st>>>(p, static_cast<const float*>(logits), ld);
+    else k2_loss_on_logits<__nv_bfloat16><<<blocks, 32, smem, st>>>(p, static_cast<const __nv_bfloat16*>(logits), ld);
+    NKBK_CHECK_LAUNCH("k2_loss_on_logits");
+    k2_heads_reduce_loss<<<1, 256, 0, st>>>(ws, blocks, T, sums);
+    NKBK_CHECK_LAUNCH("k2_heads_reduce_loss");
+    int nb = (int)(((int64_t)B * NC + 255) / 256);
+    if (nb > 148 * 8) nb = 148 * 8;
+    k2_loss_normalise<<<nb, 256, 0, st>>>(dlogits, B, NC, seg, sums, out_loss);
+    NKBK_CHECK_LAUNCH("k2_loss_normalise");
+    return NKBK_OK;
+}
+
 extern "C" int nkbk_heads_finalize(float* reduce_buf, int D, const int32_t* seg_offsets, int T, float* out_loss,
                                    int64_t* cm_total, int64_t* cm_step, int64_t n_cm, void* stream) {
     K2Seg seg;
@@ -571,8 +668,8 @@ extern "C" int nkbk_heads_finalize(float* reduce_buf, int D, const int32_t* seg_
 }
 
 extern "C" int nkbk_heads_demb(const float* dlogits, const float* reduce_buf, const float* W_cat,
-                               const int32_t* seg_offsets, int T, int B, int D, void* out_demb, int out_dtype,
-                               void* stream) {
+                               const int32_t* seg_offsets, int T, int B, int D, const float* task_scale,
+                               void* out_demb, int out_dtype, void* stream) {
     K2Seg seg;
     int rc = fill_seg(seg, seg_offsets, T, "nkbk_heads_demb");
     if (rc) return rc;
@@ -584,10 +681,10 @@ extern "C" int nkbk_heads_demb(const float* dlogits, const float* reduce_buf, co
     const float* denom = reduce_buf + (int64_t)NC * D + NC + T;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (out_dtype == NKBK_F32)
-        k2_heads_demb<float><<<B, 256, NC * sizeof(float), st>>>(dlogits, denom, W_cat, seg, NC, D,
+        k2_heads_demb<float><<<B, 256, NC * sizeof(float), st>>>(dlogits, denom, task_scale, W_cat, seg, NC, D,
                                                                  static_cast<float*>(out_demb));
     else
-        k2_heads_demb<__nv_bfloat16><<<B, 256, NC * sizeof(float), st>>>(dlogits, denom, W_cat, seg, NC, D,
+        k2_heads_demb<__nv_bfloat16><<<B, 256, NC * sizeof(float), st>>>(dlogits, denom, task_scale, W_cat, seg, NC, D,
                                                                          static_cast<__nv_bfloat16*>(out_demb));
     NKBK_CHECK_LAUNCH("k2_heads_demb");
     return NKBK_OK;

@@ -1,0 +1,103 @@
+"""Per-iteration accumulation with the reference's ``BaseLogger`` interface
+(nkb_classification/logging.py:218-294) and none of its per-step syncs.
+
+The reference does, per task and per step, ``true.cpu().tolist()``,
+``pred.softmax(..).cpu().tolist()``, ``pred.argmax(..).cpu().tolist()`` and
+``loss.item()`` -- (3T + T + 1) device->host synchronisations.  Here every step
+only appends device tensors (K2's fp32 probabilities, K3's predictions, the
+labels, the loss vector); ``get_epoch_results()`` performs ONE device->host copy
+per quantity per epoch and rebuilds exactly the reference's dict of lists, plus
+``"confusion"`` (K3's integer matrices) for ``compute_metrics``.
+
+(The reference's BaseLogger crashes for task="multi" -- it reads an attribute
+that is never set, logging.py:243; target names here come from ``classes``.)
+"""
+from __future__ import annotations
+
+from collections import defaultdict
+from typing import List, Optional
+
+import torch
+
+
+class BaseLogger:
+    def __init__(self, cfg, classes):
+        assert cfg.task in ("single", "multi")
+        self.cfg = cfg
+        self.task = cfg.task
+        self.classes = classes
+        self.target_names = None if self.task == "single" else sorted(classes)
+        self.fused = None  # set by the engine: the FusedHeads whose confusion counts belong to this epoch
+        self.init_iter_logs()
+
+    def init_iter_logs(self):
+        self.epoch_images_example = None
+        self._gt, self._conf, self._pred, self._loss = [], [], [], []
+        self._seg, self._names = None, None
+
+    # ---- fused path: everything stays on the device ----
+    def log_fused(self, out, labels: torch.Tensor):
+        """``out``: heads.HeadsOutput of this step; ``labels``: int64 [B, T] on the device."""
+        self._seg, self._names = out.seg, out.names
+        self._gt.append(labels)
+        self._conf.append(out.probs.clone())
+        self._pred.append(out.pred.clone())
+        self._loss.append(out.loss.detach().clone())
+
+    # ---- reference-compatible entry (pred / true / loss as the reference passes them) ----
+    def log_iter(self, pred, true, loss):
+        assert type(pred) == type(true)
+        if isinstance(pred, dict):
+            assert pred.keys() == true.keys()
+            names = list(pred.keys())
+            seg = [0]
+            for n in names:
+                seg.append(seg[-1] + pred[n].shape[1])
+            dev = pred[names[0]].device
+            self._seg, self._names = seg, names
+            self._gt.append(torch.stack([true[n].to(dev).reshape(-1) for n in names], 1))
+            self._conf.append(torch.cat([pred[n].detach().softmax(-1, dtype=torch.float32) for n in names], 1))
+            self._pred.append(torch.stack([pred[n].detach().argmax(-1) for n in names], 1).to(torch.int32))
+            self._loss.append(torch.stack([loss[n].detach().float() for n in names] + [loss["loss"].detach().float()]))
+        else:
+            self._seg, self._names = [0, pred.shape[1]], None
+            self._gt.append(true.to(pred.device).reshape(-1, 1))
+            self._conf.append(pred.detach().softmax(-1, dtype=torch.float32))
+            self._pred.append(pred.detach().argmax(-1).reshape(-1, 1).to(torch.int32))
+            l = loss.detach().float().reshape(1)
+            self._loss.append(torch.cat([l, l]))
+
+    def log_images_if_needed(self, images):
+        if self.epoch_images_example is None:
+            self.epoch_images_example = images.to("cpu")
+
+    def get_epoch_results(self):
+        """One D2H per quantity, then the reference's structure (logging.py:287-294)."""
+        if not self._gt:
+            empty = [] if self.task == "single" else defaultdict(list)
+            return {"running_loss": empty, "confidences": empty, "predictions": empty, "ground_truth": empty,
+                    "images": self.epoch_images_example}
+        gt = torch.cat(self._gt).cpu().numpy()
+        conf = torch.cat(self._conf).cpu().numpy()
+        pred = torch.cat(self._pred).cpu().numpy()
+        loss = torch.stack(self._loss).cpu().numpy()
+        seg, names = self._seg, self._names
+        res = {"images": self.epoch_images_example}
+        if names is None:
+            res["running_loss"] = loss[:, 0].tolist()
+            res["confidences"] = conf.tolist()
+            res["predictions"] = pred[:, 0].tolist()
+            res["ground_truth"] = gt[:, 0].tolist()
+        else:
+            rl, cf, pr, g = defaultdict(list), defaultdict(list), defaultdict(list), defaultdict(list)
+            for t, n in enumerate(names):
+                rl[n] = loss[:, t].tolist()
+                cf[n] = conf[:, seg[t]:seg[t + 1]].tolist()
+                pr[n] = pred[:, t].tolist()
+                g[n] = gt[:, t].tolist()
+            rl["loss"] = loss[:, len(names)].tolist()
+            res.update(running_loss=rl, confidences=cf, predictions=pr, ground_truth=g)
+        if self.fused is not None and self.fused.state["cm"] is not None:
+            cms = self.fused.confusion_matrices()
+            res["confusion"] = cms[0] if names is None else {n: cms[t] for t, n in enumerate(names)}
+        return res

@@ -215,14 +215,16 @@ def heads_finalize(bufs: HeadsBuffers, cm_total: Optional[torch.Tensor] = None,
 
 
 def heads_demb(bufs: HeadsBuffers, W_cat: torch.Tensor, out_dtype: torch.dtype = torch.float32,
-               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+               out: Optional[torch.Tensor] = None, task_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
     if bufs.dlogits is None:
         raise ValueError("buffers were created without gradients")
     if out is None:
         out = torch.empty((bufs.B, bufs.D), dtype=out_dtype, device=W_cat.device)
     seg, T, _ = _seg_array(bufs.seg)
+    if task_scale is not None and (task_scale.dtype != torch.float32 or task_scale.numel() != T or not task_scale.is_cuda):
+        raise ValueError("task_scale must be CUDA float32 [T]")
     check(lib().nkbk_heads_demb(_ptr(bufs.dlogits), _ptr(bufs.reduce_buf), _ptr(W_cat), seg, T, bufs.B, bufs.D,
-                                _ptr(out), _DT[out_dtype], _stream(W_cat.device)))
+                                _ptr(task_scale), _ptr(out), _DT[out_dtype], _stream(W_cat.device)))
     return out
 
 
@@ -254,3 +256,33 @@ def argmax_confusion(logits: torch.Tensor, seg_offsets: Sequence[int], labels: O
     check(lib().nkbk_argmax_confusion(_ptr(logits), _DT[logits.dtype], B, ld, seg, T, _ptr(labels), _ptr(out_pred),
                                       _ptr(cm), _stream(logits.device)))
     return out_pred, cm
+
+
+# --------------------------------------------------------------------------
+# loss on given logits (criterion(pred, true) of the reference API)
+# --------------------------------------------------------------------------
+def loss_fwd_bwd(logits: torch.Tensor, seg_offsets: Sequence[int], labels: torch.Tensor, loss_kind: int,
+                 gamma: float = 2.0, class_weight: Optional[torch.Tensor] = None, ignore_index: int = -100,
+                 want_probs: bool = False, want_grad: bool = True):
+    """Returns (loss [T+1] fp32, dlogits [B,NC] fp32 | None, probs [B,NC] fp32 | None)."""
+    _need_cuda("logits", logits)
+    _need_cuda("labels", labels)
+    if logits.dtype not in _DT or logits.dim() != 2 or logits.stride(1) != 1:
+        raise ValueError("logits must be [B,ld] float32 | bfloat16 with unit inner stride")
+    seg, T, NC = _seg_array(seg_offsets)
+    B = logits.shape[0]
+    ld = logits.stride(0) if B > 1 else logits.shape[1]
+    if labels.dtype != torch.int64 or not labels.is_contiguous() or labels.numel() != B * T:
+        raise ValueError("labels must be contiguous int64 [B,T]")
+    if class_weight is not None and (class_weight.dtype != torch.float32 or class_weight.numel() != NC
+                                     or not class_weight.is_cuda):
+        raise ValueError("class_weight must be CUDA float32 [NC]")
+    dev = logits.device
+    loss = torch.empty(T + 1, dtype=torch.float32, device=dev)
+    dl = torch.empty((B, NC), dtype=torch.float32, device=dev) if want_grad else None
+    pr = torch.empty((B, NC), dtype=torch.float32, device=dev) if want_probs else None
+    ws = torch.empty(max(16, int(lib().nkbk_loss_workspace_bytes(B, T))), dtype=torch.uint8, device=dev)
+    check(lib().nkbk_loss_fwd_bwd(_ptr(logits), _DT[logits.dtype], B, ld, seg, T, _ptr(labels), int(loss_kind),
+                                  float(gamma), _ptr(class_weight), int(ignore_index), _ptr(pr), _ptr(dl), _ptr(loss),
+                                  _ptr(ws), ws.numel(), _stream(dev)))
+    return loss, dl, pr

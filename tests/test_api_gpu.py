@@ -1,0 +1,274 @@
+"""The reference-facing API on the GPU: criterion objects, the data loader, train/val epochs and
+inference(), each checked against the CPU oracle on the same inputs."""
+import json
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import heads as oh
+from oracle import metrics as om
+from oracle import preprocess as opre
+
+pytestmark = pytest.mark.gpu
+
+MEAN, STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+
+
+def rel_err(got, exp):
+    got, exp = np.asarray(got, np.float64), np.asarray(exp, np.float64)
+    return np.abs(got - exp).max() / max(np.abs(exp).max(), 1e-30)
+
+
+CRIT_CASES = {
+    "focal_g1": {"type": "FocalLoss", "gamma": 1},
+    "focal_g2": {"type": "FocalLoss"},
+    "ce": {"type": "CrossEntropyLoss"},
+}
+
+
+@pytest.mark.parametrize("case", sorted(CRIT_CASES))
+def test_multitask_criterion_matches_reference_golden(cuda_device, golden_dir, case):
+    """get_loss(...)(pred, true) -> dict of losses + autograd gradients, vs the reference's own losses.py."""
+    from nkb_classification_b200 import losses
+    g = np.load(golden_dir / "heads_golden.npz")
+    dev = cuda_device
+    names = ["task0", "task1", "task2"]
+    crit = losses.get_loss(dict(CRIT_CASES[case], task="multi"), dev)
+    pred = {n: torch.from_numpy(g[f"{case}.f64.logits{t}"]).float().to(dev).requires_grad_(True) for t, n in enumerate(names)}
+    true = {n: torch.from_numpy(g["labels"][:, t]) for t, n in enumerate(names)}   # CPU labels, like the DataLoader gives
+    out = crit(pred, true)
+    assert list(out.keys()) == names + ["loss"]
+    out["loss"].backward()
+    exp = g[f"{case}.f64.loss"]
+    got = [float(out[n]) for n in names] + [float(out["loss"])]
+    assert rel_err(got, exp) <= 1e-5
+    # d loss / d logits from the oracle (fp64 autograd over the restated reference loss)
+    for t, n in enumerate(names):
+        z = torch.from_numpy(g[f"{case}.f64.logits{t}"]).requires_grad_(True)
+        y = torch.from_numpy(g["labels"][:, t])
+        l = oh.focal_loss(z, y, None, CRIT_CASES[case].get("gamma", 2.0)) if "Focal" in CRIT_CASES[case]["type"] \
+            else oh.cross_entropy(z, y)
+        l.backward()
+        assert rel_err(pred[n].grad.cpu().numpy(), z.grad.numpy()) <= 1e-5, n
+
+
+def test_single_task_criteria_with_weights(cuda_device, golden_dir):
+    from nkb_classification_b200 import losses
+    g = np.load(golden_dir / "heads_golden.npz")
+    dev = cuda_device
+    for t in range(3):
+        alpha = g[f"alpha{t}"]
+        z64 = torch.from_numpy(g[f"ce.f64.logits{t}"])
+        y = torch.from_numpy(g["labels"][:, t])
+        for cfg, ref in (
+            ({"type": "FocalLoss", "gamma": 0.5, "alpha": alpha.tolist(), "task": "single"},
+             lambda z: oh.focal_loss(z, y, torch.from_numpy(alpha).double(), 0.5)),
+            ({"type": "CrossEntropyLoss", "weight": alpha.tolist(), "task": "single"},
+             lambda z: oh.cross_entropy(z, y, torch.from_numpy(alpha).double())),
+        ):
+            crit = losses.get_loss(cfg, dev)
+            z = z64.float().to(dev).requires_grad_(True)
+            loss = crit(z, y.to(dev))
+            loss.backward()
+            zr = z64.clone().requires_grad_(True)
+            lr = ref(zr)
+            lr.backward()
+            assert rel_err(float(loss), float(lr)) <= 1e-5
+            assert rel_err(z.grad.cpu().numpy(), zr.grad.numpy()) <= 1e-5
+    # bf16 logits (autocast) stay within the bf16 bar
+    crit = losses.get_loss({"type": "FocalLoss", "gamma": 1, "task": "single"}, dev)
+    zb = torch.from_numpy(g["ce.f64.logits1"]).to(dev).to(torch.bfloat16)
+    lb = crit(zb, torch.from_numpy(g["labels"][:, 1]).to(dev))
+    ref = oh.focal_loss(zb.double().cpu(), torch.from_numpy(g["labels"][:, 1]), None, 1.0)
+    assert rel_err(float(lb), float(ref)) <= 1e-2
+
+
+class TinyBackbone(torch.nn.Module):
+    """Deterministic stand-in for timm.create_model(num_classes=0): [B,3,H,W] -> [B,num_features]."""
+    num_features = 16
+
+    def __init__(self):
+        super().__init__()
+        g = torch.Generator().manual_seed(3)
+        self.proj = torch.nn.Linear(3 * 4 * 4, 16)
+        with torch.no_grad():
+            self.proj.weight.copy_(torch.randn(16, 48, generator=g) * 0.2)
+            self.proj.bias.zero_()
+
+    def forward(self, x):
+        return self.proj(torch.nn.functional.adaptive_avg_pool2d(x, 4).flatten(1))
+
+
+def make_csv_dataset(root, n=22, seed=5):
+    import cv2
+    import pandas as pd
+    rng = np.random.default_rng(seed)
+    rows = []
+    for i in range(n):
+        h, w = int(rng.integers(30, 70)), int(rng.integers(30, 90))
+        cv2.imwrite(str(root / f"i{i}.png"), rng.integers(0, 256, (h, w, 3), dtype=np.uint8))
+        rows.append({"path": f"i{i}.png", "fold": "val", "color": ["red", "green", "blue"][int(rng.integers(0, 3))],
+                     "size": ["s", "l"][int(rng.integers(0, 2))]})
+    pd.DataFrame(rows).to_csv(root / "ann.csv", index=False)
+    return rows
+
+
+def oracle_images(root, rows, plan_kw):
+    import cv2
+    plan = opre.Plan(mean=MEAN, std=STD, **plan_kw)
+    out = []
+    for r in rows:
+        img = cv2.cvtColor(cv2.imread(str(root / r["path"])), cv2.COLOR_BGR2RGB)   # dataset.py:523-524
+        out.append(opre.preprocess_crop(img, (0, 0, img.shape[1], img.shape[0]), plan, "cv2")[1])
+    return np.stack(out)
+
+
+def cfg_ns(**kw):
+    base = dict(task="multi", target_names=["color", "size"], enable_mixed_presicion=False, log_gradients=False,
+                show_full_current_loss_in_terminal=False, disable_tqdm=True,
+                criterion={"task": "multi", "type": "FocalLoss", "gamma": 1})
+    base.update(kw)
+    return SimpleNamespace(**base)
+
+
+def build(tmp_path, dev, pipeline_kind="letterbox"):
+    from nkb_classification_b200 import dataset as D, losses, model as M, transforms as T
+    rows = make_csv_dataset(tmp_path)
+    if pipeline_kind == "letterbox":   # configs/multitask_config.py:130-140
+        pipe = T.Compose([T.LongestMaxSize(32, always_apply=True),
+                          T.PadIfNeeded(32, 32, always_apply=True, border_mode=T.BORDER_CONSTANT, value=0),
+                          T.Normalize(mean=MEAN, std=STD), T.ToTensorV2()])
+        plan_kw = dict(mode=opre.MODE_LETTERBOX, out_h=32, out_w=32, max_size=32)
+    else:
+        pipe = T.Compose([T.Resize(32, 32), T.Normalize(mean=MEAN, std=STD), T.ToTensorV2()])
+        plan_kw = dict(out_h=32, out_w=32)
+    data = {"type": "AnnotatedMultitaskDataset", "annotations_file": str(tmp_path / "ann.csv"),
+            "target_names": ["size", "color"], "fold": "val", "image_base_dir": str(tmp_path), "batch_size": 8,
+            "num_workers": 2, "shuffle": False, "device": str(dev)}
+    loader = D.get_dataset(data, pipe)
+    classes = loader.dataset.classes
+    cfg = cfg_ns()
+    model = M.get_model({"task": "multi", "model": TinyBackbone(), "pretrained": False, "backbone_dropout": 0.0,
+                         "classifier_dropout": 0.0, "classifier_initialization": "kaiming_normal_"}, classes, dev)
+    crit = losses.get_loss(cfg.criterion, dev)
+    return rows, loader, classes, cfg, model, crit, plan_kw
+
+
+def test_loader_yields_oracle_images(cuda_device, tmp_path):
+    rows, loader, classes, cfg, model, crit, plan_kw = build(tmp_path, cuda_device)
+    exp = oracle_images(tmp_path, rows, plan_kw)
+    got, tg = [], []
+    for img, target in loader:
+        assert img.is_cuda and img.dtype == torch.float32 and set(target) == {"color", "size"}
+        got.append(img.cpu().numpy())
+        tg.append(target["color"].numpy())
+    got = np.concatenate(got)
+    assert np.array_equal(got.view(np.uint32), exp.view(np.uint32))
+    c2i = loader.dataset.class_to_idx["color"]
+    assert np.concatenate(tg).tolist() == [c2i[r["color"]] for r in rows]
+
+
+def oracle_epoch(tmp_path, rows, classes, model_state, plan_kw, c2i, gamma=1.0):
+    """CPU restatement of val_epoch: oracle images -> same tiny backbone (CPU, fp64) -> oracle heads / loss."""
+    imgs = torch.from_numpy(oracle_images(tmp_path, rows, plan_kw)).double()
+    bb = TinyBackbone().double()
+    bb.load_state_dict({k[len("emb_model."):]: v.double() for k, v in model_state.items() if k.startswith("emb_model.")})
+    names = list(classes.keys())
+    Ws = [model_state[f"classifier.{n}.1.weight"].double() for n in names]
+    bs = [model_state[f"classifier.{n}.1.bias"].double() for n in names]
+    labels = torch.tensor([[c2i[n][r[n]] for n in names] for r in rows])
+    return imgs, bb, names, Ws, bs, labels
+
+
+def test_val_epoch_matches_oracle(cuda_device, tmp_path):
+    from nkb_classification_b200 import engine, logging as L, metrics as Mx
+    rows, loader, classes, cfg, model, crit, plan_kw = build(tmp_path, cuda_device)
+    state = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    logger = L.BaseLogger(cfg, classes)
+    res = engine.val_epoch(model, loader, crit, cuda_device, cfg, logger)
+    assert set(res) >= {"running_loss", "confidences", "predictions", "ground_truth", "images", "confusion"}
+    imgs, bb, names, Ws, bs, labels = oracle_epoch(tmp_path, rows, classes, state, plan_kw, loader.dataset.class_to_idx)
+    with torch.no_grad():
+        emb = bb(imgs)
+    ref_all = oh.heads_loss_fwd_bwd(emb, Ws, bs, labels, oh.LOSS_FOCAL, 1.0)
+    for t, n in enumerate(names):
+        z = ref_all["logits"][t].numpy()
+        assert res["ground_truth"][n] == labels[:, t].tolist()
+        assert res["predictions"][n] == om.argmax_first_fast(z).tolist()
+        assert rel_err(res["confidences"][n], ref_all["probs"][t].numpy()) <= 1e-5
+        cm = om.confusion_matrix(labels[:, t].numpy(), om.argmax_first_fast(z), z.shape[1])
+        assert np.array_equal(res["confusion"][n], cm)
+    # per-batch running losses (3 batches of 8, 8, 6)
+    for bi, (lo, hi) in enumerate(((0, 8), (8, 16), (16, 22))):
+        r = oh.heads_loss_fwd_bwd(emb[lo:hi], Ws, bs, labels[lo:hi], oh.LOSS_FOCAL, 1.0)
+        assert rel_err(res["running_loss"]["loss"][bi], float(r["total"])) <= 1e-5
+    m = Mx.compute_metrics(cfg, res)
+    exp_acc = np.mean([om.balanced_accuracy_from_cm(res["confusion"][n]) for n in cfg.target_names])
+    assert m["epoch_acc"] == exp_acc
+
+
+def test_train_epoch_updates_heads_like_the_oracle(cuda_device, tmp_path):
+    """One SGD epoch through train_epoch (autograd into the heads AND the backbone) == the same steps done with
+    torch fp64 on the CPU from the oracle's images."""
+    from nkb_classification_b200 import engine, logging as L, utils
+    rows, loader, classes, cfg, model, crit, plan_kw = build(tmp_path, cuda_device, pipeline_kind="stretch")
+    state = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    opt = utils.get_optimizer(model, {"type": "sgd", "lr": 0.05})
+    scaler = torch.amp.GradScaler("cuda", enabled=False)
+    logger = L.BaseLogger(cfg, classes)
+    res = engine.train_epoch(model, loader, opt, None, scaler, crit, cuda_device, cfg, logger)
+    assert len(res["running_loss"]["loss"]) == 3
+
+    imgs, bb, names, Ws, bs, labels = oracle_epoch(tmp_path, rows, classes, state, plan_kw, loader.dataset.class_to_idx)
+    params = [p for p in bb.parameters()] + Ws + bs
+    for p in Ws + bs:
+        p.requires_grad_(True)
+    ref_opt = torch.optim.SGD(params, lr=0.05)
+    ref_losses = []
+    for lo, hi in ((0, 8), (8, 16), (16, 22)):
+        ref_opt.zero_grad()
+        emb = bb(imgs[lo:hi])
+        total = sum(oh.focal_loss(torch.nn.functional.linear(emb, Ws[t], bs[t]), labels[lo:hi, t], None, 1.0)
+                    for t in range(len(names)))
+        total.backward()
+        ref_opt.step()
+        ref_losses.append(float(total))
+    assert rel_err(res["running_loss"]["loss"], ref_losses) <= 2e-5
+    new_state = model.state_dict()
+    for t, n in enumerate(names):
+        assert rel_err(new_state[f"classifier.{n}.1.weight"].cpu().numpy(), Ws[t].detach().numpy()) <= 2e-5
+        assert rel_err(new_state[f"classifier.{n}.1.bias"].cpu().numpy(), bs[t].detach().numpy()) <= 2e-5
+    assert rel_err(new_state["emb_model.proj.weight"].cpu().numpy(), bb.proj.weight.detach().numpy()) <= 2e-5
+    torch.jit.script(model)  # still scriptable after the heads were packed (train.py:66)
+
+
+def test_inference_writes_reference_csv(cuda_device, tmp_path):
+    import pandas as pd
+    from nkb_classification_b200 import dataset as D, inference as I, model as M, transforms as T
+    dev = cuda_device
+    img_dir = tmp_path / "imgs"
+    img_dir.mkdir()
+    rows = make_csv_dataset(img_dir, n=9, seed=8)
+    pipe = T.Compose([T.LongestMaxSize(32), T.PadIfNeeded(32, 32, border_mode=T.BORDER_CONSTANT, value=0),
+                      T.Normalize(mean=MEAN, std=STD), T.ToTensorV2()])
+    (img_dir / "ann.csv").unlink()
+    loader = D.get_inference_dataset({"folder_path": str(img_dir), "batch_size": 4, "num_workers": 0, "device": str(dev)}, pipe)
+    classes = {"color": ["blue", "green", "red"], "size": ["l", "s"]}
+    model = M.get_model({"task": "multi", "model": TinyBackbone(), "pretrained": False, "backbone_dropout": 0.0,
+                         "classifier_dropout": 0.0, "classifier_initialization": "kaiming_normal_"}, classes, dev)
+    cfg = SimpleNamespace(task="multi", target_names=["color", "size"], enable_mixed_presicion=False, disable_tqdm=True)
+    state = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    I.inference(model, loader, classes, str(tmp_path), dev, cfg)
+    table = pd.read_csv(tmp_path / "inference_annotations.csv")
+    assert list(table.columns) == ["color", "size", "path"] and len(table) == 9
+    order = [{"path": p.split("/")[-1]} for p in table["path"]]
+    imgs = torch.from_numpy(oracle_images(img_dir, order, dict(mode=opre.MODE_LETTERBOX, out_h=32, out_w=32, max_size=32))).double()
+    bb = TinyBackbone().double()
+    bb.load_state_dict({k[len("emb_model."):]: v.double() for k, v in state.items() if k.startswith("emb_model.")})
+    with torch.no_grad():
+        emb = bb(imgs)
+    for n in ("color", "size"):
+        z = torch.nn.functional.linear(emb, state[f"classifier.{n}.1.weight"].double(), state[f"classifier.{n}.1.bias"].double())
+        assert table[n].tolist() == [classes[n][i] for i in z.argmax(-1).tolist()]

@@ -1,0 +1,89 @@
+"""The N > 1 path on CPU: world_size-2 gloo processes exercise the frame sharding and the
+sum-then-normalise contract of the K4 exchange (oracle computes the local unnormalised sums)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import heads as oh
+from oracle import metrics as om
+
+
+def test_shard_range_is_balanced_and_contiguous():
+    from nkb_classification_b200.parallel import shard_frames, shard_range
+    for n in (0, 1, 7, 64, 65):
+        for world in (1, 2, 4, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    fidx = np.repeat(np.arange(10), 3)
+    fb, fe, mask = shard_frames(fidx, 10, 1, 4)
+    assert (fb, fe) == (3, 6) and mask.sum() == 9 and set(fidx[mask]) == {3, 4, 5}
+    with pytest.raises(ValueError):
+        shard_range(5, 2, 2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nkb_classification_b200 import ops
+    from nkb_classification_b200.parallel import shard_frames
+    g = torch.Generator().manual_seed(11)
+    F, per, D, classes = 6, 5, 32, (3, 4)
+    T, NC = len(classes), sum(classes)
+    B = F * per
+    emb = torch.randn(B, D, generator=g, dtype=torch.float64)
+    Ws = [torch.randn(c, D, generator=g, dtype=torch.float64) for c in classes]
+    bs = [torch.randn(c, generator=g, dtype=torch.float64) for c in classes]
+    labels = torch.stack([torch.randint(0, c, (B,), generator=g) for c in classes], 1)
+    labels[1, 0] = -100
+    fidx = np.repeat(np.arange(F), per)
+    _, _, mask = shard_frames(fidx, F, rank, world)
+    m = torch.from_numpy(mask)
+    part = oh.unnormalised_sums(emb[m], Ws, bs, labels[m], oh.LOSS_FOCAL, 1.0)
+    # pack exactly as nkbk.h documents the reduce buffer: [dW NC*D | db NC | loss_sum T | denom T]
+    n = int(ops.heads_reduce_buf_len(D, NC, T))
+    assert n == NC * D + NC + 2 * T
+    buf = torch.cat([torch.cat(part["dW_sum"]).reshape(-1), torch.cat(part["db_sum"]), torch.stack(part["loss_sum"]),
+                     torch.stack(part["denom"])])
+    assert buf.numel() == n
+    z = [torch.nn.functional.linear(emb[m], w, b) for w, b in zip(Ws, bs)]
+    cm = np.concatenate([om.confusion_matrix(labels[m][:, t].numpy(), z[t].argmax(-1).numpy(), c).reshape(-1)
+                         for t, c in enumerate(classes)])
+    cm_t = torch.from_numpy(cm)
+    dist.all_reduce(buf)       # the two payloads of nkbk_allreduce_heads
+    dist.all_reduce(cm_t)
+    denom = buf[NC * D + NC + T:]
+    loss = buf[NC * D + NC: NC * D + NC + T] / denom
+    seg = np.concatenate([[0], np.cumsum(classes)])
+    row_den = torch.repeat_interleave(denom, torch.tensor(classes))
+    dW = buf[: NC * D].reshape(NC, D) / row_den[:, None]
+    ref = oh.heads_loss_fwd_bwd(emb, Ws, bs, labels, oh.LOSS_FOCAL, 1.0)
+    np.testing.assert_allclose(loss.numpy(), [float(x) for x in ref["loss"]], rtol=1e-12)
+    np.testing.assert_allclose(dW.numpy(), torch.cat(ref["dW"]).numpy(), rtol=1e-10, atol=1e-14)
+    zf = [torch.nn.functional.linear(emb, w, b) for w, b in zip(Ws, bs)]
+    cm_ref = np.concatenate([om.confusion_matrix(labels[:, t].numpy(), zf[t].argmax(-1).numpy(), c).reshape(-1)
+                             for t, c in enumerate(classes)])
+    assert np.array_equal(cm_t.numpy(), cm_ref)
+    dist.destroy_process_group()
+    open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+
+
+def test_sharded_sums_reassemble_global_result_gloo(tmp_path):
+    world, port = 2, _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(world))
