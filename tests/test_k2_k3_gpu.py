@@ -220,3 +220,19 @@ def test_k2_k3_end_to_end_metrics_match_reference_golden(cuda_device, golden_dir
         accs.append(acc)
         off += C * C
     assert float(np.mean(accs)) == float(g["epoch_acc"])
+
+
+def test_sharded_equals_single_gpu_nccl(cuda_device):
+    """K4: needs >= 2 visible GPUs (gpurun --gpus 2); the 2-rank gloo twin of this test runs on CPU."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2 if n < 4 else 4
+    script = Path(__file__).resolve().parent / "dist_check.py"
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29671", str(script)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "DIST_CHECK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
