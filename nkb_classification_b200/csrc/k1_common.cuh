@@ -23,7 +23,8 @@ struct K1Params {
     void* out;
     uint8_t* out_u8;
     int32_t* bad_count;
-    int rows_per_warp;
+    int rows_per_warp;       // general kernel (<= 16)
+    int rows_per_warp_fast;  // TMA kernel (<= 32)
     int skip_fast;       // general kernel: skip crops the fast kernel has already produced
 };
 

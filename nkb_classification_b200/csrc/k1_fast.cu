@@ -50,14 +50,14 @@ template <int JMAX, typename OutT>
 __global__ void __launch_bounds__(K1_WARPS * 32) k1_crop_resize_normalize_tma(const K1Params p) {
     __shared__ __align__(128) uint8_t ring[K1_WARPS][K1F_RING_BYTES];
     __shared__ __align__(8) uint64_t bars[K1_WARPS][K1F_MAX_SLOTS];
-    __shared__ int fetch_rows[K1_WARPS][32];
+    __shared__ int fetch_rows[K1_WARPS][64];
 
     const int crop = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int band = blockIdx.y * K1_WARPS + warp;
-    const int y_begin = band * p.rows_per_warp;
+    const int y_begin = band * p.rows_per_warp_fast;
     if (y_begin >= p.out_h) return;
-    const int nrows = min(p.rows_per_warp, p.out_h - y_begin);
+    const int nrows = min(p.rows_per_warp_fast, p.out_h - y_begin);   // <= 32: one output row per lane
     const int ox0 = blockIdx.z * (32 * JMAX) + lane;
 
     const CropGeom g = load_geom(p, crop);

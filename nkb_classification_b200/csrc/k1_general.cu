@@ -364,6 +364,7 @@ extern "C" int nkbk_preprocess_crops(const void* frames_base, const int64_t* fra
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool f32 = out_dtype == NKBK_F32;
     p.skip_fast = 0;
+    p.rows_per_warp_fast = p.rows_per_warp;
 
     // ---- fast path: A.Resize, output width a whole number of 32*J column tiles, no uint8 side output ----
     // Crops whose frame rows are not 16-byte aligned or whose boxes are too wide for the shared-memory ring are
@@ -373,8 +374,11 @@ extern "C" int nkbk_preprocess_crops(const void* frames_base, const int64_t* fra
         int fj = 0;
         for (int j = 8; j >= 4; --j)
             if (cols % j == 0) { fj = j; break; }
-        if (fj != 0 && cols / fj <= 65535 && nby <= 65535) {
-            dim3 fgrid((unsigned)n, (unsigned)nby, (unsigned)(cols / fj));
+        // the TMA kernel amortises its per-band prologue over up to 32 rows per warp (128 per CTA)
+        const int fby = (out_h + 32 * K1_WARPS - 1) / (32 * K1_WARPS);
+        p.rows_per_warp_fast = (out_h + fby * K1_WARPS - 1) / (fby * K1_WARPS);
+        if (fj != 0 && cols / fj <= 65535 && fby <= 65535) {
+            dim3 fgrid((unsigned)n, (unsigned)fby, (unsigned)(cols / fj));
             if (launch_k1_fast(p, fj, fgrid, st, f32)) {
                 NKBK_CHECK_LAUNCH("k1_crop_resize_normalize_tma");
                 p.skip_fast = 1;

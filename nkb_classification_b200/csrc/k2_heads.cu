@@ -29,7 +29,7 @@ constexpr int K2_MAX_NC = 1024;
 constexpr int K2_FWD_WARPS = 4;
 constexpr int K2_FWD_ROWS = 4;     // rows per CTA
 constexpr int K2_FWD_NCB = 16;     // classes per pass
-constexpr int K2_FWD_ROUND = 4;    // K chunks per warp whose loads are issued together
+constexpr int K2_FWD_ROUND = 2;    // K chunks per warp whose loads are issued together
 constexpr int K2_DW_WARPS = 8;
 constexpr int K2_DW_ROWS = 256;    // rows per dW chunk (32 per warp)
 constexpr int K2_DW_COLS = 128;    // columns per dW CTA (4 per lane)
@@ -110,69 +110,98 @@ struct K2FwdParams {
     K2Seg seg;
 };
 
-// Per (row, task) softmax, loss term and dlogits for the K2_FWD_ROWS rows whose logits sit in shared
-// memory `zs` [ROWS][NC]; executed by one warp.  Writes this CTA's fixed-order loss / denominator partial.
+// Softmax, loss term and dlogits for the K2_FWD_ROWS rows whose logits sit in shared memory `zs` [ROWS][NC];
+// executed by one warp in four short stages so that no lane loops over expf():
+//   (row, task) lanes: max -> (row, class) lanes: e = exp(z - max) -> (row, task) lanes: sum, lse, loss term, q
+//   -> (row, class) lanes: p = exp(z - lse), dlogit = q * (delta - p).
+// `ls` is scratch of ROWS * (NC + 6 * T) floats.  Writes this CTA's fixed-order loss / denominator partial.
 __device__ __forceinline__ void heads_row_epilogue(const K2FwdParams& p, const float* zs, float* ls, int row0, int lane,
                                                    float* lp) {
     const int T = p.seg.T, NC = p.NC;
-    for (int i = lane; i < K2_FWD_ROWS * 2 * T; i += 32) ls[i] = 0.f;
-    __syncwarp();
+    float* es = ls;                                  // [ROWS][NC]   exp(z - max)
+    float* mxs = es + K2_FWD_ROWS * NC;              // [ROWS][T]    row max
+    float* lses = mxs + K2_FWD_ROWS * T;             // [ROWS][T]    log-sum-exp
+    float* qs = lses + K2_FWD_ROWS * T;              // [ROWS][T]    dlogit scale (0 when the row is ignored)
+    float* ys = qs + K2_FWD_ROWS * T;                // [ROWS][T]    label as float (-1 when ignored)
+    float* lt = ys + K2_FWD_ROWS * T;                // [ROWS][2T]   loss term, denominator term
     for (int idx = lane; idx < K2_FWD_ROWS * T; idx += 32) {
         const int r = idx / T, t = idx - r * T;
-        const int row = row0 + r;
-        if (row >= p.B) continue;
         const int c0 = p.seg.off[t], C = p.seg.off[t + 1] - c0;
         const float* z = zs + r * NC + c0;
         float mx = z[0];
         for (int j = 1; j < C; ++j) mx = fmaxf(mx, z[j]);
-        float se = 0.f;
-        for (int j = 0; j < C; ++j) se += expf(z[j] - mx);
-        const float lse = mx + logf(se);
-        const int64_t y = p.labels ? p.labels[(int64_t)row * T + t] : p.ignore_index;
-        const bool keep = p.labels != nullptr && y != p.ignore_index && y >= 0 && y < C;
-        float q = 0.f;  // dlogit_j = q * (delta_jy - p_j)
-        if (keep) {
-            const float logpt = z[y] - lse;
-            const float a = p.class_weight ? __ldg(p.class_weight + c0 + (int)y) : 1.f;
-            float loss_i, den_i;
-            if (p.loss_kind == NKBK_LOSS_FOCAL) {
-                const float pt = expf(logpt);
-                const float om = 1.f - pt;
-                const float g = p.gamma;
-                float ft, dterm;  // ft = om^g ; dterm = g * pt * om^(g-1) * logpt
-                if (g == 0.f) { ft = 1.f; dterm = 0.f; }
-                else {
-                    const float pw1 = (g == 1.f) ? 1.f : ((g == 2.f) ? om : powf(om, g - 1.f));
-                    ft = pw1 * om;
-                    dterm = g * pt * pw1 * logpt;
-                }
-                loss_i = -a * ft * logpt;
-                q = a * (dterm - ft);
-                den_i = 1.f;
-            } else {
-                loss_i = -a * logpt;
-                q = -a;
-                den_i = a;
-            }
-            ls[r * 2 * T + t] = loss_i;
-            ls[r * 2 * T + T + t] = den_i;
-        }
-        float* zo = p.out_logits ? p.out_logits + (int64_t)row * NC + c0 : nullptr;
-        float* po = p.out_probs ? p.out_probs + (int64_t)row * NC + c0 : nullptr;
-        float* go = p.dlogits ? p.dlogits + (int64_t)row * NC + c0 : nullptr;
-        for (int j = 0; j < C; ++j) {
-            const float zj = z[j];
-            const float pj = expf(zj - lse);
-            if (zo) zo[j] = zj;
-            if (po) po[j] = pj;
-            if (go) go[j] = keep ? q * ((j == (int)y ? 1.f : 0.f) - pj) : 0.f;
-        }
+        mxs[idx] = mx;
     }
     __syncwarp();
+    for (int idx = lane; idx < K2_FWD_ROWS * NC; idx += 32) {
+        const int r = idx / NC, c = idx - r * NC;
+        int t = 0;
+        while (t + 1 < T && c >= p.seg.off[t + 1]) ++t;
+        es[idx] = expf(zs[idx] - mxs[r * T + t]);
+    }
+    __syncwarp();
+    for (int idx = lane; idx < K2_FWD_ROWS * T; idx += 32) {
+        const int r = idx / T, t = idx - r * T;
+        const int row = row0 + r;
+        const int c0 = p.seg.off[t], C = p.seg.off[t + 1] - c0;
+        float se = 0.f;
+        for (int j = 0; j < C; ++j) se += es[r * NC + c0 + j];
+        const float lse = mxs[idx] + logf(se);
+        lses[idx] = lse;
+        float q = 0.f, loss_i = 0.f, den_i = 0.f, yf = -1.f;
+        if (row < p.B && p.labels != nullptr) {
+            const int64_t y = p.labels[(int64_t)row * T + t];
+            if (y != p.ignore_index && y >= 0 && y < C) {
+                const float logpt = zs[r * NC + c0 + (int)y] - lse;
+                const float a = p.class_weight ? __ldg(p.class_weight + c0 + (int)y) : 1.f;
+                if (p.loss_kind == NKBK_LOSS_FOCAL) {
+                    const float pt = expf(logpt);
+                    const float om = 1.f - pt;
+                    const float g = p.gamma;
+                    float ft, dterm;  // ft = om^g ; dterm = g * pt * om^(g-1) * logpt
+                    if (g == 0.f) { ft = 1.f; dterm = 0.f; }
+                    else {
+                        const float pw1 = (g == 1.f) ? 1.f : ((g == 2.f) ? om : powf(om, g - 1.f));
+                        ft = pw1 * om;
+                        dterm = g * pt * pw1 * logpt;
+                    }
+                    loss_i = -a * ft * logpt;
+                    q = a * (dterm - ft);
+                    den_i = 1.f;
+                } else {
+                    loss_i = -a * logpt;
+                    q = -a;
+                    den_i = a;
+                }
+                yf = (float)(int)y;
+            }
+        }
+        qs[idx] = q;
+        ys[idx] = yf;
+        lt[r * 2 * T + t] = loss_i;
+        lt[r * 2 * T + T + t] = den_i;
+    }
+    __syncwarp();
+    for (int idx = lane; idx < K2_FWD_ROWS * NC; idx += 32) {
+        const int r = idx / NC, c = idx - r * NC;
+        const int row = row0 + r;
+        if (row >= p.B) continue;
+        int t = 0;
+        while (t + 1 < T && c >= p.seg.off[t + 1]) ++t;
+        const float zj = zs[idx];
+        const float pj = expf(zj - lses[r * T + t]);
+        const int64_t o = (int64_t)row * NC + c;
+        if (p.out_logits) p.out_logits[o] = zj;
+        if (p.out_probs) p.out_probs[o] = pj;
+        if (p.dlogits) {
+            const float yf = ys[r * T + t];
+            p.dlogits[o] = yf >= 0.f ? qs[r * T + t] * (((float)(c - p.seg.off[t]) == yf ? 1.f : 0.f) - pj) : 0.f;
+        }
+    }
     for (int i = lane; i < 2 * T; i += 32) {  // fixed order over this CTA's rows
         float s = 0.f;
 #pragma unroll
-        for (int r = 0; r < K2_FWD_ROWS; ++r) s += ls[r * 2 * T + i];
+        for (int r = 0; r < K2_FWD_ROWS; ++r) s += lt[r * 2 * T + i];
         lp[i] = s;
     }
 }
@@ -183,8 +212,8 @@ __global__ void __launch_bounds__(K2_FWD_WARPS * 32) k2_heads_forward(const K2Fw
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = p.seg.T, NC = p.NC, D = p.D;
     float* zs = smem;                                   // [ROWS][NC] logits
-    float* ls = zs + K2_FWD_ROWS * NC;                  // [ROWS][2T] loss / denominator terms
-    float* part = ls + K2_FWD_ROWS * 2 * T;             // [WARPS][64] per-warp partial logits
+    float* ls = zs + K2_FWD_ROWS * NC;                  // epilogue scratch, ROWS * (NC + 6T)
+    float* part = ls + K2_FWD_ROWS * (NC + 6 * T);      // [WARPS][64] per-warp partial logits
     const int row0 = blockIdx.x * K2_FWD_ROWS;
     const ET* emb = static_cast<const ET*>(p.emb);
     if (blockIdx.x == 0)
@@ -211,17 +240,25 @@ __global__ void __launch_bounds__(K2_FWD_WARPS * 32) k2_heads_forward(const K2Fw
                 const int k = (c0 + u * K2_FWD_WARPS) * 128 + lane * 4;
                 if (k < D) {
 #pragma unroll
-                    for (int c = 0; c < K2_FWD_NCB; ++c) {
-                        const int cls = min(cb + c, NC - 1);
-                        const float4 w = ld4(p.W + (int64_t)cls * D + k);
+                    for (int ch = 0; ch < K2_FWD_NCB; ch += 8) {
+                        if (cb + ch >= NC) break;  // warp-uniform
+                        float4 w[8];
 #pragma unroll
-                        for (int r = 0; r < K2_FWD_ROWS; ++r) {
-                            float a = acc[r * K2_FWD_NCB + c];
-                            a = fmaf(e[u][r].x, w.x, a);
-                            a = fmaf(e[u][r].y, w.y, a);
-                            a = fmaf(e[u][r].z, w.z, a);
-                            a = fmaf(e[u][r].w, w.w, a);
-                            acc[r * K2_FWD_NCB + c] = a;
+                        for (int c = 0; c < 8; ++c)  // 8 weight loads in flight together
+                            w[c] = ld4(p.W + (int64_t)min(cb + ch + c, NC - 1) * D + k);
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            if (cb + ch + c < NC) {  // warp-uniform: padded classes skip their FFMAs
+#pragma unroll
+                                for (int r = 0; r < K2_FWD_ROWS; ++r) {
+                                    float a = acc[r * K2_FWD_NCB + ch + c];
+                                    a = fmaf(e[u][r].x, w[c].x, a);
+                                    a = fmaf(e[u][r].y, w[c].y, a);
+                                    a = fmaf(e[u][r].z, w[c].z, a);
+                                    a = fmaf(e[u][r].w, w[c].w, a);
+                                    acc[r * K2_FWD_NCB + ch + c] = a;
+                                }
+                            }
                         }
                     }
                 }
@@ -555,7 +592,7 @@ extern "C" int nkbk_heads_fwd_loss_bwd(const void* emb, int emb_dtype, int B, in
     p.n_counters = L.dw_passes * L.dw_xblocks;
     p.B = B; p.D = D; p.NC = NC; p.loss_kind = loss_kind; p.gamma = gamma; p.ignore_index = ignore_index;
     p.seg = seg;
-    const size_t smem = (size_t)(K2_FWD_ROWS * NC + K2_FWD_ROWS * 2 * T + K2_FWD_WARPS * 64) * sizeof(float);
+    const size_t smem = (size_t)(K2_FWD_ROWS * (2 * NC + 6 * T) + K2_FWD_WARPS * 64) * sizeof(float);
     if (emb_dtype == NKBK_F32) {
         if (smem > 48 * 1024)
             NKBK_CHECK_CUDA(cudaFuncSetAttribute(k2_heads_forward<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -637,7 +674,7 @@ extern "C" int nkbk_loss_fwd_bwd(const void* logits, int dtype, int B, int ld, c
     p.out_logits = nullptr; p.out_probs = out_probs; p.dlogits = dlogits; p.loss_part = ws;
     p.counters = nullptr; p.n_counters = 0;
     p.B = B; p.D = 0; p.NC = NC; p.loss_kind = loss_kind; p.gamma = gamma; p.ignore_index = ignore_index; p.seg = seg;
-    const size_t smem = (size_t)(K2_FWD_ROWS * NC + K2_FWD_ROWS * 2 * T) * sizeof(float);
+    const size_t smem = (size_t)(K2_FWD_ROWS * (2 * NC + 6 * T)) * sizeof(float);
     if (dtype == NKBK_F32) k2_loss_on_logits<float><<<blocks, 32, smem, st>>>(p, static_cast<const float*>(logits), ld);
     else k2_loss_on_logits<__nv_bfloat16><<<blocks, 32, smem, st>>>(p, static_cast<const __nv_bfloat16*>(logits), ld);
     NKBK_CHECK_LAUNCH("k2_loss_on_logits");
