@@ -1,0 +1,47 @@
+// Definitions shared by k2_heads.cu (exact-fp32 FFMA path) and k2_tc.cu (tcgen05 path for bf16 embeddings).
+#pragma once
+#include "nkbk_common.cuh"
+
+namespace nkbk {
+
+constexpr int K2_MAX_TASKS = 64;
+constexpr int K2_MAX_NC = 1024;
+constexpr int K2_FWD_WARPS = 4;
+constexpr int K2_FWD_ROWS = 4;     // rows per CTA
+constexpr int K2_FWD_NCB = 16;     // classes per pass
+constexpr int K2_FWD_ROUND = 2;    // K chunks per warp whose loads are issued together
+constexpr int K2_DW_WARPS = 8;
+constexpr int K2_DW_ROWS = 256;    // rows per dW chunk (32 per warp)
+constexpr int K2_DW_COLS = 128;    // columns per dW CTA (4 per lane)
+constexpr int K2_DW_NCB = 16;      // classes per dW pass
+
+struct K2Seg {
+    int T;
+    int off[K2_MAX_TASKS + 1];
+};
+
+struct K2FwdParams {
+    const void* emb;
+    const float* W;
+    const float* bias;
+    const int64_t* labels;
+    const float* class_weight;
+    float* out_logits;
+    float* out_probs;
+    float* dlogits;
+    float* loss_part;      // [fwd_blocks][2T]
+    unsigned int* counters;  // zeroed here for the dW kernel that follows
+    int n_counters;
+    int B, D, NC;
+    int loss_kind;
+    float gamma;
+    int64_t ignore_index;
+    K2Seg seg;
+};
+
+// k2_tc.cu: tcgen05 / TMEM / TMA forward for bf16 embeddings.  Returns the number of per-CTA loss partials it
+// will write (0 = shape not supported, caller falls back to the FFMA kernel), < 0 on error.
+int launch_k2_tc_forward(const K2FwdParams& p, void* wb_workspace, cudaStream_t st);
+int64_t k2_tc_workspace_floats(int D, int NC);
+
+}  // namespace nkbk

@@ -20,25 +20,9 @@
 //                      (again in fixed order) straight into the reduce buffer.
 //   k2_heads_finalize  divide by the (all-reduced) denominators, emit losses.
 //   k2_heads_demb      d(loss)/d(emb) for an unfrozen backbone.
-#include "nkbk_common.cuh"
+#include "k2_common.cuh"
 
 namespace nkbk {
-
-constexpr int K2_MAX_TASKS = 64;
-constexpr int K2_MAX_NC = 1024;
-constexpr int K2_FWD_WARPS = 4;
-constexpr int K2_FWD_ROWS = 4;     // rows per CTA
-constexpr int K2_FWD_NCB = 16;     // classes per pass
-constexpr int K2_FWD_ROUND = 2;    // K chunks per warp whose loads are issued together
-constexpr int K2_DW_WARPS = 8;
-constexpr int K2_DW_ROWS = 256;    // rows per dW chunk (32 per warp)
-constexpr int K2_DW_COLS = 128;    // columns per dW CTA (4 per lane)
-constexpr int K2_DW_NCB = 16;      // classes per dW pass
-
-struct K2Seg {
-    int T;
-    int off[K2_MAX_TASKS + 1];
-};
 
 struct K2Layout {  // workspace carve-up, in floats
     int fwd_blocks, dw_chunks, dw_xblocks, dw_passes;
@@ -46,6 +30,7 @@ struct K2Layout {  // workspace carve-up, in floats
     int64_t dw_part;    // [dw_chunks][NC][D]
     int64_t db_part;    // [dw_chunks][NC]
     int64_t counters;   // uint32 [dw_passes * dw_xblocks]
+    int64_t tc_w;       // bf16 copy of the head weights for the tcgen05 path
     int64_t total;
 };
 
@@ -59,7 +44,8 @@ static K2Layout k2_layout(int B, int D, int NC, int T) {
     L.dw_part = (L.loss_part + (int64_t)L.fwd_blocks * 2 * T + 3) & ~int64_t(3);
     L.db_part = L.dw_part + (int64_t)L.dw_chunks * NC * D;
     L.counters = (L.db_part + (int64_t)L.dw_chunks * NC + 3) & ~int64_t(3);
-    L.total = L.counters + (int64_t)L.dw_passes * L.dw_xblocks;
+    L.tc_w = (L.counters + (int64_t)L.dw_passes * L.dw_xblocks + 3) & ~int64_t(3);
+    L.total = L.tc_w + k2_tc_workspace_floats(D, NC);
     return L;
 }
 
@@ -90,25 +76,6 @@ __device__ __forceinline__ float warp_reduce_scatter32(float (&v)[32], int lane)
     }
     return v[0];
 }
-
-struct K2FwdParams {
-    const void* emb;
-    const float* W;
-    const float* bias;
-    const int64_t* labels;
-    const float* class_weight;
-    float* out_logits;
-    float* out_probs;
-    float* dlogits;
-    float* loss_part;      // [fwd_blocks][2T]
-    unsigned int* counters;  // zeroed here for the dW kernel that follows
-    int n_counters;
-    int B, D, NC;
-    int loss_kind;
-    float gamma;
-    int64_t ignore_index;
-    K2Seg seg;
-};
 
 // Softmax, loss term and dlogits for the K2_FWD_ROWS rows whose logits sit in shared memory `zs` [ROWS][NC];
 // executed by one warp in four short stages so that no lane loops over expf():
@@ -593,7 +560,16 @@ extern "C" int nkbk_heads_fwd_loss_bwd(const void* emb, int emb_dtype, int B, in
     p.B = B; p.D = D; p.NC = NC; p.loss_kind = loss_kind; p.gamma = gamma; p.ignore_index = ignore_index;
     p.seg = seg;
     const size_t smem = (size_t)(K2_FWD_ROWS * (2 * NC + 6 * T) + K2_FWD_WARPS * 64) * sizeof(float);
-    if (emb_dtype == NKBK_F32) {
+    int loss_parts = L.fwd_blocks;  // rows of the per-CTA loss / denominator partial table
+    int tc = 0;
+    if (emb_dtype == NKBK_BF16) {   // bf16 embeddings: tcgen05 / TMEM / TMA forward when the shape allows
+        tc = launch_k2_tc_forward(p, ws + L.tc_w, st);
+        if (tc < 0) return tc;
+        if (tc > 0) loss_parts = tc;
+    }
+    if (tc > 0) {
+        // done on the tensor cores
+    } else if (emb_dtype == NKBK_F32) {
         if (smem > 48 * 1024)
             NKBK_CHECK_CUDA(cudaFuncSetAttribute(k2_heads_forward<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  (int)smem));
@@ -604,7 +580,7 @@ extern "C" int nkbk_heads_fwd_loss_bwd(const void* emb, int emb_dtype, int B, in
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k2_heads_forward<__nv_bfloat16><<<L.fwd_blocks, K2_FWD_WARPS * 32, smem, st>>>(p);
     }
-    NKBK_CHECK_LAUNCH("k2_heads_forward");
+    if (tc == 0) NKBK_CHECK_LAUNCH("k2_heads_forward");
 
     if (dlogits != nullptr) {
         dim3 grid(L.dw_xblocks, L.dw_chunks);
@@ -615,7 +591,7 @@ extern "C" int nkbk_heads_fwd_loss_bwd(const void* emb, int emb_dtype, int B, in
             const int rem = NC - cls0;
 #define NKBK_DW(ET, NCP)                                                                                          \
     k2_heads_dw<ET, NCP><<<grid, K2_DW_WARPS * 32, 0, st>>>(static_cast<const ET*>(emb), dlogits, B, D, NC, T, cls0, \
-                                                            pass, dwp, dbp, ws + L.loss_part, L.fwd_blocks,        \
+                                                            pass, dwp, dbp, ws + L.loss_part, loss_parts,          \
                                                             p.counters, reduce_buf)
             if (emb_dtype == NKBK_F32) {
                 if (rem <= 4) NKBK_DW(float, 4);
@@ -633,7 +609,7 @@ extern "C" int nkbk_heads_fwd_loss_bwd(const void* emb, int emb_dtype, int B, in
         }
     } else {
         NKBK_CHECK_CUDA(cudaMemsetAsync(reduce_buf, 0, ((int64_t)NC * D + NC) * sizeof(float), st));
-        k2_heads_reduce_loss<<<1, 256, 0, st>>>(ws + L.loss_part, L.fwd_blocks, T, reduce_buf + (int64_t)NC * D + NC);
+        k2_heads_reduce_loss<<<1, 256, 0, st>>>(ws + L.loss_part, loss_parts, T, reduce_buf + (int64_t)NC * D + NC);
         NKBK_CHECK_LAUNCH("k2_heads_reduce_loss");
     }
     return NKBK_OK;

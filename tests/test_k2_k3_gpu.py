@@ -236,3 +236,32 @@ def test_sharded_equals_single_gpu_nccl(cuda_device):
                         "--master-addr", "127.0.0.1", "--master-port", "29671", str(script)],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "DIST_CHECK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+@pytest.mark.parametrize("B,D,classes", [
+    (1024, 768, (2, 3, 4, 7, 14)),     # BASELINE config 4: N padded to 32
+    (4096, 2048, (10,)),               # config 5 width in bf16: N padded to 16
+    (300, 128, (40, 20)),              # ragged last tile, N padded to 64
+])
+def test_k2_tcgen05_forward_bf16(cuda_device, B, D, classes, monkeypatch):
+    """bf16 embeddings take the tcgen05 / TMEM / TMA forward.  Against an fp64 oracle that sees the SAME bf16-rounded
+    operands the fp32-accumulated logits agree to ~1e-5; the FFMA path (tensor cores disabled) is the cross-check."""
+    g = torch.Generator().manual_seed(9)
+    emb = torch.randn(B, D, generator=g).to(torch.bfloat16)
+    Ws = [(torch.randn(c, D, generator=g) * (2.0 / D) ** 0.5) for c in classes]
+    bs = [torch.randn(c, generator=g) * 0.05 for c in classes]
+    labels = torch.stack([torch.randint(0, c, (B,), generator=g) for c in classes], 1)
+    labels[::19, 0] = -100
+    Wb = [w.to(torch.bfloat16).double() for w in Ws]
+    exp = oh.heads_loss_fwd_bwd(emb.double(), Wb, bs, labels, oh.LOSS_FOCAL, 1.0, dtype=torch.float64)
+    r = run_k2(cuda_device, emb, Ws, bs, labels, oh.LOSS_FOCAL, 1.0, emb_dtype=torch.bfloat16)
+    for t in range(len(classes)):
+        assert rel_err(r["logits"][t], exp["logits"][t].numpy()) <= 2e-5, t
+        assert rel_err(r["probs"][t], exp["probs"][t].numpy()) <= 2e-5, t
+        assert rel_err(r["dW"][t], exp["dW"][t].numpy()) <= 1e-4, t
+    assert rel_err(r["loss"][-1], float(exp["total"])) <= 2e-5
+    monkeypatch.setenv("NKBK_DISABLE_TCGEN05", "1")
+    f = run_k2(cuda_device, emb, Ws, bs, labels, oh.LOSS_FOCAL, 1.0, emb_dtype=torch.bfloat16)
+    monkeypatch.delenv("NKBK_DISABLE_TCGEN05")
+    for t in range(len(classes)):  # FFMA path keeps W in fp32: differs by the bf16 rounding of W only
+        assert rel_err(r["logits"][t], f["logits"][t]) <= 1e-2
