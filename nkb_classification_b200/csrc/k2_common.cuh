@@ -42,6 +42,6 @@ struct K2FwdParams {
 // k2_tc.cu: tcgen05 / TMEM / TMA forward for bf16 embeddings.  Returns the number of per-CTA loss partials it
 // will write (0 = shape not supported, caller falls back to the FFMA kernel), < 0 on error.
 int launch_k2_tc_forward(const K2FwdParams& p, void* wb_workspace, cudaStream_t st);
-int64_t k2_tc_workspace_floats(int D, int NC);
+int64_t k2_tc_workspace_floats(int B, int D, int NC);
 
 }  // namespace nkbk

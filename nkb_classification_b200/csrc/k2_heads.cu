@@ -45,7 +45,7 @@ static K2Layout k2_layout(int B, int D, int NC, int T) {
     L.db_part = L.dw_part + (int64_t)L.dw_chunks * NC * D;
     L.counters = (L.db_part + (int64_t)L.dw_chunks * NC + 3) & ~int64_t(3);
     L.tc_w = (L.counters + (int64_t)L.dw_passes * L.dw_xblocks + 3) & ~int64_t(3);
-    L.total = L.tc_w + k2_tc_workspace_floats(D, NC);
+    L.total = L.tc_w + k2_tc_workspace_floats(B, D, NC);
     return L;
 }
 

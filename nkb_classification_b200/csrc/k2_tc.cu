@@ -93,45 +93,56 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
 }
 
 struct TcSmem {  // carve-up of dynamic shared memory (after 1024-byte alignment)
-    uint32_t a_off, b_off, z_off, lt_off, bar_off, total;
+    uint32_t a_off, b_off, lt_off, bar_off, total;   // the logits rows z[128][npad+1] alias the stage buffers
 };
-__host__ __device__ inline TcSmem tc_smem_layout(int npad, int T) {
+__host__ __device__ inline TcSmem tc_smem_layout(int npad, int stages, int T) {
     TcSmem L;
     L.a_off = 0;
-    L.b_off = L.a_off + TC_STAGES * TC_BM * 128;
-    L.z_off = L.b_off + TC_STAGES * npad * 128;
-    L.lt_off = L.z_off + TC_BM * (npad + 1) * 4;
+    L.b_off = L.a_off + stages * TC_BM * 128;
+    uint32_t end = L.b_off + stages * npad * 128;
+    const uint32_t zbytes = TC_BM * (npad + 1) * 4;
+    if (end < zbytes) end = zbytes;
+    L.lt_off = (end + 15) & ~15u;
     L.bar_off = (L.lt_off + TC_BM * 2 * T * 4 + 15) & ~15u;
-    L.total = L.bar_off + (2 * TC_STAGES + 1) * 8 + 16;
+    L.total = L.bar_off + (2 * stages + 1) * 8 + 16;
     return L;
 }
 
-template <int NPAD>
+struct TcSplit {            // split-K bookkeeping (global workspace)
+    float* partial;         // [ksplit][B][NPAD] fp32 partial accumulators
+    unsigned int* counters; // [m tiles], zeroed by k2_tc_pack_weights
+};
+
+template <int NPAD, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 1) k2_tc_heads_forward(const __grid_constant__ CUtensorMap tm_emb,
                                                                    const __grid_constant__ CUtensorMap tm_w,
-                                                                   const K2FwdParams p) {
+                                                                   const K2FwdParams p, const TcSplit sp) {
     extern __shared__ uint8_t tc_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~uintptr_t(1023));
     const int T = p.seg.T, NC = p.NC;
-    const TcSmem L = tc_smem_layout(NPAD, T);
+    const TcSmem L = tc_smem_layout(NPAD, STAGES, T);
     const uint32_t sA = tc_smem_u32(smem + L.a_off), sB = tc_smem_u32(smem + L.b_off);
-    float* zs = reinterpret_cast<float*>(smem + L.z_off);     // [128][NPAD+1] logits
+    float* zs = reinterpret_cast<float*>(smem + L.a_off);     // [128][NPAD+1] logits (stage buffers are free by then)
     float* lt = reinterpret_cast<float*>(smem + L.lt_off);    // [128][2T] loss / denominator terms
     const uint32_t bars = tc_smem_u32(smem + L.bar_off);      // full[S], empty[S], tmem_full
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + L.bar_off + (2 * TC_STAGES + 1) * 8);
-    const uint32_t full0 = bars, empty0 = bars + 8 * TC_STAGES, tmem_full = bars + 16 * TC_STAGES;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + L.bar_off + (2 * STAGES + 1) * 8);
+    const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tmem_full = bars + 16 * STAGES;
+    __shared__ int s_is_last;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * TC_BM;
-    const int kblocks = p.D / TC_BK;
+    const int ks = gridDim.y, ksi = blockIdx.y;
+    const int kblocks_all = p.D / TC_BK;
+    const int kb_begin = (int)((int64_t)kblocks_all * ksi / ks), kb_end = (int)((int64_t)kblocks_all * (ksi + 1) / ks);
+    const int kblocks = kb_end - kb_begin;   // >= 1 (the host keeps ks <= kblocks_all)
     constexpr uint32_t kTmemCols = NPAD < 32 ? 32 : NPAD;
     constexpr uint32_t kStageBytes = TC_BM * 128 + NPAD * 128;
 
-    if (blockIdx.x == 0 && p.counters != nullptr)
+    if (blockIdx.x == 0 && blockIdx.y == 0 && p.counters != nullptr)
         for (int i = threadIdx.x; i < p.n_counters; i += blockDim.x) p.counters[i] = 0u;
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) {
+        for (int s = 0; s < STAGES; ++s) {
             tc_mbar_init(full0 + 8 * s, 1);
             tc_mbar_init(empty0 + 8 * s, 1);
         }
@@ -154,13 +165,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k2_tc_heads_forward(const __gri
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            for (int kb = 0; kb < kblocks; ++kb) {
-                const int s = kb % TC_STAGES;
-                const uint32_t ph = (kb / TC_STAGES) & 1;
+            for (int i = 0; i < kblocks; ++i) {
+                const int s = i % STAGES;
+                const uint32_t ph = (i / STAGES) & 1;
                 tc_mbar_wait(empty0 + 8 * s, ph ^ 1);
                 tc_mbar_expect_tx(full0 + 8 * s, kStageBytes);
-                tc_tma_load_2d(sA + s * (TC_BM * 128), &tm_emb, full0 + 8 * s, kb * TC_BK, m0);
-                tc_tma_load_2d(sB + s * (NPAD * 128), &tm_w, full0 + 8 * s, kb * TC_BK, 0);
+                tc_tma_load_2d(sA + s * (TC_BM * 128), &tm_emb, full0 + 8 * s, (kb_begin + i) * TC_BK, m0);
+                tc_tma_load_2d(sB + s * (NPAD * 128), &tm_w, full0 + 8 * s, (kb_begin + i) * TC_BK, 0);
             }
         }
     } else if (warp == 1) {
@@ -169,90 +180,123 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k2_tc_heads_forward(const __gri
         constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NPAD >> 3) << 17) |
                                    ((uint32_t)(TC_BM >> 4) << 24);
         if (lane == 0) {
-            for (int kb = 0; kb < kblocks; ++kb) {
-                const int s = kb % TC_STAGES;
-                const uint32_t ph = (kb / TC_STAGES) & 1;
+            for (int i = 0; i < kblocks; ++i) {
+                const int s = i % STAGES;
+                const uint32_t ph = (i / STAGES) & 1;
                 tc_mbar_wait(full0 + 8 * s, ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint64_t adesc = tc_smem_desc(sA + s * (TC_BM * 128));
                 const uint64_t bdesc = tc_smem_desc(sB + s * (NPAD * 128));
 #pragma unroll
                 for (int k = 0; k < TC_BK / 16; ++k)  // advance 32 bytes (= 2 x 16 B) along K inside the swizzle row
-                    tc_mma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    tc_mma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (i | k) != 0);
                 tc_commit(empty0 + 8 * s);   // frees the stage once these MMAs have read it
             }
             tc_commit(tmem_full);            // accumulator complete
         }
     } else {
-        // ===== epilogue: TMEM -> registers -> shared rows -> softmax / loss / dlogits =====
+        // ===== epilogue: TMEM -> registers -> (split-K: partials, last CTA sums) -> softmax / loss / dlogits =====
         const int q = warp & 3;                         // TMEM lane quarter this warp may access
         const int r = q * 32 + lane;                    // row inside the tile
         const int row = m0 + r;
+        const int e = threadIdx.x - 64;                 // 0..127 over the epilogue warps
         tc_mbar_wait(tmem_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         float* z = zs + r * (NPAD + 1);
+        bool active = true;
+        if (ks == 1) {
 #pragma unroll
-        for (int c0 = 0; c0 < NPAD; c0 += 16) {
-            float v[16];
-            tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
+            for (int c0 = 0; c0 < NPAD; c0 += 16) {
+                float v[16];
+                tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-                if (c0 + i < NC) z[c0 + i] = v[i] + __ldg(p.bias + c0 + i);
-        }
-        float* my_lt = lt + r * 2 * T;
-        for (int t = 0; t < T; ++t) {
-            float loss_i = 0.f, den_i = 0.f;
-            if (row < p.B) {
-                const int c0 = p.seg.off[t], C = p.seg.off[t + 1] - c0;
-                const float* zt = z + c0;
-                float mx = zt[0];
-                for (int j = 1; j < C; ++j) mx = fmaxf(mx, zt[j]);
-                float se = 0.f;
-                for (int j = 0; j < C; ++j) se += expf(zt[j] - mx);
-                const float lse = mx + logf(se);
-                const int64_t y = p.labels ? p.labels[(int64_t)row * T + t] : p.ignore_index;
-                const bool keep = p.labels != nullptr && y != p.ignore_index && y >= 0 && y < C;
-                float qv = 0.f;
-                if (keep) {
-                    const float logpt = zt[y] - lse;
-                    const float a = p.class_weight ? __ldg(p.class_weight + c0 + (int)y) : 1.f;
-                    if (p.loss_kind == NKBK_LOSS_FOCAL) {
-                        const float pt = expf(logpt);
-                        const float om = 1.f - pt;
-                        const float g = p.gamma;
-                        float ft, dterm;
-                        if (g == 0.f) { ft = 1.f; dterm = 0.f; }
-                        else {
-                            const float pw1 = (g == 1.f) ? 1.f : ((g == 2.f) ? om : powf(om, g - 1.f));
-                            ft = pw1 * om;
-                            dterm = g * pt * pw1 * logpt;
-                        }
-                        loss_i = -a * ft * logpt;
-                        qv = a * (dterm - ft);
-                        den_i = 1.f;
-                    } else {
-                        loss_i = -a * logpt;
-                        qv = -a;
-                        den_i = a;
-                    }
-                }
-                const int64_t o = (int64_t)row * NC + c0;
-                for (int j = 0; j < C; ++j) {
-                    const float zj = zt[j];
-                    const float pj = expf(zj - lse);
-                    if (p.out_logits) p.out_logits[o + j] = zj;
-                    if (p.out_probs) p.out_probs[o + j] = pj;
-                    if (p.dlogits) p.dlogits[o + j] = keep ? qv * ((j == (int)y ? 1.f : 0.f) - pj) : 0.f;
+                for (int i = 0; i < 16; ++i)
+                    if (c0 + i < NC) z[c0 + i] = v[i] + __ldg(p.bias + c0 + i);
+            }
+        } else {
+            float* mine = sp.partial + ((int64_t)ksi * p.B + row) * NPAD;
+#pragma unroll
+            for (int c0 = 0; c0 < NPAD; c0 += 16) {
+                float v[16];
+                tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
+                if (row < p.B) {
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4)
+                        *reinterpret_cast<float4*>(mine + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
                 }
             }
-            my_lt[t] = loss_i;
-            my_lt[T + t] = den_i;
+            __threadfence();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (e == 0) s_is_last = (atomicAdd(&sp.counters[blockIdx.x], 1u) == (unsigned)ks - 1u);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            active = s_is_last != 0;
+            if (active) {
+                __threadfence();
+                if (e == 0) sp.counters[blockIdx.x] = 0u;
+                if (row < p.B) {
+                    for (int c = 0; c < NC; ++c) {
+                        float s = 0.f;
+                        for (int k = 0; k < ks; ++k) s += __ldcg(sp.partial + ((int64_t)k * p.B + row) * NPAD + c);  // fixed order
+                        z[c] = s + __ldg(p.bias + c);
+                    }
+                }
+            }
+        }
+        if (active) {
+            float* my_lt = lt + r * 2 * T;
+            for (int t = 0; t < T; ++t) {
+                float loss_i = 0.f, den_i = 0.f;
+                if (row < p.B) {
+                    const int c0 = p.seg.off[t], C = p.seg.off[t + 1] - c0;
+                    const float* zt = z + c0;
+                    float mx = zt[0];
+                    for (int j = 1; j < C; ++j) mx = fmaxf(mx, zt[j]);
+                    float se = 0.f;
+                    for (int j = 0; j < C; ++j) se += expf(zt[j] - mx);
+                    const float lse = mx + logf(se);
+                    const int64_t y = p.labels ? p.labels[(int64_t)row * T + t] : p.ignore_index;
+                    const bool keep = p.labels != nullptr && y != p.ignore_index && y >= 0 && y < C;
+                    float qv = 0.f;
+                    if (keep) {
+                        const float logpt = zt[y] - lse;
+                        const float a = p.class_weight ? __ldg(p.class_weight + c0 + (int)y) : 1.f;
+                        if (p.loss_kind == NKBK_LOSS_FOCAL) {
+                            const float pt = expf(logpt);
+                            const float om = 1.f - pt;
+                            const float g = p.gamma;
+                            float ft, dterm;
+                            if (g == 0.f) { ft = 1.f; dterm = 0.f; }
+                            else {
+                                const float pw1 = (g == 1.f) ? 1.f : ((g == 2.f) ? om : powf(om, g - 1.f));
+                                ft = pw1 * om;
+                                dterm = g * pt * pw1 * logpt;
+                            }
+                            loss_i = -a * ft * logpt;
+                            qv = a * (dterm - ft);
+                            den_i = 1.f;
+                        } else {
+                            loss_i = -a * logpt;
+                            qv = -a;
+                            den_i = a;
+                        }
+                    }
+                    const int64_t o = (int64_t)row * NC + c0;
+                    for (int j = 0; j < C; ++j) {
+                        const float zj = zt[j];
+                        const float pj = expf(zj - lse);
+                        if (p.out_logits) p.out_logits[o + j] = zj;
+                        if (p.out_probs) p.out_probs[o + j] = pj;
+                        if (p.dlogits) p.dlogits[o + j] = keep ? qv * ((j == (int)y ? 1.f : 0.f) - pj) : 0.f;
+                    }
+                }
+                my_lt[t] = loss_i;
+                my_lt[T + t] = den_i;
+            }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        // named barrier over the 4 epilogue warps, then a fixed-order column sum -> this CTA's partial
+        // named barrier over the 4 epilogue warps, then a fixed-order column sum -> this row tile's partial
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        const int e = threadIdx.x - 64;  // 0..127
-        if (e < 2 * T) {
+        if (active && e < 2 * T) {
             float s = 0.f;
             for (int rr = 0; rr < TC_BM; ++rr) s += lt[rr * 2 * T + e];
             p.loss_part[(int64_t)blockIdx.x * 2 * T + e] = s;
@@ -267,7 +311,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k2_tc_heads_forward(const __gri
 
 // fp32 head weights -> bf16 [npad][D], rows >= NC zero (the tensor map's box always reads npad rows)
 __global__ void __launch_bounds__(256) k2_tc_pack_weights(const float* __restrict__ W, int NC, int D, int npad,
-                                                          __nv_bfloat16* __restrict__ out) {
+                                                          __nv_bfloat16* __restrict__ out,
+                                                          unsigned int* __restrict__ counters, int n_counters) {
+    if (blockIdx.x == 0)
+        for (int i = threadIdx.x; i < n_counters; i += blockDim.x) counters[i] = 0u;
     const int64_t n = (int64_t)npad * D;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(i / D);
@@ -314,30 +361,51 @@ static int tc_npad(int NC) {
     return 0;
 }
 
-int64_t k2_tc_workspace_floats(int D, int NC) {
-    const int npad = tc_npad(NC);
-    if (npad == 0) return 0;
-    return ((int64_t)npad * D * 2 + 1024 + 3) / 4;  // bf16 weights + alignment slack
+static int tc_ksplit(int B, int D, int npad) {
+    const int ctas_m = (B + TC_BM - 1) / TC_BM;
+    const int kblocks = D / TC_BK;
+    int ks = 148 / ctas_m;                       // fill the 148 SMs
+    if (ks > 8) ks = 8;
+    if (ks > kblocks) ks = kblocks;
+    while (ks > 1 && (int64_t)ks * B * npad * 4 > (int64_t(64) << 20)) --ks;   // cap the partial buffer at 64 MB
+    return ks < 1 ? 1 : ks;
 }
 
-template <int NPAD>
-static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tw, const K2FwdParams& p, int ctas, cudaStream_t st) {
-    const TcSmem L = tc_smem_layout(NPAD, p.seg.T);
+// bf16 weights + split-K partials + per-tile counters, in floats
+int64_t k2_tc_workspace_floats(int B, int D, int NC) {
+    const int npad = tc_npad(NC);
+    if (npad == 0 || D % TC_BK != 0) return 0;
+    const int ks = tc_ksplit(B, D, npad);
+    const int64_t wb = ((int64_t)npad * D * 2 + 1024 + 3) / 4;
+    const int64_t part = ks > 1 ? (int64_t)ks * B * npad + 4 : 0;
+    return wb + part + (B + TC_BM - 1) / TC_BM + 8;
+}
+
+template <int NPAD, int STAGES>
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tw, const K2FwdParams& p, const TcSplit& sp, dim3 grid,
+                     cudaStream_t st) {
+    const TcSmem L = tc_smem_layout(NPAD, STAGES, p.seg.T);
     const int smem = (int)L.total + 1024;
-    NKBK_CHECK_CUDA(cudaFuncSetAttribute(k2_tc_heads_forward<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    k2_tc_heads_forward<NPAD><<<ctas, TC_THREADS, smem, st>>>(ta, tw, p);
+    NKBK_CHECK_CUDA(cudaFuncSetAttribute(k2_tc_heads_forward<NPAD, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         smem));
+    k2_tc_heads_forward<NPAD, STAGES><<<grid, TC_THREADS, smem, st>>>(ta, tw, p, sp);
     NKBK_CHECK_LAUNCH("k2_tc_heads_forward");
     return NKBK_OK;
 }
 
-int launch_k2_tc_forward(const K2FwdParams& p, void* wb_workspace, cudaStream_t st) {
+int launch_k2_tc_forward(const K2FwdParams& p, void* ws_v, cudaStream_t st) {
     const int npad = tc_npad(p.NC);
     if (npad == 0 || p.seg.T > TC_MAX_TASKS || p.D % TC_BK != 0 || p.B < 1) return 0;
     if ((reinterpret_cast<uintptr_t>(p.emb) & 15) != 0) return 0;
-    const TcSmem L = tc_smem_layout(npad, p.seg.T);
-    if (L.total + 1024 > 220 * 1024) return 0;
     if (getenv("NKBK_DISABLE_TCGEN05") != nullptr) return 0;
-    __nv_bfloat16* wb = reinterpret_cast<__nv_bfloat16*>((reinterpret_cast<uintptr_t>(wb_workspace) + 1023) & ~uintptr_t(1023));
+    const int ks = tc_ksplit(p.B, p.D, npad);
+    const int ctas = (p.B + TC_BM - 1) / TC_BM;
+    float* ws = static_cast<float*>(ws_v);
+    __nv_bfloat16* wb = reinterpret_cast<__nv_bfloat16*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));
+    float* after_wb = ws + ((int64_t)npad * p.D * 2 + 1024 + 3) / 4;
+    TcSplit sp;
+    sp.partial = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(after_wb) + 15) & ~uintptr_t(15));
+    sp.counters = reinterpret_cast<unsigned int*>(after_wb + (ks > 1 ? (int64_t)ks * p.B * npad + 4 : 0));
     CUtensorMap ta, tw;
     if (!make_tmap_bf16_2d(&ta, p.emb, (uint64_t)p.B, (uint64_t)p.D, TC_BM)) return 0;
     if (!make_tmap_bf16_2d(&tw, wb, (uint64_t)npad, (uint64_t)p.D, (uint32_t)npad)) return 0;
@@ -345,19 +413,19 @@ int launch_k2_tc_forward(const K2FwdParams& p, void* wb_workspace, cudaStream_t 
         const int64_t n = (int64_t)npad * p.D;
         int blocks = (int)((n + 255) / 256);
         if (blocks > 148 * 4) blocks = 148 * 4;
-        k2_tc_pack_weights<<<blocks, 256, 0, st>>>(p.W, p.NC, p.D, npad, wb);
+        k2_tc_pack_weights<<<blocks, 256, 0, st>>>(p.W, p.NC, p.D, npad, wb, sp.counters, ctas);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { set_error("launch of k2_tc_pack_weights failed: %s", cudaGetErrorString(e)); return NKBK_E_CUDA; }
         count_launch();
     }
-    const int ctas = (p.B + TC_BM - 1) / TC_BM;
+    dim3 grid(ctas, ks);
     int rc;
-    switch (npad) {
-        case 16: rc = launch_tc<16>(ta, tw, p, ctas, st); break;
-        case 32: rc = launch_tc<32>(ta, tw, p, ctas, st); break;
-        case 64: rc = launch_tc<64>(ta, tw, p, ctas, st); break;
-        case 128: rc = launch_tc<128>(ta, tw, p, ctas, st); break;
-        default: rc = launch_tc<256>(ta, tw, p, ctas, st); break;
+    switch (npad) {   // stage count: as deep as ~150 KB of operand buffers allows
+        case 16: rc = launch_tc<16, 8>(ta, tw, p, sp, grid, st); break;
+        case 32: rc = launch_tc<32, 7>(ta, tw, p, sp, grid, st); break;
+        case 64: rc = launch_tc<64, 6>(ta, tw, p, sp, grid, st); break;
+        case 128: rc = launch_tc<128, 4>(ta, tw, p, sp, grid, st); break;
+        default: rc = launch_tc<256, 3>(ta, tw, p, sp, grid, st); break;
     }
     return rc == NKBK_OK ? ctas : rc;
 }
