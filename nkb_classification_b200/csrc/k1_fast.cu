@@ -27,10 +27,18 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
+// Source rows are re-read by overlapping boxes of the same frame (and by the neighbouring band of the same box):
+// keep them in L2 (evict_last) while the 3x larger output stream goes through with evict-first stores.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+        : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
@@ -126,11 +134,12 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_crop_resize_normalize_tma(co
 
     const uint8_t* const src_seg = p.frames + g.f_off + (int64_t)g.by0 * g.pitch + seg_start;
     const uint32_t pitch32 = (uint32_t)g.pitch;  // qualifying crops have bh * pitch < 2^31 (fast_path_qualifies)
+    const uint64_t l2pol = l2_policy_evict_last();
     // lane 0: start the bulk copy of fetch number k into the slot at (slot_addr, bar_addr)
     auto issue = [&](int k, uint32_t slot_addr, uint32_t bar_addr) {
         const uint32_t row = (uint32_t)fetch_rows[warp][k];
         mbar_expect_tx(bar_addr, seg_bytes);
-        bulk_g2s(slot_addr, src_seg + row * pitch32, seg_bytes, bar_addr);
+        bulk_g2s(slot_addr, src_seg + row * pitch32, seg_bytes, bar_addr, l2pol);
     };
     if (lane == 0) {
         const int pre = min(nslot, nfetch);
