@@ -206,6 +206,9 @@ def run_b200(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not _lib.LIB_PATH.exists() and local_rank == 0:   # normally prebuilt in-tree by __graft_entry__.build()
+        from nkb_classification_b200 import build as _build
+        _build.build()
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)

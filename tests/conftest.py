@@ -29,7 +29,7 @@ def nkbk_lib():
 
 
 @pytest.fixture(scope="session")
-def cuda_device():
+def cuda_device(nkbk_lib):
     import torch
     if not torch.cuda.is_available():
         pytest.fail("this test is marked gpu but no CUDA device is visible")

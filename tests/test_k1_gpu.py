@@ -262,3 +262,28 @@ def test_k1_empty_batch(cuda_device):
                                torch.zeros((0, 4), dtype=torch.int32, device=cuda_device),
                                torch.zeros((0,), dtype=torch.int32, device=cuda_device), plan)
     assert tuple(out.shape) == (0, 3, 16, 16)
+
+
+@pytest.mark.parametrize("name,hw,kw", [
+    ("cfg1 singletask: 224x224 ImageFolder, Resize(224) = identity + Normalize", (224, 224), dict(out_h=224, out_w=224)),
+    ("cfg2 multitask: 256x256 -> Resize(224,224)", (256, 256), dict(out_h=224, out_w=224)),
+    ("cfg2 multitask sample config: img_size=128 letterbox", (256, 256), dict(mode="letterbox", out_h=128, out_w=128)),
+    ("non-square whole images, letterbox 224", (200, 333), dict(mode="letterbox", out_h=224, out_w=224)),
+])
+def test_k1_whole_image_configs(cuda_device, name, hw, kw):
+    """BASELINE configs 1 and 2: the box is the whole image (AnnotatedSingletask/MultitaskDataset, ImageFolder)."""
+    from nkb_classification_b200 import transforms as T
+    rng = np.random.default_rng(31)
+    H, W = hw
+    frames = rng.integers(0, 256, (32, H, W, 3), dtype=np.uint8)
+    boxes = [(0, 0, W, H)] * 32
+    fidx = list(range(32))
+    plan = make_plan(T, **kw)
+    out, u8 = run_k1(cuda_device, frames, boxes, fidx, plan)
+    eu8, ef32 = preprocess_batch_c(frames, boxes, fidx, oracle_plan(plan))
+    assert np.array_equal(u8.cpu().numpy(), eu8), name
+    assert_same_f32(out, ef32)
+    out_fast, _ = run_k1(cuda_device, frames, boxes, fidx, plan, want_u8=False)
+    assert_same_f32(out_fast, ef32)
+    if hw == (224, 224):
+        assert np.array_equal(u8.cpu().numpy(), frames)  # identity resize
