@@ -15,7 +15,7 @@
 //   * all per-(lane, j) constants (smem byte offset of the 2-pixel window, funnel
 //     shift, packed 11-bit coefficients) are loop invariant, so one source row
 //     costs 3 LDS + 2 SHF + 3 PRMT + 3 IDP.2A + 3 SHF per (lane, j).
-#include "k1_common.cuh"
+#include "k1_general_impl.cuh"
 
 namespace nkbk {
 
@@ -71,7 +71,12 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_crop_resize_normalize_tma(co
     const CropGeom g = load_geom(p, crop);
     uint32_t seg_start, seg_bytes, slot_stride;
     int nslot;
-    if (!fast_path_qualifies(p, g, seg_start, seg_bytes, slot_stride, nslot)) return;  // left to the general kernel
+    if (!fast_path_qualifies(p, g, seg_start, seg_bytes, slot_stride, nslot)) {
+        // unaligned frame rows, a box wider than the ring, or an invalid box: same arithmetic, direct loads
+        k1_process_band<JMAX, OutT, true, false>(p, crop, g, y_begin, nrows, ox0,
+                                                 blockIdx.y == 0 && blockIdx.z == 0 && warp == 0);
+        return;
+    }
     const int dw = p.out_w, dh = p.out_h;
 
     // ---- per-warp barriers ----

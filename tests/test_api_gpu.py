@@ -272,3 +272,24 @@ def test_inference_writes_reference_csv(cuda_device, tmp_path):
     for n in ("color", "size"):
         z = torch.nn.functional.linear(emb, state[f"classifier.{n}.1.weight"].double(), state[f"classifier.{n}.1.bias"].double())
         assert table[n].tolist() == [classes[n][i] for i in z.argmax(-1).tolist()]
+
+
+def test_val_epoch_bf16_autocast_uses_tensor_core_heads(cuda_device, tmp_path):
+    """enable_mixed_presicion=True: the backbone runs under bf16 autocast, K2 takes bf16 embeddings (tcgen05 path).
+    Losses / probabilities stay within the bf16 bar (1e-2) of the fp64 oracle; the device still matches itself."""
+    from nkb_classification_b200 import engine, logging as L
+    rows, loader, classes, cfg, model, crit, plan_kw = build(tmp_path, cuda_device)
+    cfg.enable_mixed_presicion = True
+    state = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    res = engine.val_epoch(model, loader, crit, cuda_device, cfg, L.BaseLogger(cfg, classes))
+    imgs, bb, names, Ws, bs, labels = oracle_epoch(tmp_path, rows, classes, state, plan_kw, loader.dataset.class_to_idx)
+    with torch.no_grad():
+        emb = bb(imgs)
+    for bi, (lo, hi) in enumerate(((0, 8), (8, 16), (16, 22))):
+        r = oh.heads_loss_fwd_bwd(emb[lo:hi], Ws, bs, labels[lo:hi], oh.LOSS_FOCAL, 1.0)
+        assert rel_err(res["running_loss"]["loss"][bi], float(r["total"])) <= 1e-2
+    ref_all = oh.heads_loss_fwd_bwd(emb, Ws, bs, labels, oh.LOSS_FOCAL, 1.0)
+    for t, n in enumerate(names):
+        assert np.abs(np.asarray(res["confidences"][n]) - ref_all["probs"][t].numpy()).max() <= 1e-2
+        cm = res["confusion"][n]
+        assert cm.sum() == len(rows) and np.array_equal(cm, om.confusion_matrix(res["ground_truth"][n], res["predictions"][n], cm.shape[0]))
