@@ -25,7 +25,6 @@ struct K1Params {
     int32_t* bad_count;
     int rows_per_warp;       // general kernel (<= 16)
     int rows_per_warp_fast;  // TMA kernel (<= 32)
-    int skip_fast;       // general kernel: skip crops the fast kernel has already produced
 };
 
 template <typename OutT>
@@ -69,7 +68,7 @@ __device__ __forceinline__ CropGeom load_geom(const K1Params& p, int crop) {
 // The fast kernel stages, per source row, the 16-byte-aligned span that covers the box's pixels
 // (plus the one pixel to its right that the last 2-tap window may touch) with one bulk async copy.
 // That needs 16-byte aligned frame rows, and the span must leave room for >= 2 ring slots.
-// Both kernels evaluate this same predicate, so every crop is produced exactly once.
+// Crops that fail the predicate are produced by the direct-load band routine inside the same kernel.
 __device__ __forceinline__ bool fast_path_qualifies(const K1Params& p, const CropGeom& g, uint32_t& seg_start,
                                                     uint32_t& seg_bytes, uint32_t& slot_stride, int& nslot) {
     seg_start = 0; seg_bytes = 0; slot_stride = 0; nslot = 0;

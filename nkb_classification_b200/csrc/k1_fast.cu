@@ -14,7 +14,10 @@
 //     upper one;
 //   * all per-(lane, j) constants (smem byte offset of the 2-pixel window, funnel
 //     shift, packed 11-bit coefficients) are loop invariant, so one source row
-//     costs 3 LDS + 2 SHF + 3 PRMT + 3 IDP.2A + 3 SHF per (lane, j).
+//     costs 3 LDS + 2 SHF + 3 PRMT + 3 IDP.2A + 3 SHF per (lane, j);
+//   * crops the ring cannot serve (frame rows not 16-byte aligned, boxes wider than
+//     ~1500 px, invalid boxes) fall back, per CTA, to the direct-load band routine
+//     of k1_general_impl.cuh -- same bits, one launch for the whole batch.
 #include "k1_general_impl.cuh"
 
 namespace nkbk {

@@ -1,10 +1,15 @@
 // K1: fused YOLO-box crop + cv2-INTER_LINEAR-exact uint8 resize + Normalize +
 // HWC->NCHW, one launch per batch.  See include/nkbk.h for the contract and
-// DESIGN.md section "K1" for the layout / roofline reasoning.
+// DESIGN.md section 4 "K1" for the layout / roofline reasoning.
 //
-// Work decomposition (v1, "row walker"):
+// This file holds the C-ABI entry point and the GENERAL kernel (letterbox,
+// partial column tiles, uint8 side output).  The band routine both kernels
+// share is in k1_general_impl.cuh; the TMA-staged fast kernel, which serves
+// A.Resize pipelines with full column tiles, is in k1_fast.cu.
+//
+// Work decomposition (both kernels):
 //   grid  = (crop, band-of-rows block, column tile)       block = 4 warps
-//   warp  = one band of `rows_per_warp` consecutive output rows of one crop
+//   warp  = one band of consecutive output rows of one crop
 //   lane  = output columns  tile*32*JMAX + lane + 32*j,  j = 0..JMAX-1
 //           -> every store instruction of a warp writes one full 128-byte line
 //              of one channel plane (fp32), every source load instruction of a
@@ -22,8 +27,8 @@
 //   words with two funnel shifts, one PRMT per channel pairs the two taps, one
 //   IDP.2A (16-bit x 8-bit dot product) yields H = a0*p0 + a1*p1, >> 4.
 //   Vertical: IMAD.HI with the coefficient pre-shifted by 16 gives
-//   (b*(H>>4))>>16 with the "+2" and the second tap folded into the addend,
-//   then >> 2, int->float, (v - mean255) * denom as two rounded fp32 ops.
+//   (b*(H>>4))>>16 per tap, +2, >> 2, int->float, then (v - mean255) * denom
+//   as two separately rounded fp32 operations.
 #include "k1_general_impl.cuh"
 
 namespace nkbk {
@@ -101,7 +106,6 @@ extern "C" int nkbk_preprocess_crops(const void* frames_base, const int64_t* fra
     p.rows_per_warp = (out_h + nby * K1_WARPS - 1) / (nby * K1_WARPS);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool f32 = out_dtype == NKBK_F32;
-    p.skip_fast = 0;
     p.rows_per_warp_fast = p.rows_per_warp;
 
     // ---- fast path: A.Resize, output width a whole number of 32*J column tiles, no uint8 side output ----
