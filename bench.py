@@ -41,6 +41,8 @@ def parse_args():
     ap.add_argument("--out-dtype", default="f32", choices=["f32", "bf16"])
     ap.add_argument("--emb-dtype", default="f32", choices=["f32", "bf16"],
                     help="dtype of the synthetic backbone output fed to K2 (bf16 = autocast path, tcgen05 forward)")
+    ap.add_argument("--allreduce", default="peer", choices=["peer", "nccl"],
+                    help="exchange step at N > 1: K4' fused NVLink peer-memory all-reduce + finalize, or NCCL (K4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -178,7 +180,7 @@ def run_reference(args, wl):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(wl, out_dtype, n_gpus):
+def workload_config(wl, out_dtype, n_gpus, transport="peer"):
     return {
         "workload": wl.name,
         "frames_per_gpu": wl.frames, "frame": f"{wl.frame_w}x{wl.frame_h}x3 u8", "boxes_per_frame": wl.boxes_per_frame,
@@ -186,7 +188,9 @@ def workload_config(wl, out_dtype, n_gpus):
         "emb_dim": wl.emb_dim, "heads": list(wl.classes), "loss": wl.loss, "gamma": wl.gamma,
         "backbone": "excluded (out of scope; synthetic embeddings)",
         "l2": "inputs larger than L2 (frames + output >> 126 MB per step); no flush needed",
-        "parallelism": f"dp{n_gpus} (frames sharded per rank, K4 all-reduce of head grads + confusion counts)",
+        "parallelism": f"dp{n_gpus} (frames sharded per rank; head grads + confusion counts all-reduced by "
+                       + ("one fused push/sum/finalize kernel over NVLink peer memory, K4')" if transport == "peer"
+                          else "NCCL, K4)"),
         "pipelining": "value: K1 (stream A) overlaps K2/K3/K4 of another batch (stream B), no dependency without the "
                       "backbone; serial_value: one stream, K1 -> K2 -> K3 -> K4 back to back",
     }
@@ -221,7 +225,8 @@ def run_b200(args, wl):
 
     out_dtype = torch.float32 if args.out_dtype == "f32" else torch.bfloat16
     plan = T.compile_pipeline([T.Resize(wl.out_size, wl.out_size), T.Normalize(MEAN, STD), T.ToTensorV2()])
-    hp = hotpath.HotPath(plan, wl.classes, wl.emb_dim, wl.loss, wl.gamma, device=dev, comm=comm, out_dtype=out_dtype)
+    hp = hotpath.HotPath(plan, wl.classes, wl.emb_dim, wl.loss, wl.gamma, device=dev, comm=comm, out_dtype=out_dtype,
+                         transport=args.allreduce)
 
     # ---- synthetic inputs, generated on the device, seeded per rank ----
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -413,7 +418,7 @@ def run_b200(args, wl):
         "ms_per_step": dt_ms_max / args.steps, "serial_value": serial_value, "serial_ms_per_step": serial_ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/int32->" + args.out_dtype + (", heads bf16 x bf16 -> f32 (tcgen05)" if args.emb_dtype == "bf16" else ", heads f32"),
-        "data": "synthetic", "config": workload_config(wl, args.out_dtype, world),
+        "data": "synthetic", "config": workload_config(wl, args.out_dtype, world, hp.transport),
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": sampler.summary(),
     }

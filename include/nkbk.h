@@ -186,6 +186,39 @@ int nkbk_comm_world(void);                                 /* 0 when not initial
 int nkbk_allreduce_heads(float* reduce_buf, int64_t n_f32, int64_t* cm, int64_t n_i64, void* stream);
 int nkbk_comm_shutdown(void);
 
+/* ------------------------------------------------------------------------
+ * K4' the same exchange step fused with nkbk_heads_finalize over NVLink peer
+ *     memory: ONE kernel pushes the local reduce buffer and
+ *     step confusion counts into every peer's inbox (cudaIpc-mapped, 16-byte
+ *     stores over NVLink/NVSwitch), waits on per-(rank, CTA) flags, sums the
+ *     `world` copies in rank order (bit-identical on every rank) and applies
+ *     the finalize step.  Replaces { nkbk_allreduce_heads, nkbk_heads_finalize }.
+ *
+ *   nkbk_peer_init     allocates this rank's inbox (capacity in fp32 / int64
+ *                      elements of the largest payload) and returns its
+ *                      64-byte IPC handle in a host buffer; world == 1 is allowed
+ *   nkbk_peer_connect  maps the inboxes of all ranks: handles_host is
+ *                      world x 64 bytes, rank-major (all-gathered by the caller);
+ *                      the caller must barrier once afterwards, before first use
+ *   nkbk_peer_allreduce_finalize   same arguments and results as
+ *                      nkbk_heads_finalize, but the sums are over all ranks;
+ *                      every rank must call it the same number of times with the
+ *                      same shapes, on one stream per process
+ *   nkbk_peer_status   host-synchronous: 0 = healthy, r + 1 = a wait on rank r
+ *                      timed out (results of that step are invalid)
+ * ---------------------------------------------------------------------- */
+#define NKBK_IPC_HANDLE_BYTES 64
+int nkbk_peer_init(int rank, int world, int device, int64_t max_f32, int64_t max_i64, void* out_handle_host);
+int nkbk_peer_connect(const void* handles_host);
+int nkbk_peer_world(void);                                 /* 0 when not connected */
+int nkbk_peer_allreduce_finalize(float* reduce_buf, int D, const int32_t* seg_offsets, int T, float* out_loss,
+                                 int64_t* cm_total, int64_t* cm_step, int64_t n_cm, void* stream);
+int nkbk_peer_status(int32_t* out_status_host);
+/* Tear-down is two-phase because an exported allocation must not be freed while a peer still maps it:
+ * every rank calls nkbk_peer_disconnect (unmaps the peers), the caller barriers, then nkbk_peer_shutdown frees. */
+int nkbk_peer_disconnect(void);
+int nkbk_peer_shutdown(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,6 +19,7 @@ F32, BF16 = 0, 1
 MODE_STRETCH, MODE_LETTERBOX = 0, 1
 LOSS_CE, LOSS_FOCAL = 0, 1
 UNIQUE_ID_BYTES = 128
+IPC_HANDLE_BYTES = 64
 
 # every symbol include/nkbk.h declares: (restype, argtypes)
 SYMBOLS = {
@@ -49,6 +50,14 @@ SYMBOLS = {
     "nkbk_comm_world": (c_int, []),
     "nkbk_allreduce_heads": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     "nkbk_comm_shutdown": (c_int, []),
+    "nkbk_peer_init": (c_int, [c_int, c_int, c_int, c_int64, c_int64, c_void_p]),
+    "nkbk_peer_connect": (c_int, [c_void_p]),
+    "nkbk_peer_world": (c_int, []),
+    "nkbk_peer_allreduce_finalize": (c_int, [c_void_p, c_int, POINTER(c_int32), c_int, c_void_p, c_void_p, c_void_p,
+                                             c_int64, c_void_p]),
+    "nkbk_peer_status": (c_int, [POINTER(c_int32)]),
+    "nkbk_peer_disconnect": (c_int, []),
+    "nkbk_peer_shutdown": (c_int, []),
 }
 
 

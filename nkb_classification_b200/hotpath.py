@@ -21,7 +21,8 @@ LOSS_KINDS = {"CrossEntropyLoss": LOSS_CE, "FocalLoss": LOSS_FOCAL}
 class HotPath:
     def __init__(self, plan: PreprocessPlan, classes_per_task: Sequence[int], emb_dim: int, loss_type: str = "FocalLoss",
                  gamma: float = 2.0, class_weight: Optional[torch.Tensor] = None, ignore_index: int = -100,
-                 device="cuda:0", comm: Optional[Communicator] = None, out_dtype: torch.dtype = torch.float32):
+                 device="cuda:0", comm: Optional[Communicator] = None, out_dtype: torch.dtype = torch.float32,
+                 transport: str = "peer"):
         if loss_type not in LOSS_KINDS:
             raise NotImplementedError(f"Unknown loss type in config: {loss_type}")  # losses.py:171
         self.plan = plan
@@ -31,6 +32,9 @@ class HotPath:
         self.loss_kind, self.gamma, self.ignore_index = LOSS_KINDS[loss_type], float(gamma), int(ignore_index)
         self.class_weight = None if class_weight is None else class_weight.to(self.device, torch.float32).contiguous()
         self.comm = comm or Communicator()
+        if transport not in ("peer", "nccl"):
+            raise ValueError(f"transport must be 'peer' or 'nccl', got {transport!r}")
+        self.transport = transport   # exchange step: K4' (NVLink peer memory, fused finalize) or K4 (NCCL)
         self.out_dtype = out_dtype
         self.cm = torch.zeros(ops.confusion_len(self.seg), dtype=torch.int64, device=self.device)       # epoch totals
         self.cm_step = torch.zeros_like(self.cm)   # this step's counts: K3 -> all-reduce -> folded into cm by finalize
@@ -38,6 +42,7 @@ class HotPath:
         self._images: Dict[int, torch.Tensor] = {}
         self._pred: Dict[int, torch.Tensor] = {}
         self._desc = None
+        self._peer_ready = False
 
     # ---- K1 ----
     def preprocess(self, frames: torch.Tensor, boxes: torch.Tensor, frame_idx: torch.Tensor,
@@ -83,11 +88,22 @@ class HotPath:
                 self._pred = {B: pred}
             ops.argmax_confusion(bufs.logits, self.seg, labels if do_cm else None, self.cm_step if do_cm else None,
                                  out_pred=pred)
-        self.comm.allreduce_heads(bufs.reduce_buf, self.cm_step if do_cm else None)
-        if do_cm:
-            ops.heads_finalize(bufs, self.cm, self.cm_step)
+        if self.comm.world > 1 and self.transport == "peer" and not self._peer_ready:
+            # collective, first step only: map the peers' inboxes, sized for this path's payload (a no-op when the
+            # communicator already holds large enough ones); falls back to NCCL when P2P is not available
+            if self.comm.init_peer(self.device, ops.heads_reduce_buf_len(self.D, self.NC, self.T), self.cm.numel()):
+                self._peer_ready = True
+            else:
+                self.transport = "nccl"
+        if self.comm.world > 1 and self.transport == "peer":
+            # K4': push + wait + rank-ordered sum + finalize in one launch over NVLink peer memory
+            ops.peer_allreduce_finalize(bufs, self.cm if do_cm else None, self.cm_step if do_cm else None)
         else:
-            ops.heads_finalize(bufs)
+            self.comm.allreduce_heads(bufs.reduce_buf, self.cm_step if do_cm else None)
+            if do_cm:
+                ops.heads_finalize(bufs, self.cm, self.cm_step)
+            else:
+                ops.heads_finalize(bufs)
         bufs.pred = pred
         return bufs
 

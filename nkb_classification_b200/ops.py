@@ -214,6 +214,23 @@ def heads_finalize(bufs: HeadsBuffers, cm_total: Optional[torch.Tensor] = None,
     return bufs.loss
 
 
+def peer_allreduce_finalize(bufs: HeadsBuffers, cm_total: Optional[torch.Tensor] = None,
+                            cm_step: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """K4': the cross-rank sum of ``reduce_buf`` (+ ``cm_step``) over NVLink peer memory fused with
+    :func:`heads_finalize` -- one launch, same results contract (sums are over all ranks).  Requires
+    ``Communicator.init_peer`` (nkbk_peer_init / nkbk_peer_connect)."""
+    seg, T, _ = _seg_array(bufs.seg)
+    n_cm = 0
+    if cm_total is not None or cm_step is not None:
+        if cm_total is None or cm_step is None or cm_total.numel() != cm_step.numel() \
+                or cm_total.dtype != torch.int64 or cm_step.dtype != torch.int64:
+            raise ValueError("cm_total / cm_step must both be int64 of equal length")
+        n_cm = cm_total.numel()
+    check(lib().nkbk_peer_allreduce_finalize(_ptr(bufs.reduce_buf), bufs.D, seg, T, _ptr(bufs.loss), _ptr(cm_total),
+                                             _ptr(cm_step), n_cm, _stream(bufs.reduce_buf.device)))
+    return bufs.loss
+
+
 def heads_demb(bufs: HeadsBuffers, W_cat: torch.Tensor, out_dtype: torch.dtype = torch.float32,
                out: Optional[torch.Tensor] = None, task_scale: Optional[torch.Tensor] = None) -> torch.Tensor:
     if bufs.dlogits is None:

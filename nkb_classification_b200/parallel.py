@@ -2,10 +2,16 @@
 
 One process per GPU.  Frames (with all their boxes) are sharded contiguously
 across ranks; the only data-path exchange is one sum-all-reduce of the packed
-K2 reduce buffer per training step and one of the int64 confusion counts,
-issued through libnkbk's own NCCL communicator (nkbk_allreduce_heads).
-``torch.distributed`` is used only for rendezvous (broadcasting the NCCL
-unique id) and for barriers / timing in bench.py.
+K2 reduce buffer per training step and one of the int64 confusion counts.
+Two transports for that step live in libnkbk:
+
+* ``peer``  (K4', default when the GPUs can map each other's memory): ONE kernel
+  pushes the payload into every peer's cudaIpc-mapped inbox over NVLink, waits on
+  flags, sums in rank order and applies the K2 finalize (nkbk_peer_allreduce_finalize);
+* ``nccl``  (K4): grouped ncclAllReduce + the separate finalize launch.
+
+``torch.distributed`` is used only for rendezvous (broadcasting the NCCL unique
+id, all-gathering the 64-byte IPC handles) and for barriers / timing in bench.py.
 """
 from __future__ import annotations
 
@@ -16,7 +22,7 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
-from ._lib import UNIQUE_ID_BYTES, check, lib
+from ._lib import IPC_HANDLE_BYTES, UNIQUE_ID_BYTES, check, lib
 
 
 def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
@@ -42,7 +48,9 @@ class Communicator:
 
     def __init__(self):
         self.rank, self.world = 0, 1
-        self.active = False
+        self.active = False          # NCCL communicator (K4)
+        self.peer_active = False     # NVLink peer-memory transport (K4')
+        self._peer_cap = (0, 0)
 
     def init_from_torch_distributed(self, device: torch.device) -> "Communicator":
         import torch.distributed as dist
@@ -61,6 +69,52 @@ class Communicator:
         self.active = True
         return self
 
+    def init_peer(self, device: torch.device, max_f32: int, max_i64: int) -> bool:
+        """Set up the NVLink peer-memory transport (K4') for payloads of up to ``max_f32`` fp32 + ``max_i64`` int64
+        elements.  Collective: every rank must call it.  Returns False (and leaves the NCCL transport in charge) when
+        the devices cannot map each other's memory; all ranks take the same decision."""
+        import torch.distributed as dist
+        if self.peer_active:
+            if max_f32 <= self._peer_cap[0] and max_i64 <= self._peer_cap[1]:
+                return True
+            self._shutdown_peer()
+        if self.world > 1 and not dist.is_initialized():
+            raise RuntimeError("torch.distributed must be initialised first (it carries the IPC handles)")
+        hbuf = (ctypes.c_uint8 * IPC_HANDLE_BYTES)()
+        check(lib().nkbk_peer_init(self.rank, self.world, device.index or 0, int(max_f32), int(max_i64), hbuf))
+        ok = True
+        if self.world > 1:
+            handles: List[Optional[bytes]] = [None] * self.world
+            dist.all_gather_object(handles, bytes(hbuf))
+            raw = (ctypes.c_uint8 * (IPC_HANDLE_BYTES * self.world)).from_buffer_copy(b"".join(handles))
+            ok = lib().nkbk_peer_connect(raw) == 0
+            flags = [None] * self.world
+            dist.all_gather_object(flags, ok)          # also the barrier nkbk_peer_connect asks for
+            ok = all(flags)
+        if not ok:
+            lib().nkbk_peer_shutdown()
+            return False
+        self.peer_active = True
+        self._peer_cap = (int(max_f32), int(max_i64))
+        return True
+
+    def _shutdown_peer(self) -> None:
+        if self.peer_active:
+            # two-phase: nobody frees its inbox while a peer still maps it
+            lib().nkbk_peer_disconnect()
+            if self.world > 1:
+                import torch.distributed as dist
+                if dist.is_initialized():
+                    dist.barrier()
+            lib().nkbk_peer_shutdown()
+            self.peer_active = False
+
+    def peer_status(self) -> int:
+        """0 = healthy; r + 1 = a wait on rank r timed out (host-synchronous)."""
+        st = ctypes.c_int32(0)
+        check(lib().nkbk_peer_status(ctypes.byref(st)))
+        return int(st.value)
+
     def allreduce_heads(self, reduce_buf: Optional[torch.Tensor], cm: Optional[torch.Tensor]) -> None:
         """Sum both payloads across ranks, in place, on the current stream.  No-op for world == 1."""
         if self.world == 1:
@@ -76,6 +130,7 @@ class Communicator:
             0 if cm is None else cm.numel(), st))
 
     def shutdown(self) -> None:
+        self._shutdown_peer()
         if self.active:
             lib().nkbk_comm_shutdown()
             self.active = False

@@ -89,6 +89,17 @@ def test_argument_errors_need_no_gpu(nkbk_lib):
     assert nkbk_lib.nkbk_comm_world() == 0
     rc = nkbk_lib.nkbk_allreduce_heads(None, 0, None, 0, None)
     assert rc == _lib.NKBK_E_NCCL
+    # K4' (peer memory): not connected -> refused before any CUDA call; bad world -> argument error
+    assert nkbk_lib.nkbk_peer_world() == 0
+    rc = nkbk_lib.nkbk_peer_allreduce_finalize(None, 8, seg, 1, None, None, None, 0, None)
+    assert rc == _lib.NKBK_E_NCCL and b"not connected" in nkbk_lib.nkbk_last_error()
+    hbuf = (ctypes.c_uint8 * _lib.IPC_HANDLE_BYTES)()
+    assert nkbk_lib.nkbk_peer_init(0, 99, 0, 16, 0, hbuf) == _lib.NKBK_E_ARG
+    assert nkbk_lib.nkbk_peer_init(2, 2, 0, 16, 0, hbuf) == _lib.NKBK_E_ARG
+    assert nkbk_lib.nkbk_peer_connect(None) == _lib.NKBK_E_ARG
+    st = ctypes.c_int32(7)
+    assert nkbk_lib.nkbk_peer_status(ctypes.byref(st)) == 0 and st.value == 0
+    assert nkbk_lib.nkbk_peer_disconnect() == 0 and nkbk_lib.nkbk_peer_shutdown() == 0
 
 
 def test_ops_refuse_cpu_tensors(nkbk_lib):

@@ -238,6 +238,72 @@ def test_sharded_equals_single_gpu_nccl(cuda_device):
     assert r.returncode == 0 and "DIST_CHECK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
+def _torchrun(script, world, port, env_extra=None, timeout=600):
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    env = dict(os.environ)
+    env.update(env_extra or {})
+    return subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                           "--master-addr", "127.0.0.1", "--master-port", str(port),
+                           str(Path(__file__).resolve().parent / script)],
+                          capture_output=True, text=True, timeout=timeout, env=env)
+
+
+def test_peer_allreduce_finalize_world1_equals_finalize(cuda_device):
+    """K4' with a single rank is exactly nkbk_heads_finalize: same bits in dW/db/loss, same confusion fold."""
+    from nkb_classification_b200 import _lib, ops
+    from nkb_classification_b200.parallel import Communicator
+    g = torch.Generator().manual_seed(21)
+    classes, B, D = (3, 5, 2), 200, 516
+    seg = np.concatenate([[0], np.cumsum(classes)]).tolist()
+    emb = torch.randn(B, D, generator=g).to(cuda_device)
+    W = (torch.randn(sum(classes), D, generator=g) * 0.05).to(cuda_device)
+    b = torch.zeros(sum(classes), device=cuda_device)
+    labels = torch.stack([torch.randint(0, c, (B,), generator=g) for c in classes], 1).to(cuda_device)
+    ncm = ops.confusion_len(seg)
+    comm = Communicator()
+    assert comm.init_peer(cuda_device, ops.heads_reduce_buf_len(D, sum(classes), len(classes)), ncm)
+    try:
+        outs = []
+        for fused in (False, True, True):      # two fused calls: both slot parities
+            bufs = ops.HeadsBuffers(B, D, seg, cuda_device)
+            cm, cm_step = torch.zeros(ncm, dtype=torch.int64, device=cuda_device), torch.zeros(ncm, dtype=torch.int64, device=cuda_device)
+            ops.heads_fwd_loss_bwd(emb, W, b, labels, bufs, oh.LOSS_FOCAL, 2.0, None, -100)
+            ops.argmax_confusion(bufs.logits, seg, labels, cm_step)
+            (ops.peer_allreduce_finalize if fused else ops.heads_finalize)(bufs, cm, cm_step)
+            torch.cuda.synchronize()
+            assert int(cm.sum()) == B * len(classes) and not bool(cm_step.any())
+            outs.append((bufs.reduce_buf.clone(), bufs.loss.clone(), cm))
+        for o in outs[1:]:
+            assert torch.equal(o[0], outs[0][0]) and torch.equal(o[1], outs[0][1]) and torch.equal(o[2], outs[0][2])
+        assert comm.peer_status() == 0
+        bufs_big = ops.HeadsBuffers(B, 2 * D, seg, cuda_device)      # larger than the inbox: refused, not truncated
+        with pytest.raises(ValueError, match="capacity"):
+            ops.peer_allreduce_finalize(bufs_big)
+    finally:
+        comm.shutdown()
+    assert _lib.lib().nkbk_peer_world() == 0
+
+
+def test_peer_allreduce_two_ranks_on_one_gpu(cuda_device):
+    """K4' protocol (push into cudaIpc-mapped inboxes, flags, rank-ordered sums, finalize) with two PROCESSES sharing
+    this GPU; the N-GPU NVLink run of the same script is test_peer_allreduce_multi_gpu."""
+    r = _torchrun("peer_check.py", 2, 29673, {"NKBK_PEER_ONE_GPU": "1"}, timeout=900)
+    assert r.returncode == 0 and "PEER_CHECK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_peer_allreduce_multi_gpu(cuda_device):
+    """K4' over NVLink: needs >= 2 visible GPUs (gpurun --gpus 2)."""
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2 if n < 4 else (4 if n < 8 else 8)
+    r = _torchrun("peer_check.py", world, 29674, timeout=900)
+    assert r.returncode == 0 and "PEER_CHECK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
 @pytest.mark.parametrize("B,D,classes", [
     (1024, 768, (2, 3, 4, 7, 14)),     # BASELINE config 4: N padded to 32
     (4096, 2048, (10,)),               # config 5 width in bf16: N padded to 16
