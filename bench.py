@@ -191,8 +191,8 @@ def workload_config(wl, out_dtype, n_gpus, transport="peer"):
         "parallelism": f"dp{n_gpus} (frames sharded per rank; head grads + confusion counts all-reduced by "
                        + ("one fused push/sum/finalize kernel over NVLink peer memory, K4')" if transport == "peer"
                           else "NCCL, K4)"),
-        "pipelining": "value: K1 (stream A) overlaps K2/K3/K4 of another batch (stream B), no dependency without the "
-                      "backbone; serial_value: one stream, K1 -> K2 -> K3 -> K4 back to back",
+        "pipelining": "value: K1 (stream A) overlaps K2/K3/K4 of another batch (stream B, higher priority), no dependency "
+                      "without the backbone; serial_value: one stream, K1 -> K2 -> K3 -> K4 back to back",
     }
 
 
@@ -287,7 +287,9 @@ def run_b200(args, wl):
     # K1 of a batch and K2/K3/K4 of another batch have no data dependency (the backbone sits between them and is
     # out of scope here), so a real loop runs preprocessing of batch i+1 while the heads/loss/metric of batch i
     # execute.  All work of all K steps still happens inside the timed region; both streams are joined before e1.
-    s_pre, s_heads = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    # The heads stream has the higher priority: its short kernels take SM slots as K1's CTAs retire instead of queueing
+    # behind the whole K1 grid, so K2/K3/K4 of a batch really run under the K1 of the next one.
+    s_pre, s_heads = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev, priority=-1)
     cur = torch.cuda.current_stream(dev)
 
     def pipelined(k):

@@ -91,6 +91,7 @@ __device__ __forceinline__ int peer_task_of(const K2Seg& seg, int c) {
 __global__ void __launch_bounds__(PEER_THREADS) k4_peer_allreduce_finalize(const PeerParams p) {
     __shared__ float tail_s[2 * K2_MAX_TASKS];  // reduced [loss_sum T | denom T]
     __shared__ unsigned int step_s;
+    __shared__ bool last_s;
     const int tid = threadIdx.x, cta = blockIdx.x;
     const int T = p.seg.T, world = p.world, rank = p.rank;
     if (tid == 0) step_s = *reinterpret_cast<volatile unsigned int*>(p.ctl) + 1u;
@@ -175,14 +176,14 @@ __global__ void __launch_bounds__(PEER_THREADS) k4_peer_allreduce_finalize(const
                     const int c = (i < nW) ? (int)(i / p.D) : (int)(i - nW);
                     const float dn = tail_s[T + peer_task_of(p.seg, c)];
                     a[k] = dn > 0.f ? __fdiv_rn(a[k], dn) : 0.f;
-                } else if (i < p.n_f32) {
-                    a[k] = tail_s[i - tail0];  // loss sums / denominators stay unnormalised (k2_heads_demb reads them)
                 }
             }
-            if (i0 + 3 < p.n_f32) *reinterpret_cast<float4*>(p.reduce_buf + i0) = acc;
+            // The [loss_sum | denom] tail is NOT written here: other CTAs of this rank may still have to read the
+            // LOCAL values (for their push and for their rank-ordered sum); the last CTA to finish writes it below.
+            if (i0 + 3 < tail0) *reinterpret_cast<float4*>(p.reduce_buf + i0) = acc;
             else
                 for (int k = 0; k < 4; ++k)
-                    if (i0 + k < p.n_f32) p.reduce_buf[i0 + k] = a[k];
+                    if (i0 + k < tail0) p.reduce_buf[i0 + k] = a[k];
         } else {
             longlong2 acc = make_longlong2(0, 0);
             for (int r = 0; r < world; ++r) {
@@ -209,11 +210,17 @@ __global__ void __launch_bounds__(PEER_THREADS) k4_peer_allreduce_finalize(const
     }
 
     // ---- the last CTA to finish advances the step counter (every CTA read it before taking a ticket) ----
+    // It also publishes the global loss sums / denominators (left unnormalised: k2_heads_demb reads the
+    // denominators) -- only now, when no CTA of this rank needs the local values any more.
     __syncthreads();
     if (tid == 0) {
         __threadfence();
-        const unsigned int prev = atomicAdd(p.ctl + 1, 1u);
-        if (prev == gridDim.x - 1u) {
+        last_s = atomicAdd(p.ctl + 1, 1u) == gridDim.x - 1u;
+    }
+    __syncthreads();
+    if (last_s) {
+        if (tid < 2 * T) p.reduce_buf[tail0 + tid] = tail_s[tid];
+        if (tid == 0) {
             p.ctl[1] = 0u;
             __threadfence();
             *reinterpret_cast<volatile unsigned int*>(p.ctl) = step;
