@@ -25,7 +25,32 @@ struct K1Params {
     int32_t* bad_count;
     int rows_per_warp;       // general kernel (<= 16)
     int rows_per_warp_fast;  // TMA kernel (<= 32)
+    // ---- train-time augmentations on the resized (and padded) uint8 image, per crop (NULL = none) ----
+    // applied in the reference's order: HorizontalFlip, VerticalFlip, RandomBrightnessContrast, CoarseDropout
+    const int32_t* aug_flags;   // [n]  bit0 hflip, bit1 vflip, bit2 brightness/contrast, bits 8.. = number of holes
+    const float* aug_alpha;     // [n]  f32(1 + contrast)
+    const float* aug_beta;      // [n]  f32(brightness * max_value), added after the multiply
+    const int32_t* aug_holes;   // [n][aug_max_holes][4]  x1, y1, x2, y2 in output pixels (exclusive ends)
+    int aug_max_holes;
+    uint32_t aug_fill[3];       // CoarseDropout fill value per output channel
 };
+constexpr int K1_AUG_HFLIP = 1, K1_AUG_VFLIP = 2, K1_AUG_BC = 4;
+constexpr int K1_AUG_MAX_HOLES = 16;
+
+// albumentations 1.x `_brightness_contrast_adjust_uint` with beta_by_max: the 256-entry LUT
+// clip(f32(v) * alpha + beta, 0, 255).astype(uint8) evaluated per pixel (two rounded fp32 ops, truncation).
+__host__ __device__ __forceinline__ uint32_t k1_brightness_contrast(uint32_t v, float alpha, float beta) {
+#ifdef __CUDA_ARCH__
+    float t = __fadd_rn(__fmul_rn((float)v, alpha), beta);
+    t = fminf(fmaxf(t, 0.f), 255.f);
+    return (uint32_t)__float2int_rz(t);
+#else
+    volatile float t = (float)v * alpha;
+    t = t + beta;
+    float u = t < 0.f ? 0.f : (t > 255.f ? 255.f : t);
+    return (uint32_t)(int)u;
+#endif
+}
 
 template <typename OutT>
 __device__ __forceinline__ void store_out(OutT* p, float v);

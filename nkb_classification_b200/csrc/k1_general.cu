@@ -36,7 +36,7 @@ namespace nkbk {
 bool launch_k1_fast(const K1Params& p, int jmax, dim3 grid, cudaStream_t st, bool f32);  // k1_fast.cu
 
 // One crop per blockIdx.x, one band of rows per warp.
-template <int JMAX, typename OutT, bool GENERAL, bool WRITE_U8>
+template <int JMAX, typename OutT, bool GENERAL, bool WRITE_U8, bool AUG = false>
 __global__ void __launch_bounds__(K1_WARPS * 32) k1_crop_resize_normalize(const K1Params p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int y_begin = (blockIdx.y * K1_WARPS + warp) * p.rows_per_warp;
@@ -45,29 +45,78 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_crop_resize_normalize(const 
     const int ox0 = blockIdx.z * (32 * JMAX) + lane;
     for (int crop = blockIdx.x; crop < p.n; crop += gridDim.x) {
         const CropGeom g = load_geom(p, crop);
-        k1_process_band<JMAX, OutT, GENERAL, WRITE_U8>(p, crop, g, y_begin, nrows, ox0,
-                                                       blockIdx.y == 0 && blockIdx.z == 0 && warp == 0);
+        k1_process_band<JMAX, OutT, GENERAL, WRITE_U8, AUG>(p, crop, g, y_begin, nrows, ox0,
+                                                            blockIdx.y == 0 && blockIdx.z == 0 && warp == 0);
     }
 }
 
 template <int JMAX, typename OutT>
 static void launch_k1(const K1Params& p, dim3 grid, cudaStream_t st, bool general) {
     (void)general;
+    if (p.aug_flags != nullptr) {   // train-time pipeline: flips / brightness-contrast / dropout holes fused in
+        if (p.out_u8 != nullptr)
+            k1_crop_resize_normalize<JMAX, OutT, true, true, true><<<grid, K1_WARPS * 32, 0, st>>>(p);
+        else
+            k1_crop_resize_normalize<JMAX, OutT, true, false, true><<<grid, K1_WARPS * 32, 0, st>>>(p);
+        return;
+    }
     if (p.out_u8 != nullptr)
         k1_crop_resize_normalize<JMAX, OutT, true, true><<<grid, K1_WARPS * 32, 0, st>>>(p);
     else
         k1_crop_resize_normalize<JMAX, OutT, true, false><<<grid, K1_WARPS * 32, 0, st>>>(p);
 }
 
+struct K1AugArgs {
+    const int32_t* flags;
+    const float* alpha;
+    const float* beta;
+    const int32_t* holes;
+    int max_holes;
+    const uint8_t* fill;  // host [3]
+};
+
 }  // namespace nkbk
 
 using namespace nkbk;
+
+static int k1_preprocess_impl(const void* frames_base, const int64_t* frame_desc, int n_frames, const int32_t* boxes,
+                              const int32_t* frame_idx, int n, int mode, int out_h, int out_w, int max_size,
+                              const uint8_t* pad_value, const float* mean255, const float* denom, int channel_swap,
+                              void* out, int out_dtype, uint8_t* out_u8, int32_t* bad_count, const K1AugArgs* aug,
+                              void* stream);
 
 extern "C" int nkbk_preprocess_crops(const void* frames_base, const int64_t* frame_desc, int n_frames,
                                      const int32_t* boxes, const int32_t* frame_idx, int n, int mode, int out_h,
                                      int out_w, int max_size, const uint8_t* pad_value, const float* mean255,
                                      const float* denom, int channel_swap, void* out, int out_dtype, uint8_t* out_u8,
                                      int32_t* bad_count, void* stream) {
+    return k1_preprocess_impl(frames_base, frame_desc, n_frames, boxes, frame_idx, n, mode, out_h, out_w, max_size,
+                              pad_value, mean255, denom, channel_swap, out, out_dtype, out_u8, bad_count, nullptr,
+                              stream);
+}
+
+extern "C" int nkbk_preprocess_crops_aug(const void* frames_base, const int64_t* frame_desc, int n_frames,
+                                         const int32_t* boxes, const int32_t* frame_idx, int n, int mode, int out_h,
+                                         int out_w, int max_size, const uint8_t* pad_value, const float* mean255,
+                                         const float* denom, int channel_swap, const int32_t* aug_flags,
+                                         const float* aug_alpha, const float* aug_beta, const int32_t* aug_holes,
+                                         int max_holes, const uint8_t* hole_fill, void* out, int out_dtype,
+                                         uint8_t* out_u8, int32_t* bad_count, void* stream) {
+    NKBK_CHECK_ARG(n <= 0 || aug_flags != nullptr, "nkbk_preprocess_crops_aug: NULL aug_flags");
+    NKBK_CHECK_ARG(n <= 0 || (aug_alpha != nullptr && aug_beta != nullptr), "nkbk_preprocess_crops_aug: NULL aug_alpha / aug_beta");
+    NKBK_CHECK_ARG(max_holes >= 0 && max_holes <= K1_AUG_MAX_HOLES, "nkbk_preprocess_crops_aug: max_holes=%d outside [0,%d]",
+                   max_holes, K1_AUG_MAX_HOLES);
+    NKBK_CHECK_ARG(max_holes == 0 || n <= 0 || aug_holes != nullptr, "nkbk_preprocess_crops_aug: NULL aug_holes");
+    K1AugArgs a{aug_flags, aug_alpha, aug_beta, aug_holes, max_holes, hole_fill};
+    return k1_preprocess_impl(frames_base, frame_desc, n_frames, boxes, frame_idx, n, mode, out_h, out_w, max_size,
+                              pad_value, mean255, denom, channel_swap, out, out_dtype, out_u8, bad_count, &a, stream);
+}
+
+static int k1_preprocess_impl(const void* frames_base, const int64_t* frame_desc, int n_frames, const int32_t* boxes,
+                              const int32_t* frame_idx, int n, int mode, int out_h, int out_w, int max_size,
+                              const uint8_t* pad_value, const float* mean255, const float* denom, int channel_swap,
+                              void* out, int out_dtype, uint8_t* out_u8, int32_t* bad_count, const K1AugArgs* aug,
+                              void* stream) {
     NKBK_CHECK_ARG(n >= 0, "nkbk_preprocess_crops: n=%d < 0", n);
     if (n == 0) return NKBK_OK;
     NKBK_CHECK_ARG(frames_base && frame_desc && boxes && frame_idx && out, "nkbk_preprocess_crops: NULL pointer");
@@ -100,6 +149,13 @@ extern "C" int nkbk_preprocess_crops(const void* frames_base, const int64_t* fra
         p.sel[c] = kSel[channel_swap ? 2 - c : c];
     }
     p.out = out; p.out_u8 = out_u8; p.bad_count = bad_count;
+    p.aug_flags = nullptr; p.aug_alpha = nullptr; p.aug_beta = nullptr; p.aug_holes = nullptr; p.aug_max_holes = 0;
+    p.aug_fill[0] = p.aug_fill[1] = p.aug_fill[2] = 0u;
+    if (aug != nullptr) {
+        p.aug_flags = aug->flags; p.aug_alpha = aug->alpha; p.aug_beta = aug->beta; p.aug_holes = aug->holes;
+        p.aug_max_holes = aug->max_holes;
+        for (int c = 0; c < 3; ++c) p.aug_fill[c] = aug->fill ? aug->fill[c] : 0u;
+    }
 
     // rows per warp: split the height into blocks of <= 64 rows, 4 warps each
     const int nby = (out_h + 63) / 64;
@@ -111,7 +167,7 @@ extern "C" int nkbk_preprocess_crops(const void* frames_base, const int64_t* fra
     // ---- fast path: A.Resize, output width a whole number of 32*J column tiles, no uint8 side output ----
     // Crops whose frame rows are not 16-byte aligned or whose boxes are too wide for the shared-memory ring are
     // left untouched by the TMA kernel and produced by the general kernel in a small-grid fix-up pass.
-    if (mode == NKBK_MODE_STRETCH && out_u8 == nullptr && out_w % 32 == 0) {
+    if (mode == NKBK_MODE_STRETCH && out_u8 == nullptr && out_w % 32 == 0 && aug == nullptr) {
         const int cols = out_w / 32;
         int fj = 0;
         for (int j = 8; j >= 4; --j)
@@ -176,5 +232,11 @@ extern "C" int nkbk_debug_letterbox(int h, int w, int max_size, int out_h, int o
         return NKBK_E_UNSUPPORTED;
     }
     out4[0] = nh; out4[1] = nw; out4[2] = top; out4[3] = left;
+    return NKBK_OK;
+}
+
+extern "C" int nkbk_debug_brightness_contrast_lut(float alpha, float beta, uint8_t* lut256) {
+    NKBK_CHECK_ARG(lut256 != nullptr, "nkbk_debug_brightness_contrast_lut: NULL output");
+    for (int v = 0; v < 256; ++v) lut256[v] = (uint8_t)k1_brightness_contrast((uint32_t)v, alpha, beta);
     return NKBK_OK;
 }

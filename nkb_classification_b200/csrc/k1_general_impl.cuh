@@ -56,10 +56,14 @@ __device__ __forceinline__ void convert_row(uint32_t (&H)[JMAX][3], const RawRow
 // writes every column, no border handling, no uint8 side output.  GENERAL = true: everything.
 // One warp produces output rows [y_begin, y_begin + nrows) (nrows <= 32) of `crop`, columns ox0 + 32*j.
 // `count_bad`: this warp is the one that reports an invalid box to bad_count.
-template <int JMAX, typename OutT, bool GENERAL, bool WRITE_U8>
+// AUG = true (general variant only): the per-crop train-time augmentations of K1Params::aug_* are applied to the
+// resized + padded uint8 pixel before Normalize; flips mirror the store address, so a band of source-order rows
+// lands on the mirrored rows / columns of the output.
+template <int JMAX, typename OutT, bool GENERAL, bool WRITE_U8, bool AUG = false>
 __device__ __forceinline__ void k1_process_band(const K1Params& p, const int crop, const CropGeom& g, const int y_begin,
                                                 const int nrows, const int ox0, const bool count_bad) {
     static_assert(GENERAL || !WRITE_U8, "uint8 side output only in the general variant");
+    static_assert(GENERAL || !AUG, "augmentations only in the general variant");
     const int lane = threadIdx.x & 31;
     const int bx0 = g.bx0, by0 = g.by0, bw = g.bw, bh = g.bh, fw = g.fw;
     const int64_t f_off = g.f_off, pitch = g.pitch;
@@ -76,6 +80,42 @@ __device__ __forceinline__ void k1_process_band(const K1Params& p, const int cro
 #pragma unroll
         for (int j = 0; j < JMAX; ++j) wmask |= uint32_t(ox0 + 32 * j < p.out_w) << j;
     }
+
+    // ---- augmentation parameters of this crop ----
+    int aflags = 0, nholes = 0;
+    float a_alpha = 1.f, a_beta = 0.f;
+    const int32_t* holes = nullptr;
+    if (AUG) {
+        aflags = __ldg(p.aug_flags + crop);
+        nholes = min(aflags >> 8, p.aug_max_holes);
+        if (aflags & K1_AUG_BC) { a_alpha = __ldg(p.aug_alpha + crop); a_beta = __ldg(p.aug_beta + crop); }
+        holes = p.aug_holes + (int64_t)crop * p.aug_max_holes * 4;
+    }
+    const bool hflip = AUG && (aflags & K1_AUG_HFLIP), vflip = AUG && (aflags & K1_AUG_VFLIP);
+    const int xstep = hflip ? -32 : 32;                       // destination column step between this lane's j's
+    const int xd0 = hflip ? p.out_w - 1 - ox0 : ox0;          // destination column of j = 0
+    // final uint8 value of channel c at destination (yd, xd) given the resized / padded value v
+    auto augment = [&](uint32_t v, int c, bool in_hole) -> uint32_t {
+        if (!AUG) return v;
+        if (aflags & K1_AUG_BC) v = k1_brightness_contrast(v, a_alpha, a_beta);
+        return in_hole ? p.aug_fill[c] : v;
+    };
+    // bit j set: destination column of (lane, j) on destination row yd lies inside a CoarseDropout hole
+    auto hole_mask = [&](int yd) -> uint32_t {
+        uint32_t m = 0;
+        if (!AUG) return m;
+        for (int h = 0; h < nholes; ++h) {
+            const int x1 = __ldg(holes + 4 * h + 0), y1 = __ldg(holes + 4 * h + 1);
+            const int x2 = __ldg(holes + 4 * h + 2), y2 = __ldg(holes + 4 * h + 3);
+            if (yd < y1 || yd >= y2) continue;
+#pragma unroll
+            for (int j = 0; j < JMAX; ++j) {
+                const int xd = xd0 + xstep * j;
+                m |= uint32_t(xd >= x1 && xd < x2) << j;
+            }
+        }
+        return m;
+    };
 
     if (!ok) {
         // empty / out-of-frame box: emit the normalised pad value, count it once per crop
@@ -179,19 +219,30 @@ __device__ __forceinline__ void k1_process_band(const K1Params& p, const int cro
         const int r1 = __shfl_sync(0xffffffffu, my_r1, yy);
         const uint32_t b0 = __shfl_sync(0xffffffffu, my_b0, yy);
         const uint32_t b1 = __shfl_sync(0xffffffffu, my_b1, yy);
-        const int y = y_begin + yy;
-        OutT* o = out_crop + (int64_t)y * p.out_w + ox0;
-        uint8_t* u = WRITE_U8 ? p.out_u8 + (((int64_t)crop * p.out_h + y) * p.out_w + ox0) * 3 : nullptr;
+        const int y = AUG && vflip ? p.out_h - 1 - (y_begin + yy) : y_begin + yy;   // destination row
+        OutT* o = out_crop + (int64_t)y * p.out_w + xd0;
+        uint8_t* u = WRITE_U8 ? p.out_u8 + (((int64_t)crop * p.out_h + y) * p.out_w + xd0) * 3 : nullptr;
+        const uint32_t hmask = hole_mask(y);
 
         if (GENERAL && r0 < 0) {  // letterbox border row
 #pragma unroll
             for (int j = 0; j < JMAX; ++j)
                 if (wmask >> j & 1) {
+                    if (AUG) {
+                        const float mm[3] = {m0, m1, m2}, dd[3] = {d0, d1, d2};
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) store_out<OutT>(o + c * plane + 32 * j, p.padf[c]);
-                    if (WRITE_U8) {
-                        u[96 * j + 0] = (uint8_t)p.padu[0]; u[96 * j + 1] = (uint8_t)p.padu[1];
-                        u[96 * j + 2] = (uint8_t)p.padu[2];
+                        for (int c = 0; c < 3; ++c) {
+                            const uint32_t v = augment(p.padu[c], c, hmask >> j & 1);
+                            store_out<OutT>(o + c * plane + xstep * j, __fmul_rn(__fsub_rn((float)v, mm[c]), dd[c]));
+                            if (WRITE_U8) u[3 * xstep * j + c] = (uint8_t)v;
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) store_out<OutT>(o + c * plane + 32 * j, p.padf[c]);
+                        if (WRITE_U8) {
+                            u[96 * j + 0] = (uint8_t)p.padu[0]; u[96 * j + 1] = (uint8_t)p.padu[1];
+                            u[96 * j + 2] = (uint8_t)p.padu[2];
+                        }
                     }
                 }
             continue;
@@ -231,16 +282,18 @@ __device__ __forceinline__ void k1_process_band(const K1Params& p, const int cro
                 const uint32_t t1 = __umulhi(b1, Hb[j][c]);
                 px[c] = (t0 + t1 + 2u) >> 2;
                 if (GENERAL && !(vmask >> j & 1)) px[c] = p.padu[c];
+                if (AUG) px[c] = augment(px[c], c, hmask >> j & 1);
             }
             const float f0 = __fmul_rn(__fsub_rn((float)px[0], m0), d0);
             const float f1 = __fmul_rn(__fsub_rn((float)px[1], m1), d1);
             const float f2 = __fmul_rn(__fsub_rn((float)px[2], m2), d2);
             if (!GENERAL || (wmask >> j & 1)) {
-                store_out<OutT>(o + 32 * j, f0);
-                store_out<OutT>(o + plane + 32 * j, f1);
-                store_out<OutT>(o + 2 * plane + 32 * j, f2);
+                const int xs = AUG ? xstep * j : 32 * j;
+                store_out<OutT>(o + xs, f0);
+                store_out<OutT>(o + plane + xs, f1);
+                store_out<OutT>(o + 2 * plane + xs, f2);
                 if (WRITE_U8) {
-                    u[96 * j + 0] = (uint8_t)px[0]; u[96 * j + 1] = (uint8_t)px[1]; u[96 * j + 2] = (uint8_t)px[2];
+                    u[3 * xs + 0] = (uint8_t)px[0]; u[3 * xs + 1] = (uint8_t)px[1]; u[3 * xs + 2] = (uint8_t)px[2];
                 }
             }
         }

@@ -425,6 +425,9 @@ class DeviceCropLoader:
         self.plan = dataset.transform.plan
         self.pool = ThreadPoolExecutor(max(1, num_workers)) if num_workers and num_workers > 0 else None
         self._staging = None
+        # train pipelines: where the per-sample augmentation parameters come from (None = Python's global `random`,
+        # which is what albumentations draws from, so `random.seed(...)` governs it as in the reference)
+        self.aug_rng = None
 
     def __len__(self):
         n = len(self.sampler) if self.sampler is not None else len(self.dataset)
@@ -460,7 +463,8 @@ class DeviceCropLoader:
         flat = self._staging[:total].to(dev, non_blocking=True)
         img = ops.preprocess_crops(flat, torch.from_numpy(boxes).to(dev, non_blocking=True),
                                    torch.from_numpy(fidx).to(dev, non_blocking=True), self.plan,
-                                   out_dtype=self.out_dtype, frame_desc=desc.to(dev, non_blocking=True))
+                                   out_dtype=self.out_dtype, frame_desc=desc.to(dev, non_blocking=True),
+                                   aug=self.plan.draw(len(samples), self.aug_rng))
         return img, collate_targets([s[2] for s in samples])
 
     def __iter__(self):

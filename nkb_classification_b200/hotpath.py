@@ -46,7 +46,7 @@ class HotPath:
 
     # ---- K1 ----
     def preprocess(self, frames: torch.Tensor, boxes: torch.Tensor, frame_idx: torch.Tensor,
-                   frame_desc: Optional[torch.Tensor] = None) -> torch.Tensor:
+                   frame_desc: Optional[torch.Tensor] = None, aug=None) -> torch.Tensor:
         n = int(frame_idx.numel())
         out = self._images.get(n)
         if out is None:
@@ -57,7 +57,10 @@ class HotPath:
             if self._desc is None or self._desc[0] != key[0]:
                 self._desc = (key[0], ops.frame_descriptors(frames))
             frame_desc = self._desc[1]
-        return ops.preprocess_crops(frames, boxes, frame_idx, self.plan, self.out_dtype, out=out, frame_desc=frame_desc)
+        if aug is None and self.plan.augment is not None:
+            aug = self.plan.draw(n)            # train-time pipeline: draw this batch's per-sample parameters
+        return ops.preprocess_crops(frames, boxes, frame_idx, self.plan, self.out_dtype, out=out, frame_desc=frame_desc,
+                                    aug=aug)
 
     # ---- K2 + K3 + K4 ----
     def _buffers(self, B: int, train: bool, want_probs: bool) -> ops.HeadsBuffers:

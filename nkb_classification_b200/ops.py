@@ -63,8 +63,10 @@ def preprocess_crops(
     out_u8: Optional[torch.Tensor] = None,
     frame_desc: Optional[torch.Tensor] = None,
     bad_count: Optional[torch.Tensor] = None,
+    aug=None,                          # transforms.AugmentBatch (train-time pipeline) or None
 ) -> torch.Tensor:
-    """One K1 launch: [n,3,out_h,out_w] normalised crops (see nkbk_preprocess_crops)."""
+    """One K1 launch: [n,3,out_h,out_w] normalised crops (see nkbk_preprocess_crops / nkbk_preprocess_crops_aug).
+    ``aug``: the per-sample parameters ``plan.draw(n)`` returned; required iff the plan has fused augmentations."""
     _need_cuda("frames", frames)
     _need_cuda("boxes", boxes)
     _need_cuda("frame_idx", frame_idx)
@@ -98,10 +100,29 @@ def preprocess_crops(
     pad = (c_uint8 * 3)(*plan.pad_value)
     m = (c_float * 3)(*plan.mean255)
     d = (c_float * 3)(*plan.denom)
-    rc = lib().nkbk_preprocess_crops(
+    if (aug is None) != (getattr(plan, "augment", None) is None):
+        raise ValueError("`aug` must be given exactly when the plan has fused augmentations (aug = plan.draw(n))")
+    if aug is None:
+        rc = lib().nkbk_preprocess_crops(
+            _ptr(frames), _ptr(frame_desc), n_frames, _ptr(boxes), _ptr(frame_idx), n, plan.mode, plan.out_h,
+            plan.out_w, plan.max_size, pad, m, d, int(plan.channel_swap), _ptr(out), _DT[out_dtype], _ptr(out_u8),
+            _ptr(bad_count), _stream(frames.device),
+        )
+        check(rc)
+        return out
+    if len(aug.flags) != n:
+        raise ValueError(f"augmentation parameters for {len(aug.flags)} samples, batch has {n}")
+    dev = frames.device
+    # four small H2D copies (12 + 16 * max_holes bytes per sample); the kernel is enqueued behind them on this stream
+    a_flags = torch.from_numpy(np.ascontiguousarray(aug.flags, dtype=np.int32)).to(dev, non_blocking=True)
+    a_alpha = torch.from_numpy(np.ascontiguousarray(aug.alpha, dtype=np.float32)).to(dev, non_blocking=True)
+    a_beta = torch.from_numpy(np.ascontiguousarray(aug.beta, dtype=np.float32)).to(dev, non_blocking=True)
+    a_holes = torch.from_numpy(np.ascontiguousarray(aug.holes, dtype=np.int32)).to(dev, non_blocking=True)
+    fill = (c_uint8 * 3)(*[int(v) for v in aug.fill])
+    rc = lib().nkbk_preprocess_crops_aug(
         _ptr(frames), _ptr(frame_desc), n_frames, _ptr(boxes), _ptr(frame_idx), n, plan.mode, plan.out_h, plan.out_w,
-        plan.max_size, pad, m, d, int(plan.channel_swap), _ptr(out), _DT[out_dtype], _ptr(out_u8), _ptr(bad_count),
-        _stream(frames.device),
+        plan.max_size, pad, m, d, int(plan.channel_swap), _ptr(a_flags), _ptr(a_alpha), _ptr(a_beta), _ptr(a_holes),
+        aug.max_holes, fill, _ptr(out), _DT[out_dtype], _ptr(out_u8), _ptr(bad_count), _stream(dev),
     )
     check(rc)
     return out
@@ -114,6 +135,13 @@ def debug_axis_table(dsize: int, ssize: int, horizontal: bool):
     c1 = np.empty(dsize, dtype=np.int32)
     check(lib().nkbk_debug_axis_table(dsize, ssize, int(horizontal), s.ctypes.data, c0.ctypes.data, c1.ctypes.data))
     return s, c0, c1
+
+
+def debug_brightness_contrast_lut(alpha: float, beta255: float) -> np.ndarray:
+    """Host-only: the 256-entry brightness/contrast table K1 evaluates per pixel."""
+    lut = np.empty(256, dtype=np.uint8)
+    check(lib().nkbk_debug_brightness_contrast_lut(float(alpha), float(beta255), lut.ctypes.data))
+    return lut
 
 
 def debug_letterbox(h: int, w: int, max_size: int, out_h: int, out_w: int):

@@ -13,11 +13,20 @@ becomes a :class:`PreprocessPlan` that one fused kernel executes for the whole
 batch.  Real albumentations objects are accepted when that package is present
 (duck-typed on class name + public attributes); the small classes below carry
 the same names / keyword arguments so a config can be written without it.
-Anything else (random train-time augmentations, other border modes or
-interpolations) raises ``NotImplementedError`` -- there is no silent fallback.
+
+Train-time pipelines (configs/singletask_config.py:162-201) may add, between the
+geometry and Normalize, the ops whose arithmetic K1 fuses: ``HorizontalFlip``,
+``VerticalFlip``, ``RandomBrightnessContrast`` (brightness_by_max) and
+``CoarseDropout`` (last).  Their per-sample parameters are drawn on the host by
+:func:`draw_augmentations` (same distributions and draw order as albumentations
+1.3.x with Python's ``random``) and shipped to the kernel as small arrays.
+Anything else (HueSaturationValue, MotionBlur, fog / rain / shadow, other border
+modes or interpolations) raises ``NotImplementedError`` -- no silent fallback.
 """
 from __future__ import annotations
 
+import dataclasses
+import random as _random
 from dataclasses import dataclass, field
 from typing import Any, List, Optional, Sequence, Tuple
 
@@ -58,6 +67,44 @@ class Normalize(_Op):
         self.mean, self.std, self.max_pixel_value = tuple(mean), tuple(std), float(max_pixel_value)
 
 
+class HorizontalFlip(_Op):
+    def __init__(self, always_apply=False, p=0.5):
+        self.p, self.always_apply = float(p), bool(always_apply)
+
+
+class VerticalFlip(_Op):
+    def __init__(self, always_apply=False, p=0.5):
+        self.p, self.always_apply = float(p), bool(always_apply)
+
+
+def _to_tuple(v, low=None):
+    """albumentations 1.3 ``to_tuple``: a scalar x becomes (-x, x); a pair is kept AS GIVEN (not sorted)."""
+    if isinstance(v, (tuple, list)):
+        if len(v) != 2:
+            raise ValueError(f"limit {v!r} must be a scalar or a pair")
+        return (float(v[0]), float(v[1]))
+    return (-float(v), float(v)) if low is None else (float(low), float(v))
+
+
+class RandomBrightnessContrast(_Op):
+    def __init__(self, brightness_limit=0.2, contrast_limit=0.2, brightness_by_max=True, always_apply=False, p=0.5):
+        self.brightness_limit, self.contrast_limit = _to_tuple(brightness_limit), _to_tuple(contrast_limit)
+        self.brightness_by_max, self.p, self.always_apply = bool(brightness_by_max), float(p), bool(always_apply)
+
+
+class CoarseDropout(_Op):
+    def __init__(self, max_holes=8, max_height=8, max_width=8, min_holes=None, min_height=None, min_width=None,
+                 fill_value=0, mask_fill_value=None, always_apply=False, p=0.5):
+        self.max_holes, self.max_height, self.max_width = max_holes, max_height, max_width
+        self.min_holes = min_holes if min_holes is not None else max_holes
+        self.min_height = min_height if min_height is not None else max_height
+        self.min_width = min_width if min_width is not None else max_width
+        self.fill_value, self.mask_fill_value = fill_value, mask_fill_value
+        self.p, self.always_apply = float(p), bool(always_apply)
+        if not 0 < self.min_holes <= self.max_holes:
+            raise ValueError(f"Invalid combination of min_holes and max_holes. Got: {[min_holes, max_holes]}")
+
+
 class ToTensorV2(_Op):
     def __init__(self, transpose_mask=False, always_apply=True, p=1.0):
         pass
@@ -66,6 +113,91 @@ class ToTensorV2(_Op):
 class Compose(_Op):
     def __init__(self, transforms: Sequence[Any], **kwargs):
         self.transforms = list(transforms)
+
+
+MAX_HOLES = 16   # K1_AUG_MAX_HOLES
+AUG_HFLIP, AUG_VFLIP, AUG_BC = 1, 2, 4
+
+
+@dataclass(frozen=True)
+class AugmentSpec:
+    """The random train-time ops K1 fuses, in the order the pipeline lists them (= the order their parameters are
+    drawn in).  ``order`` holds op names out of {"HorizontalFlip", "VerticalFlip", "RandomBrightnessContrast",
+    "CoarseDropout"}."""
+    order: Tuple[str, ...] = ()
+    hflip_p: float = 0.0
+    vflip_p: float = 0.0
+    bc_p: float = 0.0
+    brightness_limit: Tuple[float, float] = (0.0, 0.0)
+    contrast_limit: Tuple[float, float] = (0.0, 0.0)
+    cd_p: float = 0.0
+    holes: Tuple[int, int] = (1, 1)                    # min_holes, max_holes
+    hole_h: Tuple[Any, Any] = (8, 8)                   # min_height, max_height (both int, or both float fractions)
+    hole_w: Tuple[Any, Any] = (8, 8)
+    fill: Tuple[int, int, int] = (0, 0, 0)             # as stored into a uint8 image
+
+
+@dataclass
+class AugmentBatch:
+    """Per-sample parameters of one batch, host side (numpy); ``ops.preprocess_crops`` uploads them."""
+    flags: np.ndarray       # int32 [n]
+    alpha: np.ndarray       # float32 [n]
+    beta: np.ndarray        # float32 [n] = f32(brightness * 255)
+    holes: np.ndarray       # int32 [n, max_holes, 4]
+    fill: Tuple[int, int, int]
+    brightness: np.ndarray  # float64 [n], the raw draw (the oracle re-derives beta * 255 from it)
+
+    @property
+    def max_holes(self) -> int:
+        return int(self.holes.shape[1])
+
+
+def draw_augmentations(spec: AugmentSpec, n: int, out_h: int, out_w: int, rng=None) -> AugmentBatch:
+    """Draw what ``A.Compose.__call__`` would draw for ``n`` samples: per op, ``random() < p`` and then the op's
+    ``get_params`` (albumentations 1.3.x: RandomBrightnessContrast draws contrast then brightness with ``uniform``;
+    CoarseDropout draws ``randint(min_holes, max_holes)`` holes, each ``randint`` sizes (or ``int(size * uniform)``
+    for fractional limits) and then ``y1``, ``x1``).  ``rng``: a ``random.Random`` (default: the module-level one,
+    which is what albumentations itself uses)."""
+    rng = rng or _random
+    max_holes = max(1, spec.holes[1]) if "CoarseDropout" in spec.order else 1
+    flags = np.zeros(n, dtype=np.int32)
+    alpha = np.ones(n, dtype=np.float32)
+    beta = np.zeros(n, dtype=np.float32)
+    bright = np.zeros(n, dtype=np.float64)
+    holes = np.zeros((n, max_holes, 4), dtype=np.int32)
+    for i in range(n):
+        f = 0
+        for name in spec.order:
+            if name == "HorizontalFlip":
+                if rng.random() < spec.hflip_p:
+                    f |= AUG_HFLIP
+            elif name == "VerticalFlip":
+                if rng.random() < spec.vflip_p:
+                    f |= AUG_VFLIP
+            elif name == "RandomBrightnessContrast":
+                if rng.random() < spec.bc_p:
+                    a = 1.0 + rng.uniform(spec.contrast_limit[0], spec.contrast_limit[1])
+                    b = 0.0 + rng.uniform(spec.brightness_limit[0], spec.brightness_limit[1])
+                    f |= AUG_BC
+                    alpha[i] = np.float32(a)          # `lut *= alpha`: python float enters a float32 multiply
+                    beta[i] = np.float32(b * 255)     # `lut += beta * max_value`: double product, float32 add
+                    bright[i] = b
+            elif name == "CoarseDropout":
+                if rng.random() < spec.cd_p:
+                    k = rng.randint(spec.holes[0], spec.holes[1])
+                    for h in range(k):
+                        if all(isinstance(v, (int, np.integer)) for v in (*spec.hole_h, *spec.hole_w)):
+                            hh = rng.randint(spec.hole_h[0], spec.hole_h[1])
+                            hw = rng.randint(spec.hole_w[0], spec.hole_w[1])
+                        else:
+                            hh = int(out_h * rng.uniform(spec.hole_h[0], spec.hole_h[1]))
+                            hw = int(out_w * rng.uniform(spec.hole_w[0], spec.hole_w[1]))
+                        y1 = rng.randint(0, out_h - hh)
+                        x1 = rng.randint(0, out_w - hw)
+                        holes[i, h] = (x1, y1, x1 + hw, y1 + hh)
+                    f |= k << 8
+        flags[i] = f
+    return AugmentBatch(flags, alpha, beta, holes, spec.fill, bright)
 
 
 @dataclass(frozen=True)
@@ -79,10 +211,14 @@ class PreprocessPlan:
     mean255: Tuple[float, float, float]   # f32(mean) * f32(max_pixel_value), as float32 values
     denom: Tuple[float, float, float]     # 1 / (f32(std) * f32(max_pixel_value))
     channel_swap: bool = False
+    augment: Optional[AugmentSpec] = None   # train-time ops fused into K1 (None: val / inference pipeline)
 
     def with_channel_swap(self, swap: bool) -> "PreprocessPlan":
-        return PreprocessPlan(self.mode, self.out_h, self.out_w, self.max_size, self.pad_value, self.mean255,
-                              self.denom, bool(swap))
+        return dataclasses.replace(self, channel_swap=bool(swap))
+
+    def draw(self, n: int, rng=None) -> Optional[AugmentBatch]:
+        """Per-sample augmentation parameters for a batch of ``n`` (None for a val / inference pipeline)."""
+        return None if self.augment is None else draw_augmentations(self.augment, n, self.out_h, self.out_w, rng)
 
 
 def normalize_constants(mean, std, max_pixel_value=255.0):
@@ -113,15 +249,81 @@ def _as_int_triplet(value) -> Tuple[int, int, int]:
     return (v[0], v[1], v[2])
 
 
+_AUG_KINDS = ("HorizontalFlip", "VerticalFlip", "RandomBrightnessContrast", "CoarseDropout")
+
+
+def _prob(op) -> float:
+    return 1.0 if getattr(op, "always_apply", False) else float(getattr(op, "p", 0.5))
+
+
+def _fill_as_u8(value) -> Tuple[int, int, int]:
+    """What ``img[y1:y2, x1:x2] = fill_value`` stores into a uint8 image (floats truncate: [0, 0.5, 1] -> 0, 0, 1)."""
+    v = np.asarray(value, dtype=np.float64).reshape(-1)
+    if v.size == 1:
+        v = np.repeat(v, 3)
+    if v.size != 3:
+        raise NotImplementedError(f"CoarseDropout fill_value {value!r}: need a scalar or 3 channels")
+    if np.any(v < 0) or np.any(v >= 256):
+        raise NotImplementedError(f"CoarseDropout fill_value {value!r} outside the uint8 range")
+    return tuple(int(x) for x in v.astype(np.uint8))
+
+
+def _compile_augment(aug_ops) -> Optional[AugmentSpec]:
+    if not aug_ops:
+        return None
+    kw = {"order": tuple(_kind(o) for o in aug_ops)}
+    for op in aug_ops:
+        k = _kind(op)
+        if k == "HorizontalFlip":
+            kw["hflip_p"] = _prob(op)
+        elif k == "VerticalFlip":
+            kw["vflip_p"] = _prob(op)
+        elif k == "RandomBrightnessContrast":
+            if not getattr(op, "brightness_by_max", True):
+                raise NotImplementedError("RandomBrightnessContrast(brightness_by_max=False) needs the image mean; "
+                                          "only brightness_by_max=True is fused")
+            kw["bc_p"] = _prob(op)
+            kw["brightness_limit"] = _to_tuple(op.brightness_limit)
+            kw["contrast_limit"] = _to_tuple(op.contrast_limit)
+        elif k == "CoarseDropout":
+            if getattr(op, "mask_fill_value", None) is not None:
+                raise NotImplementedError("CoarseDropout(mask_fill_value=...) is not supported (no masks on this path)")
+            if op.max_holes > MAX_HOLES:
+                raise NotImplementedError(f"CoarseDropout: at most {MAX_HOLES} holes are fused, got {op.max_holes}")
+            sizes = (op.min_height, op.max_height, op.min_width, op.max_width)
+            ints = all(isinstance(v, (int, np.integer)) for v in sizes)
+            floats = all(isinstance(v, float) for v in sizes)
+            if not (ints or floats):   # the same check albumentations makes when it draws
+                raise ValueError("Min width, max width, min height and max height should all either be ints or floats. "
+                                 f"Got: {[type(v) for v in sizes]} respectively")
+            kw["cd_p"] = _prob(op)
+            kw["holes"] = (int(op.min_holes), int(op.max_holes))
+            kw["hole_h"] = (op.min_height, op.max_height)
+            kw["hole_w"] = (op.min_width, op.max_width)
+            kw["fill"] = _fill_as_u8(op.fill_value)
+    return AugmentSpec(**kw)
+
+
 def compile_pipeline(pipeline, channel_swap: bool = False) -> PreprocessPlan:
     """``A.Compose([...])`` (or a plain list of ops) -> PreprocessPlan."""
     ops = list(getattr(pipeline, "transforms", pipeline))
     resize = lms = pad = norm = None
     saw_tensor = False
+    aug_ops: List[Any] = []
     for op in ops:
         k = _kind(op)
         if saw_tensor:
             raise NotImplementedError(f"{k} after ToTensorV2 is not supported")
+        if k in _AUG_KINDS:
+            if norm is not None or (resize is None and (lms is None or pad is None)):
+                raise NotImplementedError(f"{k} must sit between the geometry ops and Normalize")
+            if any(_kind(a) == k for a in aug_ops):
+                raise NotImplementedError(f"{k} listed twice")
+            if any(_kind(a) == "CoarseDropout" for a in aug_ops):
+                raise NotImplementedError("CoarseDropout must be the last fused augmentation (its fill is not "
+                                          "flipped or re-coloured)")
+            aug_ops.append(op)
+            continue
         if k == "Resize" and resize is None and lms is None:
             resize = op
         elif k == "LongestMaxSize" and lms is None and resize is None:
@@ -134,8 +336,9 @@ def compile_pipeline(pipeline, channel_swap: bool = False) -> PreprocessPlan:
             saw_tensor = True
         else:
             raise NotImplementedError(
-                f"pipeline op {op!r} is outside the fused deterministic subset "
-                "{Resize | LongestMaxSize+PadIfNeeded, Normalize, ToTensorV2}"
+                f"pipeline op {op!r} is outside the fused subset "
+                "{Resize | LongestMaxSize+PadIfNeeded, [HorizontalFlip, VerticalFlip, RandomBrightnessContrast, "
+                "CoarseDropout], Normalize, ToTensorV2}"
             )
         if norm is not None and k in ("Resize", "LongestMaxSize", "PadIfNeeded"):
             raise NotImplementedError("geometry ops must precede Normalize")
@@ -149,9 +352,12 @@ def compile_pipeline(pipeline, channel_swap: bool = False) -> PreprocessPlan:
     m, d = normalize_constants(norm.mean, norm.std, getattr(norm, "max_pixel_value", 255.0))
     mean255 = tuple(float(x) for x in m)
     denom = tuple(float(x) for x in d)
+    if float(getattr(norm, "max_pixel_value", 255.0)) != 255.0 and aug_ops:
+        raise NotImplementedError("fused augmentations assume max_pixel_value=255 (uint8 images)")
+    augment = _compile_augment(aug_ops)
     if resize is not None:
         return PreprocessPlan(MODE_STRETCH, int(resize.height), int(resize.width), 0, (0, 0, 0), mean255, denom,
-                              bool(channel_swap))
+                              bool(channel_swap), augment)
     if lms is None or pad is None:
         raise NotImplementedError("need Resize, or LongestMaxSize followed by PadIfNeeded (fixed output size)")
     if getattr(pad, "border_mode", None) != BORDER_CONSTANT:
@@ -166,4 +372,4 @@ def compile_pipeline(pipeline, channel_swap: bool = False) -> PreprocessPlan:
     if max_size > min(out_h, out_w):
         raise NotImplementedError("LongestMaxSize larger than PadIfNeeded would give variable output sizes")
     return PreprocessPlan(MODE_LETTERBOX, out_h, out_w, int(max_size), _as_int_triplet(getattr(pad, "value", None)),
-                          mean255, denom, bool(channel_swap))
+                          mean255, denom, bool(channel_swap), augment)

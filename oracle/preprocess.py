@@ -12,6 +12,9 @@ reference does on DataLoader workers:
   A.Normalize, ToTensorV2)                      metrics/det_cls_val.py:86-109
 * ``Evaluator.classify_crops`` box conversion   metrics/det_cls_val.py:228-239
 
+* train-time ops of configs/singletask_config.py:172-194 (A.HorizontalFlip, A.VerticalFlip,
+  A.RandomBrightnessContrast, A.CoarseDropout) with GIVEN per-sample parameters: ``augment_u8``
+
 Two implementations of the 8-bit bilinear resize live here so the oracle checks
 itself: ``resize_cv2`` calls OpenCV (what the reference executes, through
 albumentations), ``resize_int`` is an independent integer restatement of
@@ -224,21 +227,67 @@ def resize_stage_u8(crop: np.ndarray, plan: Plan, impl: str = "int") -> np.ndarr
     return canvas
 
 
-def preprocess_crop(frame: np.ndarray, box, plan: Plan, impl: str = "int"):
-    """One sample: returns (u8 HWC resized/padded, f32 CHW normalised)."""
+@dataclass
+class AugSample:
+    """Parameters one Compose call would have drawn for one sample (albumentations 1.3.x semantics)."""
+    hflip: bool = False
+    vflip: bool = False
+    bc: bool = False                 # RandomBrightnessContrast applied
+    alpha: float = 1.0               # 1 + contrast draw
+    beta: float = 0.0                # brightness draw (fraction of max_value: brightness_by_max=True)
+    holes: Sequence[Tuple[int, int, int, int]] = ()   # CoarseDropout (x1, y1, x2, y2), ends exclusive
+    fill: Tuple[int, int, int] = (0, 0, 0)
+
+
+def brightness_contrast_lut(alpha: float, beta: float) -> np.ndarray:
+    """albumentations 1.3 ``_brightness_contrast_adjust_uint`` with beta_by_max=True: a float32 ramp times
+    alpha (python float -> float32 multiply), plus beta * 255 (python double product, added in float32), clipped to
+    [0, 255] and truncated to uint8.  The ``!= 1`` / ``!= 0`` short-cuts of the original are exact no-ops."""
+    lut = np.arange(0, 256).astype("float32")
+    if alpha != 1:
+        lut *= alpha
+    if beta != 0:
+        lut += beta * 255
+    return np.clip(lut, 0, 255).astype(np.uint8)
+
+
+def augment_u8(img: np.ndarray, a: "AugSample") -> np.ndarray:
+    """The deterministic part of the train pipeline on the resized / padded uint8 HWC image, in Compose order:
+    HorizontalFlip (cv2.flip(img, 1)), VerticalFlip (cv2.flip(img, 0)), RandomBrightnessContrast (cv2.LUT),
+    CoarseDropout (``img[y1:y2, x1:x2] = fill_value`` per hole)."""
+    import cv2
+
+    out = np.ascontiguousarray(img)
+    if a.hflip:
+        out = cv2.flip(out, 1)
+    if a.vflip:
+        out = cv2.flip(out, 0)
+    if a.bc:
+        out = cv2.LUT(out, brightness_contrast_lut(a.alpha, a.beta))
+    if len(a.holes):
+        out = out.copy()
+        for x1, y1, x2, y2 in a.holes:
+            out[y1:y2, x1:x2] = a.fill
+    return out
+
+
+def preprocess_crop(frame: np.ndarray, box, plan: Plan, impl: str = "int", aug: Optional["AugSample"] = None):
+    """One sample: returns (u8 HWC resized/padded[/augmented], f32 CHW normalised)."""
     x0, y0, x1, y1 = [int(v) for v in box]
     crop = frame[y0:y1, x0:x1]  # dataset.py:404
     u8 = resize_stage_u8(crop, plan, impl)
+    if aug is not None:
+        u8 = augment_u8(u8, aug)
     f = normalize_f32(u8, plan.mean, plan.std, plan.max_pixel_value)
     chw = np.ascontiguousarray(f.transpose(2, 0, 1))  # ToTensorV2
     return u8, chw
 
 
-def preprocess_batch(frames, boxes, frame_idx, plan: Plan, impl: str = "int"):
+def preprocess_batch(frames, boxes, frame_idx, plan: Plan, impl: str = "int", augs=None):
     """default_collate of B samples: ([B,H,W,3] u8, [B,3,H,W] f32)."""
     u8s, chws = [], []
-    for b, fi in zip(boxes, frame_idx):
-        u8, chw = preprocess_crop(frames[int(fi)], b, plan, impl)
+    for i, (b, fi) in enumerate(zip(boxes, frame_idx)):
+        u8, chw = preprocess_crop(frames[int(fi)], b, plan, impl, None if augs is None else augs[i])
         u8s.append(u8)
         chws.append(chw)
     return np.stack(u8s), np.stack(chws)

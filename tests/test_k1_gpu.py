@@ -287,3 +287,65 @@ def test_k1_whole_image_configs(cuda_device, name, hw, kw):
     assert_same_f32(out_fast, ef32)
     if hw == (224, 224):
         assert np.array_equal(u8.cpu().numpy(), frames)  # identity resize
+
+
+def _aug_samples(batch):
+    """transforms.AugmentBatch -> the oracle's per-sample parameter objects."""
+    out = []
+    for i in range(len(batch.flags)):
+        f = int(batch.flags[i])
+        k = f >> 8
+        out.append(opre.AugSample(hflip=bool(f & 1), vflip=bool(f & 2), bc=bool(f & 4), alpha=float(batch.alpha[i]),
+                                  beta=float(batch.brightness[i]), holes=[tuple(int(v) for v in h) for h in batch.holes[i, :k]],
+                                  fill=batch.fill))
+    return out
+
+
+@pytest.mark.parametrize("kw", [
+    dict(mode="letterbox", out_h=128, out_w=128),                  # the reference train config (img_size 128)
+    dict(mode="letterbox", out_h=96, out_w=160, max_size=90, pad=(3, 50, 200), swap=True),
+    dict(out_h=224, out_w=224),                                    # A.Resize variant, full column tiles
+    dict(out_h=100, out_w=60),                                     # partial column tile + flips
+])
+def test_k1_train_pipeline_augmentations_vs_oracle(cuda_device, kw):
+    """flips + brightness/contrast LUT + CoarseDropout fused into K1 with GIVEN per-sample parameters
+    == cv2.flip / cv2.LUT / slice-assign on the oracle's resized image: uint8 bit-exact, fp32 bit-exact, bf16 = RNE."""
+    import random
+    from nkb_classification_b200 import transforms as T
+    rng = np.random.default_rng(17)
+    frames = rng.integers(0, 256, (3, 270, 480, 3), dtype=np.uint8)
+    boxes = _random_boxes(rng, 120, 270, 480, wmin=6)
+    if kw.get("mode") == "letterbox":
+        ms = kw.get("max_size") or min(kw["out_h"], kw["out_w"])
+        boxes = [b for b in boxes if min(opre.letterbox_geometry(b[3] - b[1], b[2] - b[0], ms, kw["out_h"], kw["out_w"])[:2]) >= 1]
+    boxes += [(0, 0, 480, 270), (0, 0, 7, 270), (0, 260, 480, 270)]
+    fidx = [i % 3 for i in range(len(boxes))]
+    base = make_plan(T, **kw)
+    geo = ([T.Resize(base.out_h, base.out_w)] if base.mode == T.MODE_STRETCH else
+           [T.LongestMaxSize(base.max_size), T.PadIfNeeded(base.out_h, base.out_w, border_mode=0, value=base.pad_value)])
+    plan = T.compile_pipeline(geo + [
+        T.HorizontalFlip(p=0.5), T.VerticalFlip(p=0.5),
+        T.RandomBrightnessContrast(brightness_limit=(-0.2, 0.2), contrast_limit=(0.1, -0.5), p=0.6),
+        T.CoarseDropout(max_holes=4, min_holes=1, max_height=0.2, min_height=0.05, max_width=0.2, min_width=0.05,
+                        fill_value=[0, 0.5, 1], p=0.6),
+        T.Normalize(MEAN, STD), T.ToTensorV2()], channel_swap=base.channel_swap)
+    batch = plan.draw(len(boxes), random.Random(99))
+    assert len({int(f) & 7 for f in batch.flags}) == 8, "the draw should cover every flip / LUT combination"
+    out, u8 = run_k1(cuda_device, frames, boxes, fidx, plan, aug=batch)
+    eu8, ef32 = opre.preprocess_batch(frames, boxes, fidx, oracle_plan(plan), impl="cv2", augs=_aug_samples(batch))
+    assert np.array_equal(u8.cpu().numpy(), eu8)
+    assert_same_f32(out, ef32)
+    outb, _ = run_k1(cuda_device, frames, boxes, fidx, plan, dtype=torch.bfloat16, want_u8=False, aug=batch)
+    assert np.array_equal(outb.view(torch.int16).cpu().numpy().view(np.uint16), opre.f32_to_bf16_bits(ef32).reshape(ef32.shape))
+    # identity parameters reproduce the val pipeline exactly
+    ident = plan.draw(len(boxes), random.Random(1))
+    ident.flags[:] = 0
+    out0, u80 = run_k1(cuda_device, frames, boxes, fidx, plan, aug=ident)
+    ev8, ev32 = preprocess_batch_c(frames, boxes, fidx, oracle_plan(plan))
+    assert np.array_equal(u80.cpu().numpy(), ev8)
+    assert_same_f32(out0, ev32)
+    # the plan refuses to run without its parameters (and a val plan refuses stray ones)
+    with pytest.raises(ValueError):
+        run_k1(cuda_device, frames, boxes, fidx, plan)
+    with pytest.raises(ValueError):
+        run_k1(cuda_device, frames, boxes, fidx, base, aug=batch)

@@ -47,8 +47,102 @@ def test_duck_typed_albumentations_objects():
     [T.LongestMaxSize(8), T.PadIfNeeded(8, 8), T.Normalize(), T.ToTensorV2()],   # default BORDER_REFLECT_101
     [T.LongestMaxSize(16), T.PadIfNeeded(8, 8, border_mode=0), T.Normalize(), T.ToTensorV2()],
     [T.Resize(8, 8, interpolation=2), T.Normalize(), T.ToTensorV2()],            # cubic
-    [type("HorizontalFlip", (), {})(), T.Resize(8, 8), T.Normalize(), T.ToTensorV2()],  # random train-time op
+    [type("HorizontalFlip", (), {})(), T.Resize(8, 8), T.Normalize(), T.ToTensorV2()],  # before the geometry
+    [T.Resize(8, 8), type("HueSaturationValue", (), {})(), T.Normalize(), T.ToTensorV2()],  # not fused (stays on CPU)
+    [T.Resize(8, 8), type("MotionBlur", (), {})(), T.Normalize(), T.ToTensorV2()],
+    [T.Resize(8, 8), T.Normalize(), T.HorizontalFlip(), T.ToTensorV2()],               # after Normalize
+    [T.Resize(8, 8), T.CoarseDropout(), T.HorizontalFlip(), T.Normalize(), T.ToTensorV2()],  # dropout must be last
+    [T.Resize(8, 8), T.VerticalFlip(), T.VerticalFlip(), T.Normalize(), T.ToTensorV2()],
+    [T.Resize(8, 8), T.RandomBrightnessContrast(brightness_by_max=False), T.Normalize(), T.ToTensorV2()],
+    [T.Resize(8, 8), T.CoarseDropout(max_holes=40), T.Normalize(), T.ToTensorV2()],
 ])
 def test_unsupported_pipelines_raise(ops):
     with pytest.raises(NotImplementedError):
         T.compile_pipeline(ops)
+
+
+# ---- train-time pipeline (configs/singletask_config.py:162-201 minus HueSaturationValue) ----
+def reference_train_ops(size=128):
+    return [
+        T.LongestMaxSize(size, always_apply=True),
+        T.PadIfNeeded(size, size, always_apply=True, border_mode=T.BORDER_CONSTANT, value=0),
+        T.HorizontalFlip(p=0.5),
+        T.VerticalFlip(p=0.5),
+        T.RandomBrightnessContrast(brightness_limit=(-0.2, 0.2), contrast_limit=(0.1, -0.5), p=0.5),
+        T.CoarseDropout(max_holes=4, min_holes=1, max_height=0.2, min_height=0.05, max_width=0.2, min_width=0.05,
+                        fill_value=[0, 0.5, 1], p=0.5),
+        T.Normalize(mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)),
+        T.ToTensorV2(),
+    ]
+
+
+def test_compile_train_pipeline_of_the_reference_config():
+    p = T.compile_pipeline(T.Compose(reference_train_ops()))
+    a = p.augment
+    assert a.order == ("HorizontalFlip", "VerticalFlip", "RandomBrightnessContrast", "CoarseDropout")
+    assert (a.hflip_p, a.vflip_p, a.bc_p, a.cd_p) == (0.5, 0.5, 0.5, 0.5)
+    assert a.contrast_limit == (0.1, -0.5)          # kept as given, not sorted (albumentations 1.3 to_tuple)
+    assert a.holes == (1, 4) and a.hole_h == (0.05, 0.2)
+    assert a.fill == (0, 0, 1)                      # what `img[...] = [0, 0.5, 1]` stores into uint8
+    assert T.compile_pipeline(T.Compose([T.Resize(8, 8), T.Normalize(), T.ToTensorV2()])).augment is None
+    assert T.RandomBrightnessContrast(brightness_limit=0.3).brightness_limit == (-0.3, 0.3)
+    with pytest.raises(ValueError):
+        T.CoarseDropout(max_holes=2, min_holes=3)
+    with pytest.raises(ValueError):                 # mixed int / float hole sizes: albumentations' own check
+        T.compile_pipeline([T.Resize(8, 8), T.CoarseDropout(max_height=4, max_width=0.5), T.Normalize(), T.ToTensorV2()])
+
+
+def test_draw_follows_compose_call_order():
+    """Replaying the draws by hand with the same random.Random stream gives the same parameters:
+    per op `random() < p`, then RandomBrightnessContrast: contrast, brightness; CoarseDropout: n, (h, w, y1, x1) * n."""
+    import random
+    p = T.compile_pipeline(T.Compose(reference_train_ops(64)))
+    n = 200
+    b = p.draw(n, random.Random(1234))
+    r = random.Random(1234)
+    for i in range(n):
+        hf = r.random() < 0.5
+        vf = r.random() < 0.5
+        bc = r.random() < 0.5
+        if bc:
+            alpha = 1.0 + r.uniform(0.1, -0.5)
+            beta = 0.0 + r.uniform(-0.2, 0.2)
+            assert b.alpha[i] == np.float32(alpha) and b.beta[i] == np.float32(beta * 255)
+            assert 0.5 <= alpha <= 1.1 and -0.2 <= beta <= 0.2
+        holes = []
+        if r.random() < 0.5:
+            for _ in range(r.randint(1, 4)):
+                hh, hw = int(64 * r.uniform(0.05, 0.2)), int(64 * r.uniform(0.05, 0.2))
+                y1 = r.randint(0, 64 - hh)
+                x1 = r.randint(0, 64 - hw)
+                holes.append((x1, y1, x1 + hw, y1 + hh))
+        assert b.flags[i] == (int(hf) | 2 * int(vf) | 4 * int(bc) | len(holes) << 8)
+        assert [tuple(h) for h in b.holes[i, :len(holes)]] == holes
+    assert 60 < int((b.flags & 1).sum()) < 140 and 60 < int((b.flags >> 2 & 1).sum()) < 140
+    assert T.compile_pipeline([T.Resize(8, 8), T.Normalize(), T.ToTensorV2()]).draw(5) is None
+
+
+def test_brightness_contrast_lut_matches_oracle(nkbk_lib):
+    """The per-pixel arithmetic K1 uses (compiled for the host) == the albumentations LUT restated in the oracle."""
+    import random
+    from nkb_classification_b200 import ops
+    r = random.Random(5)
+    cases = [(1.0, 0.0), (1.1, 0.2), (0.5, -0.2), (1.0, 0.1), (0.73, 0.0)]
+    cases += [(1.0 + r.uniform(0.1, -0.5), r.uniform(-0.2, 0.2)) for _ in range(300)]
+    cases += [(1.0 + r.uniform(-1.0, 1.0), r.uniform(-1.0, 1.0)) for _ in range(100)]
+    for alpha, beta in cases:
+        got = ops.debug_brightness_contrast_lut(np.float32(alpha), np.float32(beta * 255))
+        assert np.array_equal(got, opre.brightness_contrast_lut(alpha, beta)), (alpha, beta)
+
+
+def test_oracle_augment_is_cv2_and_numpy():
+    import cv2
+    rng = np.random.default_rng(2)
+    img = rng.integers(0, 256, (20, 30, 3), dtype=np.uint8)
+    a = opre.AugSample(hflip=True, vflip=True, bc=True, alpha=0.8, beta=0.1, holes=[(3, 4, 9, 11)], fill=(0, 0, 1))
+    out = opre.augment_u8(img, a)
+    exp = img[::-1, ::-1].copy()
+    exp = cv2.LUT(exp, np.clip(np.arange(256, dtype=np.float32) * np.float32(0.8) + np.float32(0.1 * 255), 0, 255).astype(np.uint8))
+    exp[4:11, 3:9] = (0, 0, 1)
+    assert np.array_equal(out, exp)
+    assert np.array_equal(opre.augment_u8(img, opre.AugSample()), img)
