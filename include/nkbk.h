@@ -192,6 +192,28 @@ int nkbk_argmax_confusion(const void* logits, int dtype, int B, int ld, const in
                           const int64_t* labels, int32_t* out_pred, int64_t* cm, void* stream);
 
 /* ------------------------------------------------------------------------
+ * K5  exact one-vs-rest ROC-AUC statistics on the device
+ *
+ * Replaces, for the quantity that needs every sample of the epoch: the per-step
+ * confidence lists of BaseLogger.log_iter (logging.py:270,279) + label_binarize +
+ * roc_auc_score of compute_targetwise_metrics (metrics.py:33-42).
+ *
+ *   probs       fp32 [N][ld], the epoch's K2 probabilities (device resident)
+ *   labels      int64 [N][T]; a row whose label is outside [0, C_t) is a
+ *               negative for every class of task t (what label_binarize makes of it)
+ *   out_counts  int64 [NC][3] = { num2, P, Q } per class column:
+ *               P / Q = positives / negatives, num2 = 2 * #{pos > neg} + #{pos == neg}
+ *               so that  AUC = num2 / (2 * P * Q)  == sklearn.metrics.roc_auc_score
+ *               (trapezoid with ties == Mann-Whitney U); P == 0 or Q == 0 -> undefined
+ *   workspace   >= nkbk_auc_workspace_bytes(N, NC) (two N-float lists per column)
+ * N < 2^31.  Integer arithmetic: exact and order independent.
+ * ---------------------------------------------------------------------- */
+int64_t nkbk_auc_workspace_bytes(int64_t N, int NC);
+int nkbk_roc_auc_counts(const float* probs, int64_t N, int ld, const int32_t* seg_offsets, int T,
+                        const int64_t* labels, int64_t* out_counts, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
+/* ------------------------------------------------------------------------
  * K4  batch sharding: the only exchange step of the path
  *
  * The reference is single-GPU (no torch.distributed anywhere);

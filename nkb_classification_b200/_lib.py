@@ -50,6 +50,9 @@ SYMBOLS = {
                                 c_int, c_void_p]),
     "nkbk_argmax_confusion": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_int32), c_int, c_void_p, c_void_p,
                                       c_void_p, c_void_p]),
+    "nkbk_auc_workspace_bytes": (c_int64, [c_int64, c_int]),
+    "nkbk_roc_auc_counts": (c_int, [c_void_p, c_int64, c_int, POINTER(c_int32), c_int, c_void_p, c_void_p, c_void_p,
+                                    c_size_t, c_void_p]),
     "nkbk_comm_unique_id": (c_int, [c_void_p]),
     "nkbk_comm_init": (c_int, [c_int, c_int, c_void_p, c_int]),
     "nkbk_comm_world": (c_int, []),

@@ -413,18 +413,41 @@ def collate_targets(labels: list):
     return torch.from_numpy(np.asarray(labels, dtype=np.int64))
 
 
+class _IngestSlot:
+    """One stage of the frame-ingest ring: pinned uint8 staging, its device twin, and the two events that make reuse
+    safe (`copied`: H2D finished, recorded on the copy stream; `consumed`: K1 has read the device buffer, recorded on
+    the consumer's stream)."""
+
+    def __init__(self):
+        self.staging: Optional[torch.Tensor] = None
+        self.dev: Optional[torch.Tensor] = None
+        self.copied: Optional[torch.cuda.Event] = None
+        self.consumed: Optional[torch.cuda.Event] = None
+
+
 class DeviceCropLoader:
-    """DataLoader stand-in: batches of sample descriptors -> K1 -> (device tensor, target)."""
+    """DataLoader stand-in: batches of sample descriptors -> K1 -> (device tensor, target).
+
+    Frame ingest: each distinct frame of a batch is decoded ONCE (thread pool), packed as uint8
+    into a pinned staging buffer with 16-byte aligned rows and copied to the device as uint8 -- the reference decodes
+    per crop and ships fp32 (dataset.py:398-409, engine.py:40).  With ``prefetch`` > 0 a producer thread runs decode +
+    pack + H2D (on its own copy stream) for the next batches while the consumer's stream runs K1 / the model on the
+    current one; a ring of ``prefetch + 2`` slots with `copied` / `consumed` events keeps buffers from being reused
+    early.  ``prefetch = 0`` does the same work inline (one slot ring, still event-guarded)."""
 
     def __init__(self, dataset: _DescDataset, batch_size: int, shuffle: bool = False, sampler=None,
-                 num_workers: int = 0, drop_last: bool = False, device="cuda:0", out_dtype=torch.float32):
+                 num_workers: int = 0, drop_last: bool = False, device="cuda:0", out_dtype=torch.float32,
+                 prefetch: Optional[int] = None):
         if dataset.transform is None:
             raise ValueError("the dataset needs a Transforms(pipeline) to compile for K1")
         self.dataset, self.batch_size, self.shuffle, self.sampler = dataset, int(batch_size), shuffle, sampler
         self.drop_last, self.device, self.out_dtype = drop_last, torch.device(device), out_dtype
         self.plan = dataset.transform.plan
         self.pool = ThreadPoolExecutor(max(1, num_workers)) if num_workers and num_workers > 0 else None
-        self._staging = None
+        # like torch's DataLoader: workers imply prefetching (prefetch_factor = 2)
+        self.prefetch = int(prefetch) if prefetch is not None else (2 if num_workers and num_workers > 0 else 0)
+        self._slots = [_IngestSlot() for _ in range(self.prefetch + 2)]
+        self._copy_stream: Optional[torch.cuda.Stream] = None
         # train pipelines: where the per-sample augmentation parameters come from (None = Python's global `random`,
         # which is what albumentations draws from, so `random.seed(...)` governs it as in the reference)
         self.aug_rng = None
@@ -446,7 +469,11 @@ class DeviceCropLoader:
                 return
             yield b
 
-    def load_batch(self, indices: List[int]):
+    # ---- producer side: host work + H2D of one batch into ring slot `k` ----
+    def _stage(self, indices: List[int], k: int) -> dict:
+        slot = self._slots[k]
+        if slot.consumed is not None:
+            slot.consumed.synchronize()          # K1 of the batch that used this slot last has read the device buffer
         samples = [self.dataset[i] for i in indices]
         paths = [s[0] for s in samples]
         uniq: Dict[str, int] = {}
@@ -454,22 +481,88 @@ class DeviceCropLoader:
             uniq.setdefault(p, len(uniq))
         plist = list(uniq)
         frames = list(self.pool.map(_imread_bgr, plist)) if self.pool else [_imread_bgr(p) for p in plist]
-        self._staging, total, desc, sizes = pack_frames(frames, self._staging)
+        slot.staging, total, desc, sizes = pack_frames(frames, slot.staging)
         fidx = np.array([uniq[p] for p in paths], dtype=np.int32)
         boxes = np.array([s[1] if s[1] is not None else (0, 0, sizes[fi][1], sizes[fi][0])
                           for s, fi in zip(samples, fidx)], dtype=np.int32).reshape(-1, 4)
         validate_boxes(boxes, fidx, sizes)
+        aug = self.plan.draw(len(samples), self.aug_rng)     # in batch order: one producer, so the stream is reproducible
         dev = self.device
-        flat = self._staging[:total].to(dev, non_blocking=True)
-        img = ops.preprocess_crops(flat, torch.from_numpy(boxes).to(dev, non_blocking=True),
-                                   torch.from_numpy(fidx).to(dev, non_blocking=True), self.plan,
-                                   out_dtype=self.out_dtype, frame_desc=desc.to(dev, non_blocking=True),
-                                   aug=self.plan.draw(len(samples), self.aug_rng))
-        return img, collate_targets([s[2] for s in samples])
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        if slot.dev is None or slot.dev.numel() < total:
+            slot.dev = torch.empty(int(total * 1.25) + 4096, dtype=torch.uint8, device=dev)
+        if slot.copied is None:
+            slot.copied = torch.cuda.Event()
+        with torch.cuda.stream(self._copy_stream):
+            slot.dev[:total].copy_(slot.staging[:total], non_blocking=True)
+            meta = dict(boxes=torch.from_numpy(boxes).to(dev, non_blocking=True),
+                        fidx=torch.from_numpy(fidx).to(dev, non_blocking=True),
+                        desc=desc.to(dev, non_blocking=True))
+            slot.copied.record(self._copy_stream)
+        meta.update(slot=k, total=total, aug=aug, target=collate_targets([s[2] for s in samples]))
+        return meta
+
+    # ---- consumer side: K1 on the caller's current stream ----
+    def _consume(self, meta: dict):
+        slot = self._slots[meta["slot"]]
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(slot.copied)
+        for t in (meta["boxes"], meta["fidx"], meta["desc"]):
+            t.record_stream(cur)                 # allocated on the copy stream, read on this one
+        img = ops.preprocess_crops(slot.dev[:meta["total"]], meta["boxes"], meta["fidx"], self.plan,
+                                   out_dtype=self.out_dtype, frame_desc=meta["desc"], aug=meta["aug"])
+        if slot.consumed is None:
+            slot.consumed = torch.cuda.Event()
+        slot.consumed.record(cur)
+        return img, meta["target"]
+
+    def load_batch(self, indices: List[int]):
+        return self._consume(self._stage(indices, 0))
 
     def __iter__(self):
-        for b in self._index_batches():
-            yield self.load_batch(b)
+        if self.prefetch <= 0:
+            for b in self._index_batches():
+                yield self.load_batch(b)
+            return
+        import queue
+        import threading
+        q: "queue.Queue" = queue.Queue(maxsize=self.prefetch)
+        stop = threading.Event()
+        nslot = len(self._slots)
+
+        def put(item) -> bool:
+            while not stop.is_set():
+                try:
+                    q.put(item, timeout=0.1)
+                    return True
+                except queue.Full:
+                    continue
+            return False
+
+        def producer():
+            try:
+                torch.cuda.set_device(self.device)
+                for i, b in enumerate(self._index_batches()):
+                    if stop.is_set() or not put(self._stage(b, i % nslot)):
+                        return
+                put(None)
+            except BaseException as e:  # surfaced in the consumer
+                put(e)
+
+        th = threading.Thread(target=producer, name="nkbk-ingest", daemon=True)
+        th.start()
+        try:
+            while True:
+                item = q.get()
+                if item is None:
+                    break
+                if isinstance(item, BaseException):
+                    raise item
+                yield self._consume(item)
+        finally:
+            stop.set()
+            th.join()
 
 
 def _device_of(data: dict):
@@ -481,7 +574,7 @@ def get_dataset(data, pipeline):
     weighted_sampling, dataset kwargs); optional extra key ``device``."""
     transform = Transforms(pipeline)
     kind = data["type"]
-    kwargs = {k: v for k, v in data.items() if k != "device"}
+    kwargs = {k: v for k, v in data.items() if k not in ("device", "prefetch")}
     if kind == "GroupsDataset":
         dataset = GroupsDataset(transform=transform, **kwargs)
     elif kind == "AnnotatedMultitaskDataset":
@@ -495,11 +588,11 @@ def get_dataset(data, pipeline):
     sampler = ImbalancedDatasetSampler(dataset) if data.get("weighted_sampling", False) else None
     return DeviceCropLoader(dataset, batch_size=data["batch_size"], shuffle=data.get("shuffle", False), sampler=sampler,
                             num_workers=data.get("num_workers", 0), drop_last=data.get("drop_last", False),
-                            device=_device_of(data))
+                            device=_device_of(data), prefetch=data.get("prefetch"))
 
 
 def get_inference_dataset(data, pipeline):
     """dataset.py:632-644: yields (img, paths)."""
     dataset = InferDataset(folder_path=data["folder_path"], transform=Transforms(pipeline))
     return DeviceCropLoader(dataset, batch_size=data["batch_size"], num_workers=data.get("num_workers", 0),
-                            device=_device_of(data))
+                            device=_device_of(data), prefetch=data.get("prefetch"))

@@ -7,7 +7,8 @@ The reference does, per task and per step, ``true.cpu().tolist()``,
 only appends device tensors (K2's fp32 probabilities, K3's predictions, the
 labels, the loss vector); ``get_epoch_results()`` performs ONE device->host copy
 per quantity per epoch and rebuilds exactly the reference's dict of lists, plus
-``"confusion"`` (K3's integer matrices) for ``compute_metrics``.
+``"confusion"`` (K3's integer matrices) and ``"roc_auc_counts"`` (K5's exact
+ROC-AUC pair counts, computed on the device-resident epoch) for ``compute_metrics``.
 
 (The reference's BaseLogger crashes for task="multi" -- it reads an attribute
 that is never set, logging.py:243; target names here come from ``classes``.)
@@ -28,6 +29,7 @@ class BaseLogger:
         self.classes = classes
         self.target_names = None if self.task == "single" else sorted(classes)
         self.fused = None  # set by the engine: the FusedHeads whose confusion counts belong to this epoch
+        self.device_roc_auc = True   # K5: ROC-AUC pair counts computed on the device at epoch end
         self.init_iter_logs()
 
     def init_iter_logs(self):
@@ -77,8 +79,14 @@ class BaseLogger:
             empty = [] if self.task == "single" else defaultdict(list)
             return {"running_loss": empty, "confidences": empty, "predictions": empty, "ground_truth": empty,
                     "images": self.epoch_images_example}
-        gt = torch.cat(self._gt).cpu().numpy()
-        conf = torch.cat(self._conf).cpu().numpy()
+        gt_d, conf_d = torch.cat(self._gt), torch.cat(self._conf)
+        auc_counts = None
+        if conf_d.is_cuda and self.device_roc_auc:
+            # K5: exact ROC-AUC pair counts from the device-resident epoch, one [NC, 3] int64 D2H
+            from . import ops
+            auc_counts = ops.roc_auc_counts(conf_d.contiguous(), self._seg, gt_d.to(torch.int64).contiguous()).cpu().numpy()
+        gt = gt_d.cpu().numpy()
+        conf = conf_d.cpu().numpy()
         pred = torch.cat(self._pred).cpu().numpy()
         loss = torch.stack(self._loss).cpu().numpy()
         seg, names = self._seg, self._names
@@ -97,6 +105,10 @@ class BaseLogger:
                 g[n] = gt[:, t].tolist()
             rl["loss"] = loss[:, len(names)].tolist()
             res.update(running_loss=rl, confidences=cf, predictions=pr, ground_truth=g)
+        if auc_counts is not None:
+            seg_ = self._seg
+            res["roc_auc_counts"] = (auc_counts if names is None else
+                                     {n: auc_counts[seg_[t]:seg_[t + 1]] for t, n in enumerate(names)})
         if self.fused is not None and self.fused.state["cm"] is not None:
             cms = self.fused.confusion_matrices()
             res["confusion"] = cms[0] if names is None else {n: cms[t] for t, n in enumerate(names)}

@@ -1,8 +1,11 @@
 """Epoch metrics with the reference's ``compute_metrics`` interface
 (nkb_classification/metrics.py).  Balanced accuracy comes from K3's integer
 confusion matrix when the epoch results carry one (bit-identical to sklearn's
-``balanced_accuracy_score``); ROC-AUC keeps using sklearn on the
-fp32 probabilities K2 emitted, exactly as the reference does."""
+``balanced_accuracy_score``).  ROC-AUC comes from K5's integer
+pair counts when the epoch results carry them (``"roc_auc_counts"``: AUC =
+num2 / (2 P Q), the Mann-Whitney form of sklearn's trapezoid, equal to
+``roc_auc_score`` to float64 rounding); otherwise sklearn runs on the fp32
+probabilities K2 emitted, exactly as the reference does."""
 from __future__ import annotations
 
 import warnings
@@ -20,6 +23,22 @@ def balanced_accuracy_from_confusion(cm) -> float:
     if not present.any():
         return float("nan")
     return float(np.mean(np.diag(cm)[present].astype(np.float64) / row[present].astype(np.float64)))
+
+
+def roc_auc_from_counts(counts, n_classes: int):
+    """K5's int64 [C, 3] (num2, P, Q) -> what metrics.py:33-42 returns: for C > 2 an array with the one-vs-rest AUC of
+    every class present in the ground truth (NaN elsewhere; all NaN with fewer than two classes present), for C == 2
+    the scalar AUC of class 1."""
+    counts = np.asarray(counts, dtype=np.int64).reshape(n_classes, 3)
+    present = counts[:, 1] > 0
+    with np.errstate(invalid="ignore", divide="ignore"):
+        auc = counts[:, 0].astype(np.float64) / (2.0 * counts[:, 1].astype(np.float64) * counts[:, 2].astype(np.float64))
+    if n_classes > 2:
+        out = np.full(n_classes, np.nan)
+        if present.sum() > 1:
+            out[present] = auc[present]
+        return out
+    return float(auc[1]) if present.sum() > 1 else np.nan
 
 
 def compute_targetwise_metrics(epoch_results, target_name=None):
@@ -40,7 +59,12 @@ def compute_targetwise_metrics(epoch_results, target_name=None):
         epoch_acc = balanced_accuracy_from_confusion(cm)
     else:
         epoch_acc = balanced_accuracy_score(ground_truth, predictions)
-    if n_classes > 2:
+    auc_counts = epoch_results.get("roc_auc_counts")
+    if auc_counts is not None and target_name is not None:
+        auc_counts = auc_counts[target_name]
+    if auc_counts is not None:
+        epoch_roc_auc = roc_auc_from_counts(auc_counts, n_classes)
+    elif n_classes > 2:
         epoch_roc_auc = np.full(n_classes, np.nan)
         if gt_n_classes > 1:
             ground_truth_bin = label_binarize(ground_truth, classes=range(n_classes))

@@ -331,3 +331,26 @@ def loss_fwd_bwd(logits: torch.Tensor, seg_offsets: Sequence[int], labels: torch
                                   float(gamma), _ptr(class_weight), int(ignore_index), _ptr(pr), _ptr(dl), _ptr(loss),
                                   _ptr(ws), ws.numel(), _stream(dev)))
     return loss, dl, pr
+
+
+# --------------------------------------------------------------------------
+# K5
+# --------------------------------------------------------------------------
+def roc_auc_counts(probs: torch.Tensor, seg_offsets: Sequence[int], labels: torch.Tensor) -> torch.Tensor:
+    """int64 [NC, 3] = (num2, P, Q) per class column: AUC = num2 / (2 P Q) (see nkbk_roc_auc_counts).
+    ``probs`` fp32 [N, >= NC], ``labels`` int64 [N, T], both CUDA; one small D2H is left to the caller."""
+    _need_cuda("probs", probs)
+    _need_cuda("labels", labels)
+    seg, T, NC = _seg_array(seg_offsets)
+    if probs.dtype != torch.float32 or probs.dim() != 2 or probs.stride(1) != 1 or probs.shape[1] < NC:
+        raise ValueError("probs must be float32 [N, >= NC] with unit column stride")
+    N = int(probs.shape[0])
+    labels = labels.reshape(N, T) if labels.numel() == N * T else labels
+    if labels.dtype != torch.int64 or tuple(labels.shape) != (N, T) or not labels.is_contiguous():
+        raise ValueError(f"labels must be contiguous int64 [{N}, {T}]")
+    out = torch.empty((NC, 3), dtype=torch.int64, device=probs.device)
+    nbytes = int(lib().nkbk_auc_workspace_bytes(N, NC))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=probs.device)
+    check(lib().nkbk_roc_auc_counts(_ptr(probs), N, int(probs.stride(0)), seg, T, _ptr(labels), _ptr(out), _ptr(ws),
+                                    nbytes, _stream(probs.device)))
+    return out

@@ -111,3 +111,23 @@ def compute_metrics(task: str, epoch_results, target_names: Sequence[str] = ()):
         m["epoch_acc"] = np.mean([m[t]["epoch_acc"] for t in target_names])
         return m
     raise ValueError(f"Unknown task type {task} for metric computation")
+
+
+def roc_auc_counts(probs: np.ndarray, labels: np.ndarray, seg_offsets: Sequence[int]) -> np.ndarray:
+    """int64 [NC, 3] = (num2, P, Q) per class column, the exact integers behind
+    ``roc_auc_score(label_binarize(gt)[:, c], conf[:, c])`` (metrics.py:36-38): P / Q positives / negatives,
+    num2 = 2 * #{pos > neg} + #{pos == neg}; AUC = num2 / (2 P Q) (Mann-Whitney U with mid-ranks == the trapezoid of
+    the ROC curve with tied thresholds merged).  Plain numpy: sort the negatives, binary-search every positive."""
+    probs = np.asarray(probs, dtype=np.float32)
+    labels = np.asarray(labels, dtype=np.int64).reshape(probs.shape[0], -1)
+    T = len(seg_offsets) - 1
+    out = np.zeros((seg_offsets[-1], 3), dtype=np.int64)
+    for t in range(T):
+        for k in range(seg_offsets[t + 1] - seg_offsets[t]):
+            c = seg_offsets[t] + k
+            is_pos = labels[:, t] == k
+            pos, neg = probs[is_pos, c], np.sort(probs[~is_pos, c])
+            lo = np.searchsorted(neg, pos, side="left").astype(np.int64)
+            hi = np.searchsorted(neg, pos, side="right").astype(np.int64)
+            out[c] = (2 * lo.sum() + (hi - lo).sum(), pos.size, neg.size)
+    return out

@@ -170,6 +170,70 @@ def test_loader_yields_oracle_images(cuda_device, tmp_path):
     assert np.concatenate(tg).tolist() == [c2i[r["color"]] for r in rows]
 
 
+def test_loader_prefetch_ring_matches_inline(cuda_device, tmp_path):
+    """the producer thread + copy stream + slot ring yields exactly what the inline loader yields, in
+    order, over more batches than the ring has slots; abandoning an iteration and starting a new one is safe."""
+    from nkb_classification_b200 import dataset as D, transforms as T
+    make_csv_dataset(tmp_path, n=37)
+    pipe = T.Compose([T.Resize(32, 32), T.Normalize(mean=MEAN, std=STD), T.ToTensorV2()])
+    data = {"type": "AnnotatedMultitaskDataset", "annotations_file": str(tmp_path / "ann.csv"),
+            "target_names": ["size", "color"], "fold": "val", "image_base_dir": str(tmp_path), "batch_size": 4,
+            "num_workers": 2, "shuffle": False, "device": str(cuda_device)}
+    inline = D.get_dataset(dict(data, prefetch=0), pipe)
+    ring = D.get_dataset(dict(data, prefetch=2), pipe)
+    assert inline.prefetch == 0 and ring.prefetch == 2 and len(ring._slots) == 4 and len(ring) == 10
+    a = [(img.cpu().numpy(), t["color"].numpy()) for img, t in inline]
+    for _ in zip(range(3), ring):      # abandon an iteration early: the producer must stop cleanly
+        pass
+    side = torch.cuda.Stream(device=cuda_device)
+    with torch.cuda.stream(side):      # consumer on a non-default stream
+        b = [(img.cpu().numpy(), t["color"].numpy()) for img, t in ring]
+    assert len(a) == len(b) == 10
+    for (ia, ta), (ib, tb) in zip(a, b):
+        assert np.array_equal(ia.view(np.uint32), ib.view(np.uint32)) and np.array_equal(ta, tb)
+
+
+def test_train_loader_with_fused_augmentations(cuda_device, tmp_path):
+    """get_dataset(train_data, train_pipeline) with the reference's train-time ops (configs/singletask_config.py:
+    162-201 minus HueSaturationValue): the loader draws per-sample parameters from its rng and K1 applies them;
+    replaying the same random stream through the oracle (cv2.flip / cv2.LUT / slice fill) gives the same bits."""
+    import random
+    import cv2
+    from nkb_classification_b200 import dataset as D, transforms as T
+    rows = make_csv_dataset(tmp_path)
+    pipe = T.Compose([T.LongestMaxSize(32, always_apply=True),
+                      T.PadIfNeeded(32, 32, always_apply=True, border_mode=T.BORDER_CONSTANT, value=0),
+                      T.HorizontalFlip(p=0.5), T.VerticalFlip(p=0.5),
+                      T.RandomBrightnessContrast(brightness_limit=(-0.2, 0.2), contrast_limit=(0.1, -0.5), p=0.5),
+                      T.CoarseDropout(max_holes=4, min_holes=1, max_height=0.2, min_height=0.05, max_width=0.2,
+                                      min_width=0.05, fill_value=[0, 0.5, 1], p=0.5),
+                      T.Normalize(mean=MEAN, std=STD), T.ToTensorV2()])
+    data = {"type": "AnnotatedMultitaskDataset", "annotations_file": str(tmp_path / "ann.csv"),
+            "target_names": ["size", "color"], "fold": "val", "image_base_dir": str(tmp_path), "batch_size": 8,
+            "num_workers": 2, "shuffle": False, "device": str(cuda_device)}
+    loader = D.get_dataset(data, pipe)
+    loader.aug_rng = random.Random(31)
+    got = np.concatenate([img.cpu().numpy() for img, _ in loader])
+    # oracle: same draws, batch by batch (the loader draws once per batch of 8, in sample order)
+    replay = random.Random(31)
+    plan = opre.Plan(mean=MEAN, std=STD, mode=opre.MODE_LETTERBOX, out_h=32, out_w=32, max_size=32)
+    exp, changed = [], 0
+    for i in range(0, len(rows), 8):
+        chunk = rows[i:i + 8]
+        b = loader.plan.draw(len(chunk), replay)
+        for k, r in enumerate(chunk):
+            f = int(b.flags[k])
+            a = opre.AugSample(hflip=bool(f & 1), vflip=bool(f & 2), bc=bool(f & 4), alpha=float(b.alpha[k]),
+                               beta=float(b.brightness[k]), holes=[tuple(int(v) for v in h) for h in b.holes[k, :f >> 8]],
+                               fill=b.fill)
+            changed += int(f != 0)
+            img = cv2.cvtColor(cv2.imread(str(tmp_path / r["path"])), cv2.COLOR_BGR2RGB)
+            exp.append(opre.preprocess_crop(img, (0, 0, img.shape[1], img.shape[0]), plan, "cv2", aug=a)[1])
+    exp = np.stack(exp)
+    assert changed > len(rows) // 2
+    assert np.array_equal(got.view(np.uint32), exp.view(np.uint32))
+
+
 def oracle_epoch(tmp_path, rows, classes, model_state, plan_kw, c2i, gamma=1.0):
     """CPU restatement of val_epoch: oracle images -> same tiny backbone (CPU, fp64) -> oracle heads / loss."""
     imgs = torch.from_numpy(oracle_images(tmp_path, rows, plan_kw)).double()
@@ -207,6 +271,11 @@ def test_val_epoch_matches_oracle(cuda_device, tmp_path):
     m = Mx.compute_metrics(cfg, res)
     exp_acc = np.mean([om.balanced_accuracy_from_cm(res["confusion"][n]) for n in cfg.target_names])
     assert m["epoch_acc"] == exp_acc
+    # ROC-AUC came from K5's device-side pair counts; the reference's sklearn route on the same lists agrees
+    assert set(res["roc_auc_counts"]) == set(names)
+    sk = Mx.compute_metrics(cfg, {k: v for k, v in res.items() if k != "roc_auc_counts"})
+    for n in names:
+        assert np.allclose(m[n]["epoch_roc_auc"], sk[n]["epoch_roc_auc"], rtol=0, atol=1e-12, equal_nan=True)
 
 
 def test_train_epoch_updates_heads_like_the_oracle(cuda_device, tmp_path):

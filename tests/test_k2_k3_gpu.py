@@ -238,6 +238,41 @@ def test_sharded_equals_single_gpu_nccl(cuda_device):
     assert r.returncode == 0 and "DIST_CHECK_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
+@pytest.mark.parametrize("N,classes,quant", [
+    (1000, (3, 2), None),
+    (5000, (2, 3, 4, 7, 14), 32),      # config 4 heads, heavily tied scores
+    (70000, (10,), None),              # > one (pos tile, neg chunk) item per column, ragged tails
+    (33, (2,), 4),
+    (1, (3,), None),
+])
+def test_k5_roc_auc_counts_exact(cuda_device, N, classes, quant):
+    """K5 == the integer Mann-Whitney counts of the oracle (which equal sklearn's roc_auc_score, tested on CPU):
+    bit-exact int64, including rows with ignored labels (negatives for every class of that task)."""
+    from nkb_classification_b200 import ops
+    from nkb_classification_b200.metrics import roc_auc_from_counts
+    rng = np.random.default_rng(8)
+    seg = np.concatenate([[0], np.cumsum(classes)]).tolist()
+    z = torch.from_numpy(rng.normal(size=(N, seg[-1])).astype(np.float32))
+    probs = torch.cat([z[:, a:b].softmax(-1) for a, b in zip(seg[:-1], seg[1:])], 1)
+    if quant:
+        probs = (probs * quant).round() / quant
+    labels = np.stack([rng.integers(0, c, N) for c in classes], 1)
+    if N > 10:
+        labels[::13, 0] = -100
+    got = ops.roc_auc_counts(probs.to(cuda_device), seg, torch.from_numpy(labels).to(cuda_device)).cpu().numpy()
+    exp = om.roc_auc_counts(probs.numpy(), labels, seg)
+    assert np.array_equal(got, exp)
+    if N >= 1000:
+        from sklearn.metrics import roc_auc_score
+        auc = roc_auc_from_counts(got[seg[-2]:seg[-1]], classes[-1])
+        t = len(classes) - 1
+        if classes[-1] > 2:
+            e = [roc_auc_score(labels[:, t] == c, probs[:, seg[t] + c].numpy()) for c in range(classes[-1])]
+        else:
+            e = roc_auc_score(labels[:, t], probs[:, seg[t] + 1].numpy())
+        assert np.allclose(auc, e, rtol=0, atol=1e-12)
+
+
 def _torchrun(script, world, port, env_extra=None, timeout=600):
     import os
     import subprocess

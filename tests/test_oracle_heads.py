@@ -93,3 +93,37 @@ def test_argmax_ties_and_nan():
     exp = torch.from_numpy(z).argmax(-1).numpy()
     assert np.array_equal(om.argmax_first(z), exp)
     assert list(exp) == [1, 0, 1, 0]
+
+
+def test_oracle_roc_auc_counts_equal_sklearn():
+    """The integer Mann-Whitney form the device kernel (K5) is checked against == sklearn.roc_auc_score, including
+    heavy ties (quantised scores) and the reference's one-vs-rest use (metrics.py:33-42)."""
+    from sklearn.metrics import roc_auc_score
+    from sklearn.preprocessing import label_binarize
+    from oracle import metrics as om
+    from nkb_classification_b200.metrics import roc_auc_from_counts
+    rng = np.random.default_rng(3)
+    for N, classes, quant in [(500, (3, 2), None), (2000, (7,), 16), (64, (2,), 4), (300, (4, 4), 2)]:
+        seg = np.concatenate([[0], np.cumsum(classes)]).tolist()
+        z = rng.normal(size=(N, seg[-1])).astype(np.float32)
+        probs = np.concatenate([np.exp(z[:, a:b]) / np.exp(z[:, a:b]).sum(1, keepdims=True)
+                                for a, b in zip(seg[:-1], seg[1:])], 1).astype(np.float32)
+        if quant:
+            probs = (np.round(probs * quant) / quant).astype(np.float32)
+        labels = np.stack([rng.integers(0, c, N) for c in classes], 1)
+        counts = om.roc_auc_counts(probs, labels, seg)
+        for t, C in enumerate(classes):
+            gt, conf = labels[:, t], probs[:, seg[t]:seg[t + 1]]
+            got = roc_auc_from_counts(counts[seg[t]:seg[t + 1]], C)
+            if C > 2:
+                gb = label_binarize(gt, classes=range(C))
+                exp = np.array([roc_auc_score(gb[:, c], conf[:, c]) for c in range(C)])
+            else:
+                exp = roc_auc_score(gt, conf[:, 1])
+            assert np.allclose(got, exp, rtol=0, atol=1e-12), (N, classes, quant, t)
+    # a class absent from the ground truth -> NaN there; a single class present -> all NaN (metrics.py:34-35)
+    c = np.array([[10, 5, 5], [0, 0, 10], [8, 5, 5]])
+    r = roc_auc_from_counts(c, 3)
+    assert np.isnan(r[1]) and r[0] == 10 / 50 and r[2] == 8 / 50
+    assert np.isnan(roc_auc_from_counts(np.array([[0, 9, 0], [0, 0, 9], [0, 0, 9]]), 3)).all()
+    assert np.isnan(roc_auc_from_counts(np.array([[0, 0, 9], [0, 9, 0]]), 2))
