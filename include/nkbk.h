@@ -147,6 +147,16 @@ int nkbk_heads_fwd_loss_bwd(const void* emb, int emb_dtype, int B, int D, const 
                             float* dlogits, float* reduce_buf, void* workspace, size_t workspace_bytes,
                             void* stream);
 
+/* nkbk_heads_fwd_loss_bwd with K3 fused into the forward epilogue (the logits are still on chip there):
+ *   out_pred  optional int32 [B][T]  per-task argmax (ties -> lowest index, NaN maximal: torch.argmax)
+ *   cm_step   optional int64 confusion counts, layout as nkbk_argmax_confusion; ACCUMULATES; needs labels
+ * One launch fewer per step than nkbk_heads_fwd_loss_bwd + nkbk_argmax_confusion; same results. */
+int nkbk_heads_step(const void* emb, int emb_dtype, int B, int D, const float* W_cat, const float* b_cat,
+                    const int32_t* seg_offsets, int T, const int64_t* labels, int loss_kind, float gamma,
+                    const float* class_weight, int64_t ignore_index, float* out_logits, float* out_probs,
+                    float* dlogits, float* reduce_buf, int32_t* out_pred, int64_t* cm_step, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
 /* In place: dW, db <- sums / denom[task]; out_loss (fp32 [T+1]) <- per-task mean
  * losses and their unweighted sum (losses.py:140-147).  denom == 0 -> 0.
  * Optionally folds the (all-reduced) per-step confusion counts into the epoch

@@ -41,6 +41,9 @@ SYMBOLS = {
     "nkbk_heads_fwd_loss_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, POINTER(c_int32), c_int,
                                         c_void_p, c_int, c_float, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_void_p, c_size_t, c_void_p]),
+    "nkbk_heads_step": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, POINTER(c_int32), c_int, c_void_p,
+                                c_int, c_float, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_size_t, c_void_p]),
     "nkbk_loss_workspace_bytes": (c_int64, [c_int, c_int]),
     "nkbk_loss_fwd_bwd": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_int32), c_int, c_void_p, c_int, c_float,
                                   c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -10,8 +10,10 @@ constexpr int K2_FWD_WARPS = 4;
 constexpr int K2_FWD_ROWS = 4;     // rows per CTA
 constexpr int K2_FWD_NCB = 16;     // classes per pass
 constexpr int K2_FWD_ROUND = 2;    // K chunks per warp whose loads are issued together
-constexpr int K2_DW_WARPS = 8;
-constexpr int K2_DW_ROWS = 256;    // rows per dW chunk (32 per warp)
+constexpr int K2_V3_WARPS = 4;     // forward v3: warps per CTA, each owning K2_FWD_ROWS rows over the full K
+constexpr int K2_V3_PD = 4;        // forward v3: 128-column chunks of embedding loads in flight per warp
+constexpr int K2_DW_WARPS = 4;
+constexpr int K2_DW_ROWS = 128;    // rows per dW chunk (32 per warp)
 constexpr int K2_DW_COLS = 128;    // columns per dW CTA (4 per lane)
 constexpr int K2_DW_NCB = 16;      // classes per dW pass
 
@@ -29,6 +31,8 @@ struct K2FwdParams {
     float* out_logits;
     float* out_probs;
     float* dlogits;
+    int32_t* out_pred;     // optional [B][T]: per-task argmax (K3 fused into the forward epilogue)
+    unsigned long long* cm_step;  // optional confusion counts to add to (needs labels)
     float* loss_part;      // [fwd_blocks][2T]
     unsigned int* counters;  // zeroed here for the dW kernel that follows
     int n_counters;

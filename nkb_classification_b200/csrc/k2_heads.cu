@@ -7,13 +7,14 @@
 // would break the 1e-5 fp32 parity bar).  bf16 embeddings are widened on load.
 // Everything is deterministic: partial sums are combined in a fixed order.
 //
-//   k2_heads_forward   CTA = 4 rows; its 4 warps split K (chunks of 128 columns,
-//                      round-robin) with all embedding loads of a round issued
-//                      up front; 16 classes per pass; a 31-shuffle transposing
-//                      reduction + a fixed-order cross-warp sum leave the logits
-//                      in shared memory; per-(row, task) lanes then do softmax /
-//                      loss / dlogits.
-//   k2_heads_dw        CTA = 256 rows x 128 columns, 8 warps x 32 rows, thread =
+//   k2_heads_forward_v3  warp = 4 rows over the whole K (4 chunks of 128 columns in flight,
+//                      streamed past L1), weights of a 16-class pass staged once per
+//                      CTA in shared memory; a 31-shuffle transposing reduction leaves
+//                      the logits in the warp's private shared-memory slice; per-(row,
+//                      task) lanes then do softmax / loss / dlogits and the fused K3
+//                      (argmax + confusion counts).  No cross-warp reduction.
+//   k2_heads_forward   (previous version, kept for reference: CTA = 4 rows, warps split K)
+//   k2_heads_dw        CTA = 128 rows x 128 columns, 4 warps x 32 rows, thread =
 //                      4 columns x NCP classes in registers, dlogits broadcast
 //                      from shared memory; fixed-order cross-warp tree; the last
 //                      CTA to finish a column block sums the per-chunk partials
@@ -21,6 +22,8 @@
 //   k2_heads_finalize  divide by the (all-reduced) denominators, emit losses.
 //   k2_heads_demb      d(loss)/d(emb) for an unfrozen backbone.
 #include "k2_common.cuh"
+
+#include <algorithm>
 
 namespace nkbk {
 
@@ -254,46 +257,223 @@ __global__ void __launch_bounds__(K2_FWD_WARPS * 32) k2_heads_forward(const K2Fw
     heads_row_epilogue(p, zs, ls, row0, lane, p.loss_part + (int64_t)blockIdx.x * 2 * T);
 }
 
+// ---- forward v3: one warp = K2_FWD_ROWS rows over the whole K, no cross-warp reduction, K3 fused ----------------
+// Each warp streams its 4 embedding rows once (K2_V3_PD chunks of 128 columns in flight per lane, so ~8 KB per warp
+// is always outstanding), multiplies them against the head weights (read through L1, shared by every warp of the SM),
+// folds the 64 per-lane partial sums with the transposing shuffle reduction, and runs the softmax / loss / dlogits
+// epilogue on its own rows from its private slice of shared memory -- no __syncthreads anywhere.  The per-task
+// argmax and the confusion counts (K3) are taken from the logits while they are still on chip.
+// Embedding rows are read exactly once: stream them past L1 so the head weights stay resident there.
+__device__ __forceinline__ float4 ld4_stream(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ld4_stream(const __nv_bfloat16* p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    float4 v;
+    v.x = __uint_as_float(r.x << 16);
+    v.y = __uint_as_float(r.x & 0xffff0000u);
+    v.z = __uint_as_float(r.y << 16);
+    v.w = __uint_as_float(r.y & 0xffff0000u);
+    return v;
+}
+
+// WS = true: the weights of the current 16-class pass ([<=16][D] fp32) are staged once per CTA in shared memory and
+// read from there (no L1 misses in the inner loop); WS = false (tile larger than shared memory): through L1.
+template <typename ET, bool WS>
+__global__ void __launch_bounds__(K2_V3_WARPS * 32) k2_heads_forward_v3(const K2FwdParams p) {
+    extern __shared__ __align__(16) float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int T = p.seg.T, NC = p.NC, D = p.D;
+    float* zs = smem + warp * (K2_FWD_ROWS * (2 * NC + 6 * T));  // [ROWS][NC] logits of this warp's rows
+    float* ls = zs + K2_FWD_ROWS * NC;                            // epilogue scratch, ROWS * (NC + 6T)
+    // staged weights start on a 16-byte boundary after the per-warp slices
+    float* wsm = smem + ((K2_V3_WARPS * K2_FWD_ROWS * (2 * NC + 6 * T) + 3) & ~3);
+    if (blockIdx.x == 0)
+        for (int i = threadIdx.x; i < p.n_counters; i += blockDim.x) p.counters[i] = 0u;
+    const int gw = blockIdx.x * K2_V3_WARPS + warp;
+    const int row0 = gw * K2_FWD_ROWS;
+    const bool active = row0 < p.B;
+    if (!WS && !active) return;
+    const ET* er[K2_FWD_ROWS];
+#pragma unroll
+    for (int r = 0; r < K2_FWD_ROWS; ++r)  // tail rows recompute the last row, never stored
+        er[r] = static_cast<const ET*>(p.emb) + (int64_t)min(row0 + r, p.B - 1) * D;
+    const int nchunks = (D + 127) / 128;
+
+    for (int cb = 0; cb < NC; cb += K2_FWD_NCB) {
+        float acc[K2_FWD_ROWS * K2_FWD_NCB];
+#pragma unroll
+        for (int i = 0; i < K2_FWD_ROWS * K2_FWD_NCB; ++i) acc[i] = 0.f;
+        float4 e[K2_V3_PD][K2_FWD_ROWS];
+        auto load_chunk = [&](float4 (&dst)[K2_FWD_ROWS], int chunk) {
+            const int k = chunk * 128 + lane * 4;
+#pragma unroll
+            for (int r = 0; r < K2_FWD_ROWS; ++r)
+                dst[r] = (active && chunk < nchunks && k < D) ? ld4_stream(er[r] + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+#pragma unroll
+        for (int u = 0; u < K2_V3_PD; ++u) load_chunk(e[u], u);   // embedding loads are in flight while W is staged
+        if (WS) {
+            if (cb > 0) __syncthreads();                          // everyone is done with the previous pass's tile
+            const int ncls = min(K2_FWD_NCB, NC - cb);
+            // cp.async (LDGSTS): every 16-byte piece of the tile is in flight at once, no registers involved
+            const float4* src = reinterpret_cast<const float4*>(p.W + (int64_t)cb * D);
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(wsm);
+            const int n4 = ncls * (D >> 2);
+            for (int i = threadIdx.x; i < n4; i += K2_V3_WARPS * 32)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * (uint32_t)i), "l"(src + i) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();
+        }
+        if (active)
+        for (int c0 = 0; c0 < nchunks; c0 += K2_V3_PD) {
+#pragma unroll
+            for (int u = 0; u < K2_V3_PD; ++u) {
+                const int chunk = c0 + u;
+                if (chunk < nchunks) {  // warp-uniform
+                    const int k = min(chunk * 128 + lane * 4, D - 4);  // lanes past D hold zeros in e: any valid W address
+#pragma unroll
+                    for (int ch = 0; ch < K2_FWD_NCB; ch += 8) {
+                        if (cb + ch >= NC) break;  // warp-uniform
+                        float4 w[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            if (WS) w[c] = *reinterpret_cast<const float4*>(wsm + min(ch + c, NC - cb - 1) * D + k);
+                            else w[c] = ld4(p.W + (int64_t)min(cb + ch + c, NC - 1) * D + k);
+                        }
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            if (cb + ch + c < NC) {  // warp-uniform: padded classes skip their FFMAs
+#pragma unroll
+                                for (int r = 0; r < K2_FWD_ROWS; ++r) {
+                                    float a = acc[r * K2_FWD_NCB + ch + c];
+                                    a = fmaf(e[u][r].x, w[c].x, a);
+                                    a = fmaf(e[u][r].y, w[c].y, a);
+                                    a = fmaf(e[u][r].z, w[c].z, a);
+                                    a = fmaf(e[u][r].w, w[c].w, a);
+                                    acc[r * K2_FWD_NCB + ch + c] = a;
+                                }
+                            }
+                        }
+                    }
+                    load_chunk(e[u], chunk + K2_V3_PD);  // refill the stage just consumed
+                }
+            }
+        }
+        // 64 partial sums -> lane L owns entries L and 32 + L  (entry = r * 16 + c)
+        float lo[32], hi[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { lo[i] = acc[i]; hi[i] = acc[32 + i]; }
+        const float s_lo = warp_reduce_scatter32(lo, lane);
+        const float s_hi = warp_reduce_scatter32(hi, lane);
+        const int c = cb + (lane & 15), r = lane >> 4;
+        if (c < NC) {
+            const float b = __ldg(p.bias + c);
+            zs[r * NC + c] = s_lo + b;
+            zs[(r + 2) * NC + c] = s_hi + b;
+        }
+    }
+    if (!active) return;   // (WS: inactive warps only took part in the staging barriers)
+    __syncwarp();
+    heads_row_epilogue(p, zs, ls, row0, lane, p.loss_part + (int64_t)gw * 2 * T);
+
+    // ---- K3 fused: per-task argmax (first maximum, NaN maximal -- torch.argmax) + confusion counts ----
+    if (p.out_pred != nullptr || p.cm_step != nullptr) {
+        for (int idx = lane; idx < K2_FWD_ROWS * T; idx += 32) {
+            const int rr = idx / T, t = idx - rr * T;
+            const int row = row0 + rr;
+            if (row >= p.B) continue;
+            const int c0 = p.seg.off[t], C = p.seg.off[t + 1] - c0;
+            const float* z = zs + rr * NC + c0;
+            float best = z[0];
+            int bi = 0;
+            for (int j = 1; j < C; ++j) {
+                const float v = z[j];
+                if (!(best != best) && (v > best || v != v)) { best = v; bi = j; }
+            }
+            if (p.out_pred) p.out_pred[(int64_t)row * T + t] = bi;
+            if (p.cm_step != nullptr && p.labels != nullptr) {
+                const int64_t y = p.labels[(int64_t)row * T + t];
+                if (y >= 0 && y < C) {
+                    int64_t off = 0;
+                    for (int s = 0; s < t; ++s) {
+                        const int64_t Cs = p.seg.off[s + 1] - p.seg.off[s];
+                        off += Cs * Cs;
+                    }
+                    atomicAdd(p.cm_step + off + y * C + bi, 1ull);
+                }
+            }
+        }
+    }
+}
+
 // Sum `n` floats spaced `stride` apart in a fixed order with one warp (lane-strided partial sums, xor tree).
 __device__ __forceinline__ float warp_fixed_sum(const float* base, int n, int64_t stride, int lane) {
     float s = 0.f;
-    for (int i = lane; i < n; i += 32) s += __ldcg(base + (int64_t)i * stride);
+    for (int i0 = lane; i0 < n; i0 += 32 * 8) {   // 8 loads in flight per lane, added in index order
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (i0 + 32 * u < n) v[u] = __ldcg(base + (int64_t)(i0 + 32 * u) * stride);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (i0 + 32 * u < n) s += v[u];
+    }
     return warp_sum(s);
 }
 
 // ---- dW / db ---------------------------------------------------------------
 template <typename ET, int NCP>
-__global__ void __launch_bounds__(K2_DW_WARPS * 32) k2_heads_dw(
+__global__ void __launch_bounds__(K2_DW_WARPS * 32, 4) k2_heads_dw(
     const ET* __restrict__ emb, const float* __restrict__ dlogits, int B, int D, int NC, int T, int cls0, int pass,
     float* __restrict__ dw_part, float* __restrict__ db_part, const float* __restrict__ loss_part, int fwd_blocks,
     unsigned int* __restrict__ counters, float* __restrict__ reduce_buf) {
-    // dl [256][NCP] while accumulating, then the cross-warp reduction buffer [4][NCP][128] (aliased)
-    __shared__ __align__(16) float sm[4 * NCP * K2_DW_COLS > K2_DW_ROWS * NCP ? 4 * NCP * K2_DW_COLS : K2_DW_ROWS * NCP];
+    // dl [ROWS][NCP] while accumulating, then the cross-warp reduction buffer [WARPS/2][NCP][128] (aliased)
+    constexpr int RED = (K2_DW_WARPS / 2) * NCP * K2_DW_COLS;
+    __shared__ __align__(16) float sm[RED > K2_DW_ROWS * NCP ? RED : K2_DW_ROWS * NCP];
     __shared__ int is_last;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int chunk = blockIdx.y, chunks = gridDim.y;
     const int rbeg = chunk * K2_DW_ROWS, rows = min(K2_DW_ROWS, B - rbeg);
     const int ncls = min(NCP, NC - cls0);
     float (*dl)[NCP] = reinterpret_cast<float (*)[NCP]>(sm);
-    for (int i = threadIdx.x; i < K2_DW_ROWS * NCP; i += blockDim.x) {
+    // The warp's 32 rows go through two register stages of 8 rows: 16 row loads are in flight before the dlogits are
+    // even staged, and every stage is refilled as soon as it has been consumed.
+    constexpr int RB = 8;
+    const int k0 = blockIdx.x * K2_DW_COLS + lane * 4;
+    const int r_lo = warp * 32, r_hi = min(r_lo + 32, rows);
+    float4 eb[2][RB];
+    auto load_batch = [&](float4 (&dst)[RB], int r_start) {
+#pragma unroll
+        for (int i = 0; i < RB; ++i) {
+            const int r = r_start + i;
+            dst[i] = (k0 < D && r < r_hi) ? ld4(emb + (int64_t)(rbeg + r) * D + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    load_batch(eb[0], r_lo);
+    load_batch(eb[1], r_lo + RB);
+#pragma unroll
+    for (int i = threadIdx.x; i < K2_DW_ROWS * NCP; i += K2_DW_WARPS * 32) {
         const int r = i / NCP, c = i - r * NCP;
         dl[r][c] = (r < rows && c < ncls) ? __ldg(dlogits + (int64_t)(rbeg + r) * NC + cls0 + c) : 0.f;
     }
     __syncthreads();
 
-    const int k0 = blockIdx.x * K2_DW_COLS + lane * 4;
     float acc[NCP][4];
 #pragma unroll
     for (int c = 0; c < NCP; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f;
-    if (k0 < D) {
-        const int r_lo = warp * 32, r_hi = min(r_lo + 32, rows);
-        const ET* ep = emb + (int64_t)(rbeg + r_lo) * D + k0;
-#pragma unroll 8
-        for (int r = r_lo; r < r_hi; ++r, ep += D) {
-            const float4 e = ld4(ep);
+    auto consume = [&](const float4 (&src)[RB], int r_start) {   // rows past r_hi hold e = 0 (and dl = 0)
+#pragma unroll
+        for (int i = 0; i < RB; ++i) {
+            const float4 e = src[i];
 #pragma unroll
             for (int c4 = 0; c4 < NCP; c4 += 4) {
-                const float4 g = *reinterpret_cast<const float4*>(&dl[r][c4]);
+                const float4 g = *reinterpret_cast<const float4*>(&dl[r_start + i][c4]);
                 const float gg[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -304,6 +484,13 @@ __global__ void __launch_bounds__(K2_DW_WARPS * 32) k2_heads_dw(
                 }
             }
         }
+    };
+#pragma unroll
+    for (int b = 0; b < 32 / RB; b += 2) {
+        consume(eb[0], r_lo + b * RB);
+        if (b + 2 < 32 / RB) load_batch(eb[0], r_lo + (b + 2) * RB);
+        consume(eb[1], r_lo + (b + 1) * RB);
+        if (b + 3 < 32 / RB) load_batch(eb[1], r_lo + (b + 3) * RB);
     }
     // db partial of this chunk (column block 0 only), before dl is overwritten
     if (blockIdx.x == 0 && threadIdx.x < ncls) {
@@ -351,18 +538,36 @@ __global__ void __launch_bounds__(K2_DW_WARPS * 32) k2_heads_dw(
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    const int cols = min(K2_DW_COLS, D - blockIdx.x * K2_DW_COLS);
-    for (int i = threadIdx.x; i < ncls * cols; i += blockDim.x) {
-        const int c = i / cols, col = i - c * cols;
-        const int64_t e = (int64_t)(cls0 + c) * D + blockIdx.x * K2_DW_COLS + col;
-        float s = 0.f;
-        for (int ch = 0; ch < chunks; ++ch) s += __ldcg(dw_part + (int64_t)ch * nW + e);
-        reduce_buf[e] = s;
+    // D % 4 == 0 and column blocks start on multiples of 128: the sums go four columns at a time; the loads of 8
+    // chunks are issued together (one L2 round trip per 8 partials), the additions keep their fixed chunk order
+    const int cols4 = min(K2_DW_COLS, D - blockIdx.x * K2_DW_COLS) >> 2;
+    for (int i = threadIdx.x; i < ncls * cols4; i += K2_DW_WARPS * 32) {
+        const int c = i / cols4, q = i - c * cols4;
+        const int64_t e = (int64_t)(cls0 + c) * D + blockIdx.x * K2_DW_COLS + 4 * q;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int ch0 = 0; ch0 < chunks; ch0 += 8) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (ch0 + u < chunks) v[u] = __ldcg(reinterpret_cast<const float4*>(dw_part + (int64_t)(ch0 + u) * nW + e));
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (ch0 + u < chunks) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
+        }
+        *reinterpret_cast<float4*>(reduce_buf + e) = s;
     }
     if (blockIdx.x == 0) {
-        for (int c = threadIdx.x; c < ncls; c += blockDim.x) {
+        for (int c = threadIdx.x; c < ncls; c += K2_DW_WARPS * 32) {
             float s = 0.f;
-            for (int ch = 0; ch < chunks; ++ch) s += __ldcg(db_part + (int64_t)ch * NC + cls0 + c);
+            for (int ch0 = 0; ch0 < chunks; ch0 += 8) {
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (ch0 + u < chunks) v[u] = __ldcg(db_part + (int64_t)(ch0 + u) * NC + cls0 + c);
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (ch0 + u < chunks) s += v[u];
+            }
             reduce_buf[nW + cls0 + c] = s;
         }
         if (pass == 0)  // loss sums / denominators: one warp per entry, fixed order
@@ -523,6 +728,16 @@ extern "C" int nkbk_heads_fwd_loss_bwd(const void* emb, int emb_dtype, int B, in
                                        int loss_kind, float gamma, const float* class_weight, int64_t ignore_index,
                                        float* out_logits, float* out_probs, float* dlogits, float* reduce_buf,
                                        void* workspace, size_t workspace_bytes, void* stream) {
+    return nkbk_heads_step(emb, emb_dtype, B, D, W_cat, b_cat, seg_offsets, T, labels, loss_kind, gamma, class_weight,
+                           ignore_index, out_logits, out_probs, dlogits, reduce_buf, nullptr, nullptr, workspace,
+                           workspace_bytes, stream);
+}
+
+extern "C" int nkbk_heads_step(const void* emb, int emb_dtype, int B, int D, const float* W_cat, const float* b_cat,
+                               const int32_t* seg_offsets, int T, const int64_t* labels, int loss_kind, float gamma,
+                               const float* class_weight, int64_t ignore_index, float* out_logits, float* out_probs,
+                               float* dlogits, float* reduce_buf, int32_t* out_pred, int64_t* cm_step, void* workspace,
+                               size_t workspace_bytes, void* stream) {
     K2Seg seg;
     int rc = fill_seg(seg, seg_offsets, T, "nkbk_heads_fwd_loss_bwd");
     if (rc) return rc;
@@ -554,13 +769,17 @@ extern "C" int nkbk_heads_fwd_loss_bwd(const void* emb, int emb_dtype, int B, in
     K2FwdParams p;
     p.emb = emb; p.W = W_cat; p.bias = b_cat; p.labels = labels; p.class_weight = class_weight;
     p.out_logits = out_logits; p.out_probs = out_probs; p.dlogits = dlogits;
+    p.out_pred = out_pred;
+    p.cm_step = (cm_step != nullptr && labels != nullptr) ? reinterpret_cast<unsigned long long*>(cm_step) : nullptr;
     p.loss_part = ws + L.loss_part;
     p.counters = reinterpret_cast<unsigned int*>(ws + L.counters);
     p.n_counters = L.dw_passes * L.dw_xblocks;
     p.B = B; p.D = D; p.NC = NC; p.loss_kind = loss_kind; p.gamma = gamma; p.ignore_index = ignore_index;
     p.seg = seg;
-    const size_t smem = (size_t)(K2_FWD_ROWS * (2 * NC + 6 * T) + K2_FWD_WARPS * 64) * sizeof(float);
-    int loss_parts = L.fwd_blocks;  // rows of the per-CTA loss / denominator partial table
+    // forward v3: warp = 4 rows over the whole K, private shared-memory slice per warp, K3 fused
+    const size_t smem = (size_t)K2_V3_WARPS * K2_FWD_ROWS * (2 * NC + 6 * T) * sizeof(float);
+    const int v3_blocks = (L.fwd_blocks + K2_V3_WARPS - 1) / K2_V3_WARPS;
+    int loss_parts = L.fwd_blocks;  // rows of the per-warp loss / denominator partial table
     int tc = 0;
     if (emb_dtype == NKBK_BF16) {   // bf16 embeddings: tcgen05 / TMEM / TMA forward when the shape allows
         tc = launch_k2_tc_forward(p, ws + L.tc_w, st);
@@ -568,19 +787,34 @@ extern "C" int nkbk_heads_fwd_loss_bwd(const void* emb, int emb_dtype, int B, in
         if (tc > 0) loss_parts = tc;
     }
     if (tc > 0) {
-        // done on the tensor cores
-    } else if (emb_dtype == NKBK_F32) {
-        if (smem > 48 * 1024)
-            NKBK_CHECK_CUDA(cudaFuncSetAttribute(k2_heads_forward<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)smem));
-        k2_heads_forward<float><<<L.fwd_blocks, K2_FWD_WARPS * 32, smem, st>>>(p);
+        // done on the tensor cores; argmax / confusion counts from the logits it wrote
+        if (out_pred != nullptr || p.cm_step != nullptr) {
+            if (out_logits == nullptr) {
+                set_error("nkbk_heads_step: out_pred / cm_step on the tcgen05 path need out_logits");
+                return NKBK_E_ARG;
+            }
+            rc = nkbk_argmax_confusion(out_logits, NKBK_F32, B, NC, seg_offsets, T, p.cm_step ? labels : nullptr,
+                                       out_pred, p.cm_step ? cm_step : nullptr, stream);
+            if (rc) return rc;
+        }
     } else {
-        if (smem > 48 * 1024)
-            NKBK_CHECK_CUDA(cudaFuncSetAttribute(k2_heads_forward<__nv_bfloat16>,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k2_heads_forward<__nv_bfloat16><<<L.fwd_blocks, K2_FWD_WARPS * 32, smem, st>>>(p);
+        // stage the <= 16 x D weight tile of a pass in shared memory when it fits next to the per-warp slices
+        const size_t wtile = (size_t)std::min(NC, K2_FWD_NCB) * D * sizeof(float);
+        const size_t smem_ws = ((smem + 15) & ~size_t(15)) + wtile;
+        const bool ws_fits = smem_ws <= 200 * 1024;
+        const size_t sm = ws_fits ? smem_ws : smem;
+#define NKBK_FWD(ET, WSV)                                                                                              \
+    do {                                                                                                               \
+        if (sm > 48 * 1024)                                                                                            \
+            NKBK_CHECK_CUDA(cudaFuncSetAttribute(k2_heads_forward_v3<ET, WSV>,                                         \
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));               \
+        k2_heads_forward_v3<ET, WSV><<<v3_blocks, K2_V3_WARPS * 32, sm, st>>>(p);                                      \
+    } while (0)
+        if (emb_dtype == NKBK_F32) { if (ws_fits) NKBK_FWD(float, true); else NKBK_FWD(float, false); }
+        else { if (ws_fits) NKBK_FWD(__nv_bfloat16, true); else NKBK_FWD(__nv_bfloat16, false); }
+#undef NKBK_FWD
     }
-    if (tc == 0) NKBK_CHECK_LAUNCH("k2_heads_forward");
+    if (tc == 0) NKBK_CHECK_LAUNCH("k2_heads_forward_v3");
 
     if (dlogits != nullptr) {
         dim3 grid(L.dw_xblocks, L.dw_chunks);
@@ -648,6 +882,7 @@ extern "C" int nkbk_loss_fwd_bwd(const void* logits, int dtype, int B, int ld, c
     K2FwdParams p;
     p.emb = nullptr; p.W = nullptr; p.bias = nullptr; p.labels = labels; p.class_weight = class_weight;
     p.out_logits = nullptr; p.out_probs = out_probs; p.dlogits = dlogits; p.loss_part = ws;
+    p.out_pred = nullptr; p.cm_step = nullptr;
     p.counters = nullptr; p.n_counters = 0;
     p.B = B; p.D = 0; p.NC = NC; p.loss_kind = loss_kind; p.gamma = gamma; p.ignore_index = ignore_index; p.seg = seg;
     const size_t smem = (size_t)(K2_FWD_ROWS * (2 * NC + 6 * T)) * sizeof(float);

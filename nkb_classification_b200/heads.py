@@ -65,16 +65,16 @@ class _FusedHeads(torch.autograd.Function):
             bufs = ops.HeadsBuffers(B, pack.D, pack.seg, emb_c.device, want_logits=True, want_probs=True,
                                     want_grads=need_grads)
             state["bufs"] = {key: bufs}
-        ops.heads_fwd_loss_bwd(emb_c, pack.W_cat, pack.b_cat, labels, bufs, state["loss_kind"], state["gamma"],
-                               state["class_weight"], state["ignore_index"])
         cm, cm_step = state.get("cm"), state.get("cm_step")
         pred = None
         if state.get("want_pred", True):
             pred = torch.empty((B, pack_T(pack)), dtype=torch.int32, device=emb_c.device)
-            ops.argmax_confusion(bufs.logits, pack.seg, labels if cm_step is not None else None, cm_step, out_pred=pred)
+        # K3 (argmax + confusion counts) rides in K2's forward epilogue
+        ops.heads_fwd_loss_bwd(emb_c, pack.W_cat, pack.b_cat, labels, bufs, state["loss_kind"], state["gamma"],
+                               state["class_weight"], state["ignore_index"], out_pred=pred,
+                               cm_step=cm_step if (pred is not None and labels is not None) else None)
         comm: Communicator = state["comm"]
-        comm.allreduce_heads(bufs.reduce_buf, cm_step)
-        ops.heads_finalize(bufs, cm, cm_step)
+        comm.exchange_finalize(bufs, cm, cm_step, state.get("transport", "peer"))
         ctx.state, ctx.bufs, ctx.emb_dtype, ctx.need_demb = state, bufs, emb.dtype, emb.requires_grad
         ctx.n_params = len(params)
         state["last"] = (bufs, pred)

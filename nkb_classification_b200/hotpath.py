@@ -42,7 +42,6 @@ class HotPath:
         self._images: Dict[int, torch.Tensor] = {}
         self._pred: Dict[int, torch.Tensor] = {}
         self._desc = None
-        self._peer_ready = False
 
     # ---- K1 ----
     def preprocess(self, frames: torch.Tensor, boxes: torch.Tensor, frame_idx: torch.Tensor,
@@ -80,8 +79,6 @@ class HotPath:
         (already summed over ranks)."""
         B = emb.shape[0]
         bufs = self._buffers(B, train, want_probs)
-        ops.heads_fwd_loss_bwd(emb, W_cat, b_cat, labels, bufs, self.loss_kind, self.gamma, self.class_weight,
-                               self.ignore_index)
         do_cm = update_confusion and labels is not None
         pred = None
         if want_pred or do_cm:
@@ -89,24 +86,14 @@ class HotPath:
             if pred is None:
                 pred = torch.empty((B, self.T), dtype=torch.int32, device=self.device)
                 self._pred = {B: pred}
-            ops.argmax_confusion(bufs.logits, self.seg, labels if do_cm else None, self.cm_step if do_cm else None,
-                                 out_pred=pred)
-        if self.comm.world > 1 and self.transport == "peer" and not self._peer_ready:
-            # collective, first step only: map the peers' inboxes, sized for this path's payload (a no-op when the
-            # communicator already holds large enough ones); falls back to NCCL when P2P is not available
-            if self.comm.init_peer(self.device, ops.heads_reduce_buf_len(self.D, self.NC, self.T), self.cm.numel()):
-                self._peer_ready = True
-            else:
-                self.transport = "nccl"
-        if self.comm.world > 1 and self.transport == "peer":
-            # K4': push + wait + rank-ordered sum + finalize in one launch over NVLink peer memory
-            ops.peer_allreduce_finalize(bufs, self.cm if do_cm else None, self.cm_step if do_cm else None)
-        else:
-            self.comm.allreduce_heads(bufs.reduce_buf, self.cm_step if do_cm else None)
-            if do_cm:
-                ops.heads_finalize(bufs, self.cm, self.cm_step)
-            else:
-                ops.heads_finalize(bufs)
+        # K2 with K3 fused into its epilogue: argmax + confusion counts while the logits are on chip
+        ops.heads_fwd_loss_bwd(emb, W_cat, b_cat, labels, bufs, self.loss_kind, self.gamma, self.class_weight,
+                               self.ignore_index, out_pred=pred, cm_step=self.cm_step if do_cm else None)
+        # K4' (fused push / rank-ordered sum / finalize over NVLink peer memory) or K4 (NCCL) + finalize
+        used = self.comm.exchange_finalize(bufs, self.cm if do_cm else None, self.cm_step if do_cm else None,
+                                           self.transport)
+        if self.comm.world > 1:
+            self.transport = used
         bufs.pred = pred
         return bufs
 

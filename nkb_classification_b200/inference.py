@@ -48,8 +48,8 @@ def inference(model: torch.nn.Module, loader, classes: Union[list, dict], save_p
         if pack is not None:
             emb = emb.contiguous()
             bufs = ops.HeadsBuffers(emb.shape[0], pack.D, pack.seg, emb.device, want_probs=False, want_grads=False)
-            ops.heads_fwd_loss_bwd(emb, pack.W_cat, pack.b_cat, None, bufs)
-            pred, _ = ops.argmax_confusion(bufs.logits, pack.seg)
+            pred = torch.empty((emb.shape[0], len(pack.seg) - 1), dtype=torch.int32, device=emb.device)
+            ops.heads_fwd_loss_bwd(emb, pack.W_cat, pack.b_cat, None, bufs, out_pred=pred)   # K2 forward + fused argmax
             names = pack.names
         else:  # scripted / foreign model: logits from the model, argmax still K3
             if isinstance(out, dict):

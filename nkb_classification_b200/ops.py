@@ -193,9 +193,11 @@ class HeadsBuffers:
 def heads_fwd_loss_bwd(
     emb: torch.Tensor, W_cat: torch.Tensor, b_cat: torch.Tensor, labels: Optional[torch.Tensor], bufs: HeadsBuffers,
     loss_kind: int = LOSS_FOCAL, gamma: float = 2.0, class_weight: Optional[torch.Tensor] = None,
-    ignore_index: int = -100,
+    ignore_index: int = -100, out_pred: Optional[torch.Tensor] = None, cm_step: Optional[torch.Tensor] = None,
 ) -> HeadsBuffers:
-    """Forward + loss terms + dlogits + unnormalised dW/db into ``bufs`` (see nkbk_heads_fwd_loss_bwd)."""
+    """Forward + loss terms + dlogits + unnormalised dW/db into ``bufs`` (see nkbk_heads_step).
+    ``out_pred`` int32 [B,T] / ``cm_step`` int64 confusion counts (accumulated; needs labels): K3 fused into the
+    forward epilogue -- same results as a separate :func:`argmax_confusion` on ``bufs.logits``, one launch fewer."""
     _need_cuda("emb", emb)
     _need_cuda("W_cat", W_cat)
     if emb.dtype not in _DT:
@@ -217,10 +219,19 @@ def heads_fwd_loss_bwd(
         if class_weight.dtype != torch.float32 or class_weight.numel() != bufs.NC or not class_weight.is_cuda:
             raise ValueError("class_weight must be CUDA float32 [NC]")
     seg, T, _ = _seg_array(bufs.seg)
-    rc = lib().nkbk_heads_fwd_loss_bwd(
+    if out_pred is not None and (out_pred.dtype != torch.int32 or out_pred.numel() != B * T
+                                 or not out_pred.is_contiguous() or not out_pred.is_cuda):
+        raise ValueError("out_pred must be a contiguous CUDA int32 [B,T]")
+    if cm_step is not None:
+        if labels is None:
+            raise ValueError("cm_step needs labels")
+        if cm_step.dtype != torch.int64 or cm_step.numel() != confusion_len(bufs.seg) or not cm_step.is_cuda:
+            raise ValueError("cm_step must be CUDA int64 of confusion_len(seg) elements")
+    rc = lib().nkbk_heads_step(
         _ptr(emb), _DT[emb.dtype], B, D, _ptr(W_cat), _ptr(b_cat), seg, T, _ptr(labels), int(loss_kind), float(gamma),
         _ptr(class_weight), int(ignore_index), _ptr(bufs.logits), _ptr(bufs.probs), _ptr(bufs.dlogits),
-        _ptr(bufs.reduce_buf), _ptr(bufs.workspace), bufs.workspace.numel(), _stream(emb.device),
+        _ptr(bufs.reduce_buf), _ptr(out_pred), _ptr(cm_step), _ptr(bufs.workspace), bufs.workspace.numel(),
+        _stream(emb.device),
     )
     check(rc)
     return bufs

@@ -51,6 +51,7 @@ class Communicator:
         self.active = False          # NCCL communicator (K4)
         self.peer_active = False     # NVLink peer-memory transport (K4')
         self._peer_cap = (0, 0)
+        self._peer_failed = False
 
     def init_from_torch_distributed(self, device: torch.device) -> "Communicator":
         import torch.distributed as dist
@@ -74,6 +75,8 @@ class Communicator:
         elements.  Collective: every rank must call it.  Returns False (and leaves the NCCL transport in charge) when
         the devices cannot map each other's memory; all ranks take the same decision."""
         import torch.distributed as dist
+        if self._peer_failed:
+            return False
         if self.peer_active:
             if max_f32 <= self._peer_cap[0] and max_i64 <= self._peer_cap[1]:
                 return True
@@ -93,6 +96,7 @@ class Communicator:
             ok = all(flags)
         if not ok:
             lib().nkbk_peer_shutdown()
+            self._peer_failed = True     # do not retry the collective set-up every step
             return False
         self.peer_active = True
         self._peer_cap = (int(max_f32), int(max_i64))
@@ -114,6 +118,26 @@ class Communicator:
         st = ctypes.c_int32(0)
         check(lib().nkbk_peer_status(ctypes.byref(st)))
         return int(st.value)
+
+    def exchange_finalize(self, bufs, cm_total: Optional[torch.Tensor] = None, cm_step: Optional[torch.Tensor] = None,
+                          transport: str = "peer") -> str:
+        """The path's exchange step + K2 finalize for one training step: sums ``bufs.reduce_buf`` (and ``cm_step``)
+        over the ranks, divides by the global denominators, folds the step confusion counts into ``cm_total``.
+        ``transport``: "peer" = K4' (one fused kernel over NVLink peer memory; set up collectively on first use,
+        silently replaced by "nccl" when the GPUs cannot map each other's memory), "nccl" = K4 + finalize launch.
+        Returns the transport used.  world == 1: just the finalize."""
+        from . import ops
+        if self.world > 1 and transport == "peer":
+            dev = bufs.reduce_buf.device
+            n_cm = 0 if cm_step is None else cm_step.numel()
+            if not self.init_peer(dev, bufs.reduce_buf.numel(), n_cm):
+                transport = "nccl"
+        if self.world > 1 and transport == "peer":
+            ops.peer_allreduce_finalize(bufs, cm_total, cm_step)
+            return "peer"
+        self.allreduce_heads(bufs.reduce_buf, cm_step)
+        ops.heads_finalize(bufs, cm_total, cm_step)
+        return "nccl" if self.world > 1 else "local"
 
     def allreduce_heads(self, reduce_buf: Optional[torch.Tensor], cm: Optional[torch.Tensor]) -> None:
         """Sum both payloads across ranks, in place, on the current stream.  No-op for world == 1."""
