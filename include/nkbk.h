@@ -84,21 +84,30 @@ int nkbk_preprocess_crops(const void* frames_base, const int64_t* frame_desc, in
 
 /* K1 with the deterministic part of the TRAIN-time pipeline fused in: per-crop parameters drawn on
  * the host (configs/singletask_config.py:172-194 -- A.HorizontalFlip, A.VerticalFlip, A.RandomBrightnessContrast
- * with brightness_by_max, A.CoarseDropout) are applied, in that order, to the resized / padded uint8 image before
- * Normalize; same arithmetic as albumentations 1.x (cv2.flip, the clip(f32(v)*alpha + beta*255).astype(uint8)
- * look-up table, rectangle fill).  All other arguments as nkbk_preprocess_crops.
+ * with brightness_by_max, A.HueSaturationValue, A.CoarseDropout) are applied, in that order, to the resized / padded
+ * uint8 image before Normalize; same arithmetic as albumentations 1.x (cv2.flip, the clip(f32(v)*alpha +
+ * beta*255).astype(uint8) look-up table, cv2 RGB2HSV -> hue/sat/val LUTs -> cv2 HSV2RGB, rectangle fill).
+ * All other arguments as nkbk_preprocess_crops.
  *   aug_flags   int32 [n]   bit 0 horizontal flip, bit 1 vertical flip, bit 2 brightness/contrast on,
- *                           bits 8.. number of holes (<= max_holes)
+ *                           bit 3 hue/saturation/value shift on, bits 8.. number of holes (<= max_holes)
  *   aug_alpha   fp32 [n]    1 + contrast draw        (read when bit 2 is set)
  *   aug_beta    fp32 [n]    f32(brightness draw * max_pixel_value)
  *   aug_holes   int32 [n][max_holes][4] = x1, y1, x2, y2 in output pixels (ends exclusive); max_holes <= 16
- *   hole_fill   host uint8[3], CoarseDropout fill_value in OUTPUT channel order (NULL = 0) */
+ *   hole_fill   host uint8[3], CoarseDropout fill_value in OUTPUT channel order (NULL = 0)
+ *   aug_hsv_lut uint8 [n][3][256]: per sample the hue, sat and val tables albumentations builds
+ *               (mod(h + shift, 180), clip(s + shift, 0, 255), clip(v + shift, 0, 255), truncated); read only for
+ *               samples with bit 3 set; may be NULL when no sample sets it
+ *   hsv_trunc_cols  cv2's 8-bit HSV2RGB converts x * 255 to uint8 by TRUNCATION in its vectorised body (the first
+ *               (out_w / lanes) * lanes pixels of every image row; lanes = 32 with AVX2) and by round-to-nearest-
+ *               even in the scalar tail of the row: output columns [0, hsv_trunc_cols) take the former, the rest the
+ *               latter (pass (out_w / 32) * 32 to reproduce an AVX2 host, 0 for the scalar rounding everywhere) */
 int nkbk_preprocess_crops_aug(const void* frames_base, const int64_t* frame_desc, int n_frames, const int32_t* boxes,
                               const int32_t* frame_idx, int n, int mode, int out_h, int out_w, int max_size,
                               const uint8_t* pad_value, const float* mean255, const float* denom, int channel_swap,
                               const int32_t* aug_flags, const float* aug_alpha, const float* aug_beta,
-                              const int32_t* aug_holes, int max_holes, const uint8_t* hole_fill, void* out,
-                              int out_dtype, uint8_t* out_u8, int32_t* bad_count, void* stream);
+                              const int32_t* aug_holes, int max_holes, const uint8_t* hole_fill,
+                              const uint8_t* aug_hsv_lut, int hsv_trunc_cols, void* out, int out_dtype,
+                              uint8_t* out_u8, int32_t* bad_count, void* stream);
 
 /* Host-only helper (no CUDA): the per-axis coefficient table K1 uses, for
  * parity tests on machines without a GPU.  Writes dsize entries each. */
@@ -107,6 +116,8 @@ int nkbk_debug_axis_table(int dsize, int ssize, int horizontal, int32_t* src_ind
 int nkbk_debug_letterbox(int h, int w, int max_size, int out_h, int out_w, int32_t* out4);
 /* Host-only helper: the brightness/contrast look-up table K1 evaluates per pixel (256 entries). */
 int nkbk_debug_brightness_contrast_lut(float alpha, float beta, uint8_t* lut256);
+/* Host-only helper: K1's HueSaturationValue pixel function (RGB2HSV, the [3][256] LUTs, HSV2RGB) on n RGB pixels. */
+int nkbk_debug_hsv_shift(const uint8_t* rgb_in, int64_t n, const uint8_t* lut768, int trunc, uint8_t* rgb_out);
 
 /* ------------------------------------------------------------------------
  * K2  all task heads as one segmented GEMM + softmax + CE/focal loss + grads

@@ -31,8 +31,9 @@ SYMBOLS = {
                                       c_void_p, c_void_p, c_void_p]),
     "nkbk_preprocess_crops_aug": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                           c_int, POINTER(c_uint8), POINTER(c_float), POINTER(c_float), c_int,
-                                          c_void_p, c_void_p, c_void_p, c_void_p, c_int, POINTER(c_uint8),
-                                          c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+                                          c_void_p, c_void_p, c_void_p, c_void_p, c_int, POINTER(c_uint8), c_void_p,
+                                          c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "nkbk_debug_hsv_shift": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_void_p]),
     "nkbk_debug_brightness_contrast_lut": (c_int, [c_float, c_float, c_void_p]),
     "nkbk_debug_axis_table": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "nkbk_debug_letterbox": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p]),

@@ -3,6 +3,7 @@
 #pragma once
 #include "nkbk_common.cuh"
 #include "k1_coef.h"
+#include <math.h>
 
 namespace nkbk {
 
@@ -33,8 +34,10 @@ struct K1Params {
     const int32_t* aug_holes;   // [n][aug_max_holes][4]  x1, y1, x2, y2 in output pixels (exclusive ends)
     int aug_max_holes;
     uint32_t aug_fill[3];       // CoarseDropout fill value per output channel
+    const uint8_t* aug_hsv_lut; // [n][3][256]  HueSaturationValue look-up tables (hue, sat, val), read when bit 3 is set
+    int aug_hsv_trunc_cols;     // output columns [0, this) take cv2's SIMD rounding (truncation), the rest its scalar one
 };
-constexpr int K1_AUG_HFLIP = 1, K1_AUG_VFLIP = 2, K1_AUG_BC = 4;
+constexpr int K1_AUG_HFLIP = 1, K1_AUG_VFLIP = 2, K1_AUG_BC = 4, K1_AUG_HSV = 8;
 constexpr int K1_AUG_MAX_HOLES = 16;
 
 // albumentations 1.x `_brightness_contrast_adjust_uint` with beta_by_max: the 256-entry LUT
@@ -50,6 +53,81 @@ __host__ __device__ __forceinline__ uint32_t k1_brightness_contrast(uint32_t v, 
     float u = t < 0.f ? 0.f : (t > 255.f ? 255.f : t);
     return (uint32_t)(int)u;
 #endif
+}
+
+// ---- A.HueSaturationValue on uint8 RGB: cv2.cvtColor(RGB2HSV) -> three 256-entry LUTs -> cv2.cvtColor(HSV2RGB) ----
+// RGB2HSV is OpenCV's 8-bit fixed-point path (hsv_shift = 12, division tables cvRound((255 << 12) / v) and
+// cvRound((180 << 12) / (6 diff)), evaluated here as exact round-half-even integer divisions); HSV2RGB is its
+// float path with the contraction OpenCV's build uses: tab2 = v * fma(-s, f, 1), tab3 = v * fma(-s, 1 - f, 1),
+// then x * 255 -> uint8.  OpenCV converts that last value in two different ways: its vectorised body (the first
+// (W / lanes) * lanes pixels of every image row, lanes = 32 with AVX2) TRUNCATES, the scalar tail of the row rounds
+// to nearest even -- `trunc` selects which.  Checked exhaustively against cv2 4.13 (2^24 RGB triples; 180 * 2^16
+// HSV triples, both roundings).
+__host__ __device__ __forceinline__ int k1_div_rhe(int n, int d) {  // round-half-even(n / d), n, d > 0
+    const int q = n / d, r = n - q * d, t = 2 * r;
+    return q + ((t > d || (t == d && (q & 1))) ? 1 : 0);
+}
+__host__ __device__ __forceinline__ void k1_rgb2hsv(int r, int g, int b, int& h, int& s, int& v) {
+    v = r > g ? r : g; v = v > b ? v : b;
+    int vmin = r < g ? r : g; vmin = vmin < b ? vmin : b;
+    const int diff = v - vmin;
+    const int sd = v ? k1_div_rhe(255 << 12, v) : 0;
+    const int hd = diff ? k1_div_rhe((180 << 12) / 6, diff) : 0;
+    s = (diff * sd + (1 << 11)) >> 12;
+    int hh = (v == r) ? (g - b) : ((v == g) ? (b - r + 2 * diff) : (r - g + 4 * diff));
+    hh = (hh * hd + (1 << 11)) >> 12;   // arithmetic shift, as in OpenCV
+    h = hh < 0 ? hh + 180 : hh;
+}
+__host__ __device__ __forceinline__ void k1_hsv2rgb(int h, int s, int v, bool trunc, uint32_t& r, uint32_t& g,
+                                                    uint32_t& b) {
+    const float k255 = 0x1.010102p-8f;   // 1.f / 255.f
+    const float hscale = 0x1.111112p-5f; // 6.f / 180.f
+#ifdef __CUDA_ARCH__
+    const float sf = __fmul_rn((float)s, k255), vf = __fmul_rn((float)v, k255), hf = __fmul_rn((float)h, hscale);
+    const float pre = truncf(hf), fr = __fsub_rn(hf, pre);
+    const float t1 = __fmul_rn(vf, __fsub_rn(1.f, sf));
+    const float t2 = __fmul_rn(vf, __fmaf_rn(-sf, fr, 1.f));
+    const float t3 = __fmul_rn(vf, __fmaf_rn(-sf, __fsub_rn(1.f, fr), 1.f));
+#else
+    volatile float sf = (float)s * k255, vf = (float)v * k255, hf = (float)h * hscale;
+    volatile float pre = truncf(hf);
+    volatile float fr = hf - pre;
+    volatile float oms = 1.f - sf, omf = 1.f - fr;
+    volatile float t1 = vf * oms;
+    volatile float i2 = fmaf(-sf, fr, 1.f), i3 = fmaf(-sf, omf, 1.f);
+    volatile float t2 = vf * i2, t3 = vf * i3;
+#endif
+    int sector = (int)pre;
+    sector = sector >= 6 ? sector - 6 : sector;
+    float bb, gg, rr;   // sector_data = {1,3,0},{1,0,2},{3,0,1},{0,2,1},{0,1,3},{2,1,0} -> (b, g, r) from tab0..3
+    switch (sector) {
+        case 0: bb = t1; gg = t3; rr = vf; break;
+        case 1: bb = t1; gg = vf; rr = t2; break;
+        case 2: bb = t3; gg = vf; rr = t1; break;
+        case 3: bb = vf; gg = t2; rr = t1; break;
+        case 4: bb = vf; gg = t1; rr = t3; break;
+        default: bb = t2; gg = t1; rr = vf; break;
+    }
+#ifdef __CUDA_ARCH__
+    const float r255 = __fmul_rn(rr, 255.f), g255 = __fmul_rn(gg, 255.f), b255 = __fmul_rn(bb, 255.f);
+    const int ri = trunc ? __float2int_rz(r255) : __float2int_rn(r255);
+    const int gi = trunc ? __float2int_rz(g255) : __float2int_rn(g255);
+    const int bi = trunc ? __float2int_rz(b255) : __float2int_rn(b255);
+#else
+    volatile float r255 = rr * 255.f, g255 = gg * 255.f, b255 = bb * 255.f;
+    const int ri = trunc ? (int)r255 : (int)rintf(r255), gi = trunc ? (int)g255 : (int)rintf(g255),
+              bi = trunc ? (int)b255 : (int)rintf(b255);
+#endif
+    r = (uint32_t)(ri < 0 ? 0 : (ri > 255 ? 255 : ri));
+    g = (uint32_t)(gi < 0 ? 0 : (gi > 255 ? 255 : gi));
+    b = (uint32_t)(bi < 0 ? 0 : (bi > 255 ? 255 : bi));
+}
+// lut: [3][256] = hue, sat, val tables of this sample
+template <typename LoadByte>
+__host__ __device__ __forceinline__ void k1_hsv_shift(uint32_t& r, uint32_t& g, uint32_t& b, bool trunc, LoadByte ld) {
+    int h, s, v;
+    k1_rgb2hsv((int)r, (int)g, (int)b, h, s, v);
+    k1_hsv2rgb((int)ld(h), (int)ld(256 + s), (int)ld(512 + v), trunc, r, g, b);
 }
 
 template <typename OutT>

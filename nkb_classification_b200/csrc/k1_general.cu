@@ -72,7 +72,9 @@ struct K1AugArgs {
     const float* beta;
     const int32_t* holes;
     int max_holes;
-    const uint8_t* fill;  // host [3]
+    const uint8_t* fill;     // host [3]
+    const uint8_t* hsv_lut;  // device [n][3][256] or NULL
+    int hsv_trunc_cols;
 };
 
 }  // namespace nkbk
@@ -100,14 +102,15 @@ extern "C" int nkbk_preprocess_crops_aug(const void* frames_base, const int64_t*
                                          int out_w, int max_size, const uint8_t* pad_value, const float* mean255,
                                          const float* denom, int channel_swap, const int32_t* aug_flags,
                                          const float* aug_alpha, const float* aug_beta, const int32_t* aug_holes,
-                                         int max_holes, const uint8_t* hole_fill, void* out, int out_dtype,
-                                         uint8_t* out_u8, int32_t* bad_count, void* stream) {
+                                         int max_holes, const uint8_t* hole_fill, const uint8_t* aug_hsv_lut,
+                                         int hsv_trunc_cols, void* out, int out_dtype, uint8_t* out_u8,
+                                         int32_t* bad_count, void* stream) {
     NKBK_CHECK_ARG(n <= 0 || aug_flags != nullptr, "nkbk_preprocess_crops_aug: NULL aug_flags");
     NKBK_CHECK_ARG(n <= 0 || (aug_alpha != nullptr && aug_beta != nullptr), "nkbk_preprocess_crops_aug: NULL aug_alpha / aug_beta");
     NKBK_CHECK_ARG(max_holes >= 0 && max_holes <= K1_AUG_MAX_HOLES, "nkbk_preprocess_crops_aug: max_holes=%d outside [0,%d]",
                    max_holes, K1_AUG_MAX_HOLES);
     NKBK_CHECK_ARG(max_holes == 0 || n <= 0 || aug_holes != nullptr, "nkbk_preprocess_crops_aug: NULL aug_holes");
-    K1AugArgs a{aug_flags, aug_alpha, aug_beta, aug_holes, max_holes, hole_fill};
+    K1AugArgs a{aug_flags, aug_alpha, aug_beta, aug_holes, max_holes, hole_fill, aug_hsv_lut, hsv_trunc_cols};
     return k1_preprocess_impl(frames_base, frame_desc, n_frames, boxes, frame_idx, n, mode, out_h, out_w, max_size,
                               pad_value, mean255, denom, channel_swap, out, out_dtype, out_u8, bad_count, &a, stream);
 }
@@ -151,9 +154,13 @@ static int k1_preprocess_impl(const void* frames_base, const int64_t* frame_desc
     p.out = out; p.out_u8 = out_u8; p.bad_count = bad_count;
     p.aug_flags = nullptr; p.aug_alpha = nullptr; p.aug_beta = nullptr; p.aug_holes = nullptr; p.aug_max_holes = 0;
     p.aug_fill[0] = p.aug_fill[1] = p.aug_fill[2] = 0u;
+    p.aug_hsv_lut = nullptr;
+    p.aug_hsv_trunc_cols = 0;
     if (aug != nullptr) {
         p.aug_flags = aug->flags; p.aug_alpha = aug->alpha; p.aug_beta = aug->beta; p.aug_holes = aug->holes;
         p.aug_max_holes = aug->max_holes;
+        p.aug_hsv_lut = aug->hsv_lut;
+        p.aug_hsv_trunc_cols = aug->hsv_trunc_cols;
         for (int c = 0; c < 3; ++c) p.aug_fill[c] = aug->fill ? aug->fill[c] : 0u;
     }
 
@@ -238,5 +245,16 @@ extern "C" int nkbk_debug_letterbox(int h, int w, int max_size, int out_h, int o
 extern "C" int nkbk_debug_brightness_contrast_lut(float alpha, float beta, uint8_t* lut256) {
     NKBK_CHECK_ARG(lut256 != nullptr, "nkbk_debug_brightness_contrast_lut: NULL output");
     for (int v = 0; v < 256; ++v) lut256[v] = (uint8_t)k1_brightness_contrast((uint32_t)v, alpha, beta);
+    return NKBK_OK;
+}
+
+extern "C" int nkbk_debug_hsv_shift(const uint8_t* rgb_in, int64_t n, const uint8_t* lut768, int trunc,
+                                    uint8_t* rgb_out) {
+    NKBK_CHECK_ARG(n >= 0 && (n == 0 || (rgb_in && lut768 && rgb_out)), "nkbk_debug_hsv_shift: bad argument");
+    for (int64_t i = 0; i < n; ++i) {
+        uint32_t r = rgb_in[3 * i], g = rgb_in[3 * i + 1], b = rgb_in[3 * i + 2];
+        k1_hsv_shift(r, g, b, trunc != 0, [&](int k) { return (uint32_t)lut768[k]; });
+        rgb_out[3 * i] = (uint8_t)r; rgb_out[3 * i + 1] = (uint8_t)g; rgb_out[3 * i + 2] = (uint8_t)b;
+    }
     return NKBK_OK;
 }

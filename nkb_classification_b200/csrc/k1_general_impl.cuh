@@ -94,11 +94,18 @@ __device__ __forceinline__ void k1_process_band(const K1Params& p, const int cro
     const bool hflip = AUG && (aflags & K1_AUG_HFLIP), vflip = AUG && (aflags & K1_AUG_VFLIP);
     const int xstep = hflip ? -32 : 32;                       // destination column step between this lane's j's
     const int xd0 = hflip ? p.out_w - 1 - ox0 : ox0;          // destination column of j = 0
-    // final uint8 value of channel c at destination (yd, xd) given the resized / padded value v
-    auto augment = [&](uint32_t v, int c, bool in_hole) -> uint32_t {
-        if (!AUG) return v;
-        if (aflags & K1_AUG_BC) v = k1_brightness_contrast(v, a_alpha, a_beta);
-        return in_hole ? p.aug_fill[c] : v;
+    // the colour ops on one pixel, in the reference's order: RandomBrightnessContrast, HueSaturationValue, then the
+    // CoarseDropout fill.  px is in OUTPUT channel order (RGB after the optional BGR swap).
+    const uint8_t* hsv_lut = (AUG && (aflags & K1_AUG_HSV)) ? p.aug_hsv_lut + (int64_t)crop * 768 : nullptr;
+    auto augment3 = [&](uint32_t (&px)[3], bool in_hole, int xd) {   // xd: destination column of the pixel
+        if (!AUG) return;
+        if (aflags & K1_AUG_BC) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) px[c] = k1_brightness_contrast(px[c], a_alpha, a_beta);
+        }
+        if (hsv_lut != nullptr)
+            k1_hsv_shift(px[0], px[1], px[2], xd < p.aug_hsv_trunc_cols, [&](int i) { return (uint32_t)__ldg(hsv_lut + i); });
+        if (in_hole) { px[0] = p.aug_fill[0]; px[1] = p.aug_fill[1]; px[2] = p.aug_fill[2]; }
     };
     // bit j set: destination column of (lane, j) on destination row yd lies inside a CoarseDropout hole
     auto hole_mask = [&](int yd) -> uint32_t {
@@ -230,11 +237,12 @@ __device__ __forceinline__ void k1_process_band(const K1Params& p, const int cro
                 if (wmask >> j & 1) {
                     if (AUG) {
                         const float mm[3] = {m0, m1, m2}, dd[3] = {d0, d1, d2};
+                        uint32_t pv[3] = {p.padu[0], p.padu[1], p.padu[2]};
+                        augment3(pv, hmask >> j & 1, xd0 + xstep * j);
 #pragma unroll
                         for (int c = 0; c < 3; ++c) {
-                            const uint32_t v = augment(p.padu[c], c, hmask >> j & 1);
-                            store_out<OutT>(o + c * plane + xstep * j, __fmul_rn(__fsub_rn((float)v, mm[c]), dd[c]));
-                            if (WRITE_U8) u[3 * xstep * j + c] = (uint8_t)v;
+                            store_out<OutT>(o + c * plane + xstep * j, __fmul_rn(__fsub_rn((float)pv[c], mm[c]), dd[c]));
+                            if (WRITE_U8) u[3 * xstep * j + c] = (uint8_t)pv[c];
                         }
                     } else {
 #pragma unroll
@@ -282,8 +290,8 @@ __device__ __forceinline__ void k1_process_band(const K1Params& p, const int cro
                 const uint32_t t1 = __umulhi(b1, Hb[j][c]);
                 px[c] = (t0 + t1 + 2u) >> 2;
                 if (GENERAL && !(vmask >> j & 1)) px[c] = p.padu[c];
-                if (AUG) px[c] = augment(px[c], c, hmask >> j & 1);
             }
+            if (AUG) augment3(px, hmask >> j & 1, xd0 + xstep * j);
             const float f0 = __fmul_rn(__fsub_rn((float)px[0], m0), d0);
             const float f1 = __fmul_rn(__fsub_rn((float)px[1], m1), d1);
             const float f2 = __fmul_rn(__fsub_rn((float)px[2], m2), d2);

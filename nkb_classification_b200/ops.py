@@ -119,10 +119,18 @@ def preprocess_crops(
     a_beta = torch.from_numpy(np.ascontiguousarray(aug.beta, dtype=np.float32)).to(dev, non_blocking=True)
     a_holes = torch.from_numpy(np.ascontiguousarray(aug.holes, dtype=np.int32)).to(dev, non_blocking=True)
     fill = (c_uint8 * 3)(*[int(v) for v in aug.fill])
+    a_hsv = None
+    if getattr(aug, "hsv_lut", None) is not None:
+        if aug.hsv_lut.shape != (n, 3, 256) or aug.hsv_lut.dtype != np.uint8:
+            raise ValueError("hsv_lut must be uint8 [n, 3, 256]")
+        a_hsv = torch.from_numpy(np.ascontiguousarray(aug.hsv_lut)).to(dev, non_blocking=True)
+    elif np.any(np.asarray(aug.flags) & 8):
+        raise ValueError("a sample has the HueSaturationValue flag but the batch carries no hsv_lut")
     rc = lib().nkbk_preprocess_crops_aug(
         _ptr(frames), _ptr(frame_desc), n_frames, _ptr(boxes), _ptr(frame_idx), n, plan.mode, plan.out_h, plan.out_w,
         plan.max_size, pad, m, d, int(plan.channel_swap), _ptr(a_flags), _ptr(a_alpha), _ptr(a_beta), _ptr(a_holes),
-        aug.max_holes, fill, _ptr(out), _DT[out_dtype], _ptr(out_u8), _ptr(bad_count), _stream(dev),
+        aug.max_holes, fill, _ptr(a_hsv), int(getattr(aug, "hsv_trunc_cols", 0)), _ptr(out), _DT[out_dtype],
+        _ptr(out_u8), _ptr(bad_count), _stream(dev),
     )
     check(rc)
     return out
@@ -142,6 +150,16 @@ def debug_brightness_contrast_lut(alpha: float, beta255: float) -> np.ndarray:
     lut = np.empty(256, dtype=np.uint8)
     check(lib().nkbk_debug_brightness_contrast_lut(float(alpha), float(beta255), lut.ctypes.data))
     return lut
+
+
+def debug_hsv_shift(rgb: np.ndarray, lut: np.ndarray, trunc: bool = False) -> np.ndarray:
+    """Host-only: K1's HueSaturationValue pixel function on uint8 [..., 3] RGB pixels with a [3, 256] table;
+    ``trunc``: cv2's vectorised rounding (truncate) instead of its scalar one (nearest even)."""
+    rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+    lut = np.ascontiguousarray(lut, dtype=np.uint8).reshape(768)
+    out = np.empty_like(rgb)
+    check(lib().nkbk_debug_hsv_shift(rgb.ctypes.data, rgb.size // 3, lut.ctypes.data, int(bool(trunc)), out.ctypes.data))
+    return out
 
 
 def debug_letterbox(h: int, w: int, max_size: int, out_h: int, out_w: int):

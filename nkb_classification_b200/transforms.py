@@ -16,11 +16,12 @@ the same names / keyword arguments so a config can be written without it.
 
 Train-time pipelines (configs/singletask_config.py:162-201) may add, between the
 geometry and Normalize, the ops whose arithmetic K1 fuses: ``HorizontalFlip``,
-``VerticalFlip``, ``RandomBrightnessContrast`` (brightness_by_max) and
-``CoarseDropout`` (last).  Their per-sample parameters are drawn on the host by
+``VerticalFlip``, ``RandomBrightnessContrast`` (brightness_by_max),
+``HueSaturationValue`` and ``CoarseDropout`` (last) -- i.e. the whole train
+pipeline of configs/singletask_config.py and configs/multitask_config.py.  Their per-sample parameters are drawn on the host by
 :func:`draw_augmentations` (same distributions and draw order as albumentations
 1.3.x with Python's ``random``) and shipped to the kernel as small arrays.
-Anything else (HueSaturationValue, MotionBlur, fog / rain / shadow, other border
+Anything else (MotionBlur, fog / rain / shadow, other border
 modes or interpolations) raises ``NotImplementedError`` -- no silent fallback.
 """
 from __future__ import annotations
@@ -92,6 +93,59 @@ class RandomBrightnessContrast(_Op):
         self.brightness_by_max, self.p, self.always_apply = bool(brightness_by_max), float(p), bool(always_apply)
 
 
+class HueSaturationValue(_Op):
+    def __init__(self, hue_shift_limit=20, sat_shift_limit=30, val_shift_limit=20, always_apply=False, p=0.5):
+        self.hue_shift_limit = _to_tuple(hue_shift_limit)
+        self.sat_shift_limit = _to_tuple(sat_shift_limit)
+        self.val_shift_limit = _to_tuple(val_shift_limit)
+        self.p, self.always_apply = float(p), bool(always_apply)
+
+
+_CV2_HSV_LANES: Optional[int] = None
+
+
+def cv2_hsv_simd_lanes() -> int:
+    """How many pixels per step cv2's vectorised 8-bit HSV2RGB body handles on THIS host (16 / 32 / 64; 0 if it has no
+    vector body).  OpenCV truncates ``x * 255`` there but rounds to nearest in the scalar tail of each row, so
+    ``A.HueSaturationValue`` output depends on it; K1 reproduces the host it runs next to.  Probed once from cv2
+    itself (a 1 x 256 strip against the same pixels fed one per row); 32 (AVX2) when cv2 is not importable."""
+    global _CV2_HSV_LANES
+    if _CV2_HSV_LANES is None:
+        try:
+            import cv2
+            rng = np.random.default_rng(0)
+            strip = np.stack([rng.integers(0, 180, 255), rng.integers(1, 256, 255), rng.integers(1, 256, 255)],
+                             -1).astype(np.uint8).reshape(1, 255, 3)
+            wide = cv2.cvtColor(strip, cv2.COLOR_HSV2RGB)[0]
+            tall = cv2.cvtColor(strip.reshape(255, 1, 3), cv2.COLOR_HSV2RGB)[:, 0]
+            diff = np.nonzero((wide != tall).any(-1))[0]
+            lanes = 0
+            if diff.size:   # the body covers columns [0, (255 // lanes) * lanes): the largest power of two explaining it
+                for cand in (64, 32, 16, 8):
+                    if diff.max() < (255 // cand) * cand and diff.max() >= (255 // cand) * cand - cand:
+                        lanes = cand
+                        break
+            _CV2_HSV_LANES = lanes
+        except Exception:
+            _CV2_HSV_LANES = 32
+    return _CV2_HSV_LANES
+
+
+def hsv_luts(hue_shift: float, sat_shift: float, val_shift: float) -> np.ndarray:
+    """uint8 [3, 256]: the hue / sat / val tables of albumentations 1.3 ``_shift_hsv_uint8`` (an int16 ramp plus the
+    float shift, ``mod 180`` for hue / ``clip(0, 255)`` for the others, truncated to uint8); a zero shift leaves the
+    identity, as the original skips that LUT."""
+    ramp = np.arange(0, 256, dtype=np.int16)
+    out = np.tile(np.arange(256, dtype=np.uint8), (3, 1))
+    if hue_shift != 0:
+        out[0] = np.mod(ramp + hue_shift, 180).astype(np.uint8)
+    if sat_shift != 0:
+        out[1] = np.clip(ramp + sat_shift, 0, 255).astype(np.uint8)
+    if val_shift != 0:
+        out[2] = np.clip(ramp + val_shift, 0, 255).astype(np.uint8)
+    return out
+
+
 class CoarseDropout(_Op):
     def __init__(self, max_holes=8, max_height=8, max_width=8, min_holes=None, min_height=None, min_width=None,
                  fill_value=0, mask_fill_value=None, always_apply=False, p=0.5):
@@ -116,20 +170,24 @@ class Compose(_Op):
 
 
 MAX_HOLES = 16   # K1_AUG_MAX_HOLES
-AUG_HFLIP, AUG_VFLIP, AUG_BC = 1, 2, 4
+AUG_HFLIP, AUG_VFLIP, AUG_BC, AUG_HSV = 1, 2, 4, 8
 
 
 @dataclass(frozen=True)
 class AugmentSpec:
     """The random train-time ops K1 fuses, in the order the pipeline lists them (= the order their parameters are
     drawn in).  ``order`` holds op names out of {"HorizontalFlip", "VerticalFlip", "RandomBrightnessContrast",
-    "CoarseDropout"}."""
+    "HueSaturationValue", "CoarseDropout"}."""
     order: Tuple[str, ...] = ()
     hflip_p: float = 0.0
     vflip_p: float = 0.0
     bc_p: float = 0.0
     brightness_limit: Tuple[float, float] = (0.0, 0.0)
     contrast_limit: Tuple[float, float] = (0.0, 0.0)
+    hsv_p: float = 0.0
+    hue_limit: Tuple[float, float] = (0.0, 0.0)
+    sat_limit: Tuple[float, float] = (0.0, 0.0)
+    val_limit: Tuple[float, float] = (0.0, 0.0)
     cd_p: float = 0.0
     holes: Tuple[int, int] = (1, 1)                    # min_holes, max_holes
     hole_h: Tuple[Any, Any] = (8, 8)                   # min_height, max_height (both int, or both float fractions)
@@ -146,6 +204,9 @@ class AugmentBatch:
     holes: np.ndarray       # int32 [n, max_holes, 4]
     fill: Tuple[int, int, int]
     brightness: np.ndarray  # float64 [n], the raw draw (the oracle re-derives beta * 255 from it)
+    hsv_shift: Optional[np.ndarray] = None   # float64 [n, 3] raw hue / sat / val draws (None: op not in the pipeline)
+    hsv_lut: Optional[np.ndarray] = None     # uint8 [n, 3, 256] the tables built from them
+    hsv_trunc_cols: int = 0                  # output columns that take cv2's vectorised (truncating) HSV2RGB rounding
 
     @property
     def max_holes(self) -> int:
@@ -165,6 +226,9 @@ def draw_augmentations(spec: AugmentSpec, n: int, out_h: int, out_w: int, rng=No
     beta = np.zeros(n, dtype=np.float32)
     bright = np.zeros(n, dtype=np.float64)
     holes = np.zeros((n, max_holes, 4), dtype=np.int32)
+    has_hsv = "HueSaturationValue" in spec.order
+    hsv_shift = np.zeros((n, 3), dtype=np.float64) if has_hsv else None
+    hsv_lut = np.tile(np.arange(256, dtype=np.uint8), (n, 3, 1)) if has_hsv else None
     for i in range(n):
         f = 0
         for name in spec.order:
@@ -182,6 +246,15 @@ def draw_augmentations(spec: AugmentSpec, n: int, out_h: int, out_w: int, rng=No
                     alpha[i] = np.float32(a)          # `lut *= alpha`: python float enters a float32 multiply
                     beta[i] = np.float32(b * 255)     # `lut += beta * max_value`: double product, float32 add
                     bright[i] = b
+            elif name == "HueSaturationValue":
+                if rng.random() < spec.hsv_p:
+                    hs = rng.uniform(spec.hue_limit[0], spec.hue_limit[1])
+                    ss = rng.uniform(spec.sat_limit[0], spec.sat_limit[1])
+                    vs = rng.uniform(spec.val_limit[0], spec.val_limit[1])
+                    hsv_shift[i] = (hs, ss, vs)
+                    if hs != 0 or ss != 0 or vs != 0:    # `shift_hsv` returns the image untouched for all-zero shifts
+                        f |= AUG_HSV
+                        hsv_lut[i] = hsv_luts(hs, ss, vs)
             elif name == "CoarseDropout":
                 if rng.random() < spec.cd_p:
                     k = rng.randint(spec.holes[0], spec.holes[1])
@@ -197,7 +270,9 @@ def draw_augmentations(spec: AugmentSpec, n: int, out_h: int, out_w: int, rng=No
                         holes[i, h] = (x1, y1, x1 + hw, y1 + hh)
                     f |= k << 8
         flags[i] = f
-    return AugmentBatch(flags, alpha, beta, holes, spec.fill, bright)
+    lanes = cv2_hsv_simd_lanes() if has_hsv else 0
+    return AugmentBatch(flags, alpha, beta, holes, spec.fill, bright, hsv_shift, hsv_lut,
+                        (out_w // lanes) * lanes if lanes else 0)
 
 
 @dataclass(frozen=True)
@@ -249,7 +324,7 @@ def _as_int_triplet(value) -> Tuple[int, int, int]:
     return (v[0], v[1], v[2])
 
 
-_AUG_KINDS = ("HorizontalFlip", "VerticalFlip", "RandomBrightnessContrast", "CoarseDropout")
+_AUG_KINDS = ("HorizontalFlip", "VerticalFlip", "RandomBrightnessContrast", "HueSaturationValue", "CoarseDropout")
 
 
 def _prob(op) -> float:
@@ -285,6 +360,11 @@ def _compile_augment(aug_ops) -> Optional[AugmentSpec]:
             kw["bc_p"] = _prob(op)
             kw["brightness_limit"] = _to_tuple(op.brightness_limit)
             kw["contrast_limit"] = _to_tuple(op.contrast_limit)
+        elif k == "HueSaturationValue":
+            kw["hsv_p"] = _prob(op)
+            kw["hue_limit"] = _to_tuple(op.hue_shift_limit)
+            kw["sat_limit"] = _to_tuple(op.sat_shift_limit)
+            kw["val_limit"] = _to_tuple(op.val_shift_limit)
         elif k == "CoarseDropout":
             if getattr(op, "mask_fill_value", None) is not None:
                 raise NotImplementedError("CoarseDropout(mask_fill_value=...) is not supported (no masks on this path)")
@@ -319,6 +399,9 @@ def compile_pipeline(pipeline, channel_swap: bool = False) -> PreprocessPlan:
                 raise NotImplementedError(f"{k} must sit between the geometry ops and Normalize")
             if any(_kind(a) == k for a in aug_ops):
                 raise NotImplementedError(f"{k} listed twice")
+            if k == "RandomBrightnessContrast" and any(_kind(a) == "HueSaturationValue" for a in aug_ops):
+                raise NotImplementedError("RandomBrightnessContrast after HueSaturationValue: the fused kernel applies "
+                                          "brightness/contrast first (the order of the reference's configs)")
             if any(_kind(a) == "CoarseDropout" for a in aug_ops):
                 raise NotImplementedError("CoarseDropout must be the last fused augmentation (its fill is not "
                                           "flipped or re-coloured)")
@@ -338,7 +421,7 @@ def compile_pipeline(pipeline, channel_swap: bool = False) -> PreprocessPlan:
             raise NotImplementedError(
                 f"pipeline op {op!r} is outside the fused subset "
                 "{Resize | LongestMaxSize+PadIfNeeded, [HorizontalFlip, VerticalFlip, RandomBrightnessContrast, "
-                "CoarseDropout], Normalize, ToTensorV2}"
+                "HueSaturationValue, CoarseDropout], Normalize, ToTensorV2}"
             )
         if norm is not None and k in ("Resize", "LongestMaxSize", "PadIfNeeded"):
             raise NotImplementedError("geometry ops must precede Normalize")

@@ -237,6 +237,7 @@ class AugSample:
     beta: float = 0.0                # brightness draw (fraction of max_value: brightness_by_max=True)
     holes: Sequence[Tuple[int, int, int, int]] = ()   # CoarseDropout (x1, y1, x2, y2), ends exclusive
     fill: Tuple[int, int, int] = (0, 0, 0)
+    hsv: Optional[Tuple[float, float, float]] = None  # HueSaturationValue (hue, sat, val) shifts; None = not applied
 
 
 def brightness_contrast_lut(alpha: float, beta: float) -> np.ndarray:
@@ -251,10 +252,88 @@ def brightness_contrast_lut(alpha: float, beta: float) -> np.ndarray:
     return np.clip(lut, 0, 255).astype(np.uint8)
 
 
+def shift_hsv_u8(img: np.ndarray, hue_shift: float, sat_shift: float, val_shift: float) -> np.ndarray:
+    """albumentations 1.3 ``shift_hsv`` / ``_shift_hsv_uint8`` for a 3-channel uint8 RGB image, verbatim:
+    untouched for all-zero shifts, else cv2 RGB2HSV, one cv2.LUT per non-zero shift (int16 ramp + float shift,
+    ``mod 180`` / ``clip``, truncated), cv2 HSV2RGB."""
+    import cv2
+
+    if hue_shift == 0 and sat_shift == 0 and val_shift == 0:
+        return img
+    dtype = img.dtype
+    img = cv2.cvtColor(np.ascontiguousarray(img), cv2.COLOR_RGB2HSV)
+    hue, sat, val = cv2.split(img)
+    if hue_shift != 0:
+        lut_hue = np.arange(0, 256, dtype=np.int16)
+        lut_hue = np.mod(lut_hue + hue_shift, 180).astype(dtype)
+        hue = cv2.LUT(hue, lut_hue)
+    if sat_shift != 0:
+        lut_sat = np.arange(0, 256, dtype=np.int16)
+        lut_sat = np.clip(lut_sat + sat_shift, 0, 255).astype(dtype)
+        sat = cv2.LUT(sat, lut_sat)
+    if val_shift != 0:
+        lut_val = np.arange(0, 256, dtype=np.int16)
+        lut_val = np.clip(lut_val + val_shift, 0, 255).astype(dtype)
+        val = cv2.LUT(val, lut_val)
+    img = cv2.merge((hue, sat, val)).astype(dtype)
+    return cv2.cvtColor(img, cv2.COLOR_HSV2RGB)
+
+
+def rgb2hsv_int(rgb: np.ndarray) -> np.ndarray:
+    """Independent integer restatement of OpenCV's 8-bit RGB2HSV (hsv_shift = 12, hrange 180), uint8 [..., 3]."""
+    x = np.asarray(rgb).astype(np.int64)
+    r, g, b = x[..., 0], x[..., 1], x[..., 2]
+    i = np.arange(1, 256, dtype=np.float64)
+    sdiv = np.concatenate([[0], np.rint((255 << 12) / (1.0 * i))]).astype(np.int64)
+    hdiv = np.concatenate([[0], np.rint((180 << 12) / (6.0 * i))]).astype(np.int64)
+    v = np.maximum(np.maximum(r, g), b)
+    diff = v - np.minimum(np.minimum(r, g), b)
+    s = (diff * sdiv[v] + (1 << 11)) >> 12
+    h = np.where(v == r, g - b, np.where(v == g, b - r + 2 * diff, r - g + 4 * diff))
+    h = (h * hdiv[diff] + (1 << 11)) >> 12
+    h = np.where(h < 0, h + 180, h)
+    return np.stack([h, s, v], -1).astype(np.uint8)
+
+
+def hsv2rgb_f32(hsv: np.ndarray, trunc: bool = False) -> np.ndarray:
+    """Restatement of OpenCV's 8-bit HSV2RGB (float path, hue < 180): s, v scaled by 1/255, h by 6/180, sector =
+    trunc, tab1 = v(1 - s), tab2 = v * fma(-s, f, 1), tab3 = v * fma(-s, 1 - f, 1), then x * 255 -> uint8 by
+    round-to-nearest-even (OpenCV's scalar code: the tail of each row) or, ``trunc=True``, by truncation (its
+    vectorised body: the first (W / lanes) * lanes pixels of each row).  The two fma's are how OpenCV's build
+    contracts ``1 - s*f``; formulas and both roundings were found by exhaustive comparison with cv2 4.13 over all
+    180 * 2^16 inputs (tests/test_transforms.py repeats it).  fma is emulated in float64 (exact product, one extra
+    rounding that the exhaustive check shows never matters on this domain)."""
+    f32 = np.float32
+    x = np.asarray(hsv)
+    h, s, v = (x[..., k].astype(np.float32) for k in range(3))
+    s = s * f32(1.0 / 255.0)
+    v = v * f32(1.0 / 255.0)
+    h = h * (f32(6.0) / f32(180.0))
+    pre = np.trunc(h)
+    fr = (h - pre).astype(np.float32)
+    sector = pre.astype(np.int64) % 6
+
+    def fma(a, b_, c):
+        return (a.astype(np.float64) * b_.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
+
+    one = np.ones_like(s)
+    t0 = v
+    t1 = (v * (one - s)).astype(np.float32)
+    t2 = (v * fma(-s, fr, one)).astype(np.float32)
+    t3 = (v * fma(-s, (one - fr).astype(np.float32), one)).astype(np.float32)
+    tab = np.stack([t0, t1, t2, t3], 0)
+    sd = np.array([[1, 3, 0], [1, 0, 2], [3, 0, 1], [0, 2, 1], [0, 1, 3], [2, 1, 0]])
+    pick = lambda k: np.take_along_axis(tab, sd[sector, k][None], 0)[0]
+    bb, gg, rr = pick(0), pick(1), pick(2)
+    rnd = np.trunc if trunc else np.rint
+    sat = lambda t: np.clip(rnd((t * f32(255.0)).astype(np.float32)), 0, 255).astype(np.uint8)
+    return np.stack([sat(rr), sat(gg), sat(bb)], -1)
+
+
 def augment_u8(img: np.ndarray, a: "AugSample") -> np.ndarray:
     """The deterministic part of the train pipeline on the resized / padded uint8 HWC image, in Compose order:
     HorizontalFlip (cv2.flip(img, 1)), VerticalFlip (cv2.flip(img, 0)), RandomBrightnessContrast (cv2.LUT),
-    CoarseDropout (``img[y1:y2, x1:x2] = fill_value`` per hole)."""
+    HueSaturationValue (shift_hsv_u8), CoarseDropout (``img[y1:y2, x1:x2] = fill_value`` per hole)."""
     import cv2
 
     out = np.ascontiguousarray(img)
@@ -264,6 +343,8 @@ def augment_u8(img: np.ndarray, a: "AugSample") -> np.ndarray:
         out = cv2.flip(out, 0)
     if a.bc:
         out = cv2.LUT(out, brightness_contrast_lut(a.alpha, a.beta))
+    if a.hsv is not None:
+        out = shift_hsv_u8(out, *a.hsv)
     if len(a.holes):
         out = out.copy()
         for x1, y1, x2, y2 in a.holes:

@@ -195,7 +195,7 @@ def test_loader_prefetch_ring_matches_inline(cuda_device, tmp_path):
 
 def test_train_loader_with_fused_augmentations(cuda_device, tmp_path):
     """get_dataset(train_data, train_pipeline) with the reference's train-time ops (configs/singletask_config.py:
-    162-201 minus HueSaturationValue): the loader draws per-sample parameters from its rng and K1 applies them;
+    162-201, all of them): the loader draws per-sample parameters from its rng and K1 applies them;
     replaying the same random stream through the oracle (cv2.flip / cv2.LUT / slice fill) gives the same bits."""
     import random
     import cv2
@@ -205,6 +205,7 @@ def test_train_loader_with_fused_augmentations(cuda_device, tmp_path):
                       T.PadIfNeeded(32, 32, always_apply=True, border_mode=T.BORDER_CONSTANT, value=0),
                       T.HorizontalFlip(p=0.5), T.VerticalFlip(p=0.5),
                       T.RandomBrightnessContrast(brightness_limit=(-0.2, 0.2), contrast_limit=(0.1, -0.5), p=0.5),
+                      T.HueSaturationValue(hue_shift_limit=0, sat_shift_limit=10, val_shift_limit=50, p=0.5),
                       T.CoarseDropout(max_holes=4, min_holes=1, max_height=0.2, min_height=0.05, max_width=0.2,
                                       min_width=0.05, fill_value=[0, 0.5, 1], p=0.5),
                       T.Normalize(mean=MEAN, std=STD), T.ToTensorV2()])
@@ -225,7 +226,7 @@ def test_train_loader_with_fused_augmentations(cuda_device, tmp_path):
             f = int(b.flags[k])
             a = opre.AugSample(hflip=bool(f & 1), vflip=bool(f & 2), bc=bool(f & 4), alpha=float(b.alpha[k]),
                                beta=float(b.brightness[k]), holes=[tuple(int(v) for v in h) for h in b.holes[k, :f >> 8]],
-                               fill=b.fill)
+                               fill=b.fill, hsv=tuple(float(v) for v in b.hsv_shift[k]) if (f & 8) else None)
             changed += int(f != 0)
             img = cv2.cvtColor(cv2.imread(str(tmp_path / r["path"])), cv2.COLOR_BGR2RGB)
             exp.append(opre.preprocess_crop(img, (0, 0, img.shape[1], img.shape[0]), plan, "cv2", aug=a)[1])

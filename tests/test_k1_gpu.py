@@ -295,9 +295,10 @@ def _aug_samples(batch):
     for i in range(len(batch.flags)):
         f = int(batch.flags[i])
         k = f >> 8
+        hsv = tuple(float(v) for v in batch.hsv_shift[i]) if (f & 8) else None
         out.append(opre.AugSample(hflip=bool(f & 1), vflip=bool(f & 2), bc=bool(f & 4), alpha=float(batch.alpha[i]),
                                   beta=float(batch.brightness[i]), holes=[tuple(int(v) for v in h) for h in batch.holes[i, :k]],
-                                  fill=batch.fill))
+                                  fill=batch.fill, hsv=hsv))
     return out
 
 
@@ -308,8 +309,9 @@ def _aug_samples(batch):
     dict(out_h=100, out_w=60),                                     # partial column tile + flips
 ])
 def test_k1_train_pipeline_augmentations_vs_oracle(cuda_device, kw):
-    """flips + brightness/contrast LUT + CoarseDropout fused into K1 with GIVEN per-sample parameters
-    == cv2.flip / cv2.LUT / slice-assign on the oracle's resized image: uint8 bit-exact, fp32 bit-exact, bf16 = RNE."""
+    """flips + brightness/contrast LUT + HueSaturationValue + CoarseDropout (the whole train pipeline of
+    configs/singletask_config.py:162-201) fused into K1 with GIVEN per-sample parameters == cv2.flip / cv2.LUT /
+    cv2.cvtColor round trip / slice-assign on the oracle's resized image: uint8 bit-exact, fp32 bit-exact, bf16 = RNE."""
     import random
     from nkb_classification_b200 import transforms as T
     rng = np.random.default_rng(17)
@@ -326,11 +328,13 @@ def test_k1_train_pipeline_augmentations_vs_oracle(cuda_device, kw):
     plan = T.compile_pipeline(geo + [
         T.HorizontalFlip(p=0.5), T.VerticalFlip(p=0.5),
         T.RandomBrightnessContrast(brightness_limit=(-0.2, 0.2), contrast_limit=(0.1, -0.5), p=0.6),
+        T.HueSaturationValue(hue_shift_limit=(0 if kw.get("mode") == "letterbox" else 20), sat_shift_limit=10,
+                             val_shift_limit=50, p=0.6),
         T.CoarseDropout(max_holes=4, min_holes=1, max_height=0.2, min_height=0.05, max_width=0.2, min_width=0.05,
                         fill_value=[0, 0.5, 1], p=0.6),
         T.Normalize(MEAN, STD), T.ToTensorV2()], channel_swap=base.channel_swap)
     batch = plan.draw(len(boxes), random.Random(99))
-    assert len({int(f) & 7 for f in batch.flags}) == 8, "the draw should cover every flip / LUT combination"
+    assert len({int(f) & 15 for f in batch.flags}) == 16, "the draw should cover every flip / LUT / HSV combination"
     out, u8 = run_k1(cuda_device, frames, boxes, fidx, plan, aug=batch)
     eu8, ef32 = opre.preprocess_batch(frames, boxes, fidx, oracle_plan(plan), impl="cv2", augs=_aug_samples(batch))
     assert np.array_equal(u8.cpu().numpy(), eu8)

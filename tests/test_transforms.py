@@ -48,7 +48,8 @@ def test_duck_typed_albumentations_objects():
     [T.LongestMaxSize(16), T.PadIfNeeded(8, 8, border_mode=0), T.Normalize(), T.ToTensorV2()],
     [T.Resize(8, 8, interpolation=2), T.Normalize(), T.ToTensorV2()],            # cubic
     [type("HorizontalFlip", (), {})(), T.Resize(8, 8), T.Normalize(), T.ToTensorV2()],  # before the geometry
-    [T.Resize(8, 8), type("HueSaturationValue", (), {})(), T.Normalize(), T.ToTensorV2()],  # not fused (stays on CPU)
+    [T.Resize(8, 8), type("RandomShadow", (), {})(), T.Normalize(), T.ToTensorV2()],  # not fused (stays on CPU)
+    [T.Resize(8, 8), T.HueSaturationValue(), T.RandomBrightnessContrast(), T.Normalize(), T.ToTensorV2()],  # order
     [T.Resize(8, 8), type("MotionBlur", (), {})(), T.Normalize(), T.ToTensorV2()],
     [T.Resize(8, 8), T.Normalize(), T.HorizontalFlip(), T.ToTensorV2()],               # after Normalize
     [T.Resize(8, 8), T.CoarseDropout(), T.HorizontalFlip(), T.Normalize(), T.ToTensorV2()],  # dropout must be last
@@ -69,6 +70,7 @@ def reference_train_ops(size=128):
         T.HorizontalFlip(p=0.5),
         T.VerticalFlip(p=0.5),
         T.RandomBrightnessContrast(brightness_limit=(-0.2, 0.2), contrast_limit=(0.1, -0.5), p=0.5),
+        T.HueSaturationValue(hue_shift_limit=0, sat_shift_limit=10, val_shift_limit=50, p=0.5),
         T.CoarseDropout(max_holes=4, min_holes=1, max_height=0.2, min_height=0.05, max_width=0.2, min_width=0.05,
                         fill_value=[0, 0.5, 1], p=0.5),
         T.Normalize(mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)),
@@ -77,10 +79,13 @@ def reference_train_ops(size=128):
 
 
 def test_compile_train_pipeline_of_the_reference_config():
+    """configs/singletask_config.py:162-201, every op of it."""
     p = T.compile_pipeline(T.Compose(reference_train_ops()))
     a = p.augment
-    assert a.order == ("HorizontalFlip", "VerticalFlip", "RandomBrightnessContrast", "CoarseDropout")
-    assert (a.hflip_p, a.vflip_p, a.bc_p, a.cd_p) == (0.5, 0.5, 0.5, 0.5)
+    assert a.order == ("HorizontalFlip", "VerticalFlip", "RandomBrightnessContrast", "HueSaturationValue",
+                       "CoarseDropout")
+    assert (a.hflip_p, a.vflip_p, a.bc_p, a.hsv_p, a.cd_p) == (0.5, 0.5, 0.5, 0.5, 0.5)
+    assert (a.hue_limit, a.sat_limit, a.val_limit) == ((0.0, 0.0), (-10.0, 10.0), (-50.0, 50.0))
     assert a.contrast_limit == (0.1, -0.5)          # kept as given, not sorted (albumentations 1.3 to_tuple)
     assert a.holes == (1, 4) and a.hole_h == (0.05, 0.2)
     assert a.fill == (0, 0, 1)                      # what `img[...] = [0, 0.5, 1]` stores into uint8
@@ -109,6 +114,12 @@ def test_draw_follows_compose_call_order():
             beta = 0.0 + r.uniform(-0.2, 0.2)
             assert b.alpha[i] == np.float32(alpha) and b.beta[i] == np.float32(beta * 255)
             assert 0.5 <= alpha <= 1.1 and -0.2 <= beta <= 0.2
+        hsv = r.random() < 0.5
+        if hsv:
+            shifts = (r.uniform(-0.0, 0.0), r.uniform(-10.0, 10.0), r.uniform(-50.0, 50.0))
+            assert tuple(b.hsv_shift[i]) == shifts and shifts[0] == 0
+            assert np.array_equal(b.hsv_lut[i], T.hsv_luts(*shifts))
+            assert np.array_equal(b.hsv_lut[i][0], np.arange(256, dtype=np.uint8))     # zero hue shift: identity table
         holes = []
         if r.random() < 0.5:
             for _ in range(r.randint(1, 4)):
@@ -116,7 +127,7 @@ def test_draw_follows_compose_call_order():
                 y1 = r.randint(0, 64 - hh)
                 x1 = r.randint(0, 64 - hw)
                 holes.append((x1, y1, x1 + hw, y1 + hh))
-        assert b.flags[i] == (int(hf) | 2 * int(vf) | 4 * int(bc) | len(holes) << 8)
+        assert b.flags[i] == (int(hf) | 2 * int(vf) | 4 * int(bc) | 8 * int(hsv) | len(holes) << 8)
         assert [tuple(h) for h in b.holes[i, :len(holes)]] == holes
     assert 60 < int((b.flags & 1).sum()) < 140 and 60 < int((b.flags >> 2 & 1).sum()) < 140
     assert T.compile_pipeline([T.Resize(8, 8), T.Normalize(), T.ToTensorV2()]).draw(5) is None
@@ -146,3 +157,47 @@ def test_oracle_augment_is_cv2_and_numpy():
     exp[4:11, 3:9] = (0, 0, 1)
     assert np.array_equal(out, exp)
     assert np.array_equal(opre.augment_u8(img, opre.AugSample()), img)
+
+
+def test_hsv_restatements_match_cv2_exhaustively():
+    """Pins the colour-space restatements to cv2 on their ENTIRE domains: RGB2HSV (fixed point) over all 2^24 RGB
+    triples; HSV2RGB (float path with OpenCV's fma contraction) over all 180 * 2^16 HSV triples, in BOTH of cv2's
+    roundings: one pixel per row exercises its scalar code (round to nearest even), 65536-pixel rows its vectorised
+    body (truncation)."""
+    import cv2
+    g = np.arange(256, dtype=np.uint8)
+    rgb = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 1, 3)
+    assert np.array_equal(opre.rgb2hsv_int(rgb), cv2.cvtColor(rgb, cv2.COLOR_RGB2HSV))
+    hsv = np.stack(np.meshgrid(np.arange(180, dtype=np.uint8), g, g, indexing="ij"), -1).reshape(180, 65536, 3)
+    assert np.array_equal(opre.hsv2rgb_f32(hsv.reshape(-1, 1, 3)), cv2.cvtColor(hsv.reshape(-1, 1, 3), cv2.COLOR_HSV2RGB))
+    if T.cv2_hsv_simd_lanes():
+        assert np.array_equal(opre.hsv2rgb_f32(hsv, trunc=True), cv2.cvtColor(hsv, cv2.COLOR_HSV2RGB))
+
+
+def test_hsv_pixel_function_matches_albumentations_oracle(nkbk_lib):
+    """K1's HueSaturationValue pixel function (the same source compiled for the host) == albumentations'
+    `_shift_hsv_uint8` executed verbatim with cv2, on every RGB triple, for shifts of the reference config's range
+    and for hue shifts, in both roundings; all-zero shifts leave the image untouched (flag not set by the draw)."""
+    from nkb_classification_b200 import ops
+    g = np.arange(256, dtype=np.uint8)
+    rgb = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(4096, 4096, 3)
+    lanes = T.cv2_hsv_simd_lanes()
+    assert lanes in (0, 16, 32, 64)
+    for shifts in [(0.0, 7.3, -31.2), (12.5, -9.99, 49.9), (-170.25, 0.0, 0.0)]:
+        lut = T.hsv_luts(*shifts)
+        tall = rgb.reshape(-1, 1, 3)                       # one pixel per row: cv2's scalar rounding
+        assert np.array_equal(ops.debug_hsv_shift(tall, lut, False), opre.shift_hsv_u8(tall, *shifts)), shifts
+        if lanes:                                          # 4096-pixel rows: cv2's vectorised rounding everywhere
+            assert np.array_equal(ops.debug_hsv_shift(rgb, lut, True), opre.shift_hsv_u8(rgb, *shifts)), shifts
+    assert opre.shift_hsv_u8(rgb, 0, 0, 0) is rgb
+    assert np.array_equal(T.hsv_luts(0, 0, 0), np.tile(g, (3, 1)))
+    # a row that is not a multiple of the vector width: body truncates, tail rounds -- the rule K1 is given
+    rng = np.random.default_rng(4)
+    img = rng.integers(0, 256, (9, 100, 3), dtype=np.uint8)
+    lut = T.hsv_luts(3.3, 4.4, -20.2)
+    tc = (100 // lanes) * lanes if lanes else 0
+    emu = np.concatenate([ops.debug_hsv_shift(np.ascontiguousarray(img[:, :tc]), lut, True),
+                          ops.debug_hsv_shift(np.ascontiguousarray(img[:, tc:]), lut, False)], 1)
+    assert np.array_equal(emu, opre.shift_hsv_u8(img, 3.3, 4.4, -20.2))
+    b = T.compile_pipeline(reference_train_ops(100)).draw(3, __import__("random").Random(0))
+    assert b.hsv_trunc_cols == tc
