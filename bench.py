@@ -217,6 +217,15 @@ def run_b200(args, wl):
         raise RuntimeError("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if world > 1:
+        # N ranks pull 398 MB of pinned frames per step each: keep every rank (and the pinned pages it first-touches)
+        # on the CPU socket its GPU hangs off, otherwise the e2e leg crosses the inter-socket link
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        except Exception:
+            pass
     comm = Communicator()
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")

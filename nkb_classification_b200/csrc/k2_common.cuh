@@ -6,10 +6,8 @@ namespace nkbk {
 
 constexpr int K2_MAX_TASKS = 64;
 constexpr int K2_MAX_NC = 1024;
-constexpr int K2_FWD_WARPS = 4;
 constexpr int K2_FWD_ROWS = 4;     // rows per CTA
 constexpr int K2_FWD_NCB = 16;     // classes per pass
-constexpr int K2_FWD_ROUND = 2;    // K chunks per warp whose loads are issued together
 constexpr int K2_V3_WARPS = 4;     // forward v3: warps per CTA, each owning K2_FWD_ROWS rows over the full K
 constexpr int K2_V3_PD = 4;        // forward v3: 128-column chunks of embedding loads in flight per warp
 constexpr int K2_DW_WARPS = 4;

@@ -13,7 +13,6 @@
 //                      the logits in the warp's private shared-memory slice; per-(row,
 //                      task) lanes then do softmax / loss / dlogits and the fused K3
 //                      (argmax + confusion counts).  No cross-warp reduction.
-//   k2_heads_forward   (previous version, kept for reference: CTA = 4 rows, warps split K)
 //   k2_heads_dw        CTA = 128 rows x 128 columns, 4 warps x 32 rows, thread =
 //                      4 columns x NCP classes in registers, dlogits broadcast
 //                      from shared memory; fixed-order cross-warp tree; the last
@@ -174,87 +173,6 @@ __device__ __forceinline__ void heads_row_epilogue(const K2FwdParams& p, const f
         for (int r = 0; r < K2_FWD_ROWS; ++r) s += lt[r * 2 * T + i];
         lp[i] = s;
     }
-}
-
-template <typename ET>
-__global__ void __launch_bounds__(K2_FWD_WARPS * 32) k2_heads_forward(const K2FwdParams p) {
-    extern __shared__ float smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int T = p.seg.T, NC = p.NC, D = p.D;
-    float* zs = smem;                                   // [ROWS][NC] logits
-    float* ls = zs + K2_FWD_ROWS * NC;                  // epilogue scratch, ROWS * (NC + 6T)
-    float* part = ls + K2_FWD_ROWS * (NC + 6 * T);      // [WARPS][64] per-warp partial logits
-    const int row0 = blockIdx.x * K2_FWD_ROWS;
-    const ET* emb = static_cast<const ET*>(p.emb);
-    if (blockIdx.x == 0)
-        for (int i = threadIdx.x; i < p.n_counters; i += blockDim.x) p.counters[i] = 0u;
-
-    const int nchunks = (D + 127) / 128;
-    for (int cb = 0; cb < NC; cb += K2_FWD_NCB) {
-        float acc[K2_FWD_ROWS * K2_FWD_NCB];
-#pragma unroll
-        for (int i = 0; i < K2_FWD_ROWS * K2_FWD_NCB; ++i) acc[i] = 0.f;
-        for (int c0 = warp; c0 < nchunks; c0 += K2_FWD_WARPS * K2_FWD_ROUND) {
-            float4 e[K2_FWD_ROUND][K2_FWD_ROWS];
-#pragma unroll
-            for (int u = 0; u < K2_FWD_ROUND; ++u) {
-                const int k = (c0 + u * K2_FWD_WARPS) * 128 + lane * 4;
-#pragma unroll
-                for (int r = 0; r < K2_FWD_ROWS; ++r) {
-                    const int row = min(row0 + r, p.B - 1);  // tail rows recompute the last row, never stored
-                    e[u][r] = k < D ? ld4(emb + (int64_t)row * D + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < K2_FWD_ROUND; ++u) {
-                const int k = (c0 + u * K2_FWD_WARPS) * 128 + lane * 4;
-                if (k < D) {
-#pragma unroll
-                    for (int ch = 0; ch < K2_FWD_NCB; ch += 8) {
-                        if (cb + ch >= NC) break;  // warp-uniform
-                        float4 w[8];
-#pragma unroll
-                        for (int c = 0; c < 8; ++c)  // 8 weight loads in flight together
-                            w[c] = ld4(p.W + (int64_t)min(cb + ch + c, NC - 1) * D + k);
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            if (cb + ch + c < NC) {  // warp-uniform: padded classes skip their FFMAs
-#pragma unroll
-                                for (int r = 0; r < K2_FWD_ROWS; ++r) {
-                                    float a = acc[r * K2_FWD_NCB + ch + c];
-                                    a = fmaf(e[u][r].x, w[c].x, a);
-                                    a = fmaf(e[u][r].y, w[c].y, a);
-                                    a = fmaf(e[u][r].z, w[c].z, a);
-                                    a = fmaf(e[u][r].w, w[c].w, a);
-                                    acc[r * K2_FWD_NCB + ch + c] = a;
-                                }
-                            }
-                        }
-                    }
-                }
-            }
-        }
-        // 64 partial sums -> lane L owns entries L and 32+L  (entry = r*16 + c)
-        float lo[32], hi[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) { lo[i] = acc[i]; hi[i] = acc[32 + i]; }
-        part[warp * 64 + lane] = warp_reduce_scatter32(lo, lane);
-        part[warp * 64 + 32 + lane] = warp_reduce_scatter32(hi, lane);
-        __syncthreads();
-        if (threadIdx.x < 64) {
-            const int c = cb + (threadIdx.x & 15), r = threadIdx.x >> 4;
-            if (c < NC) {
-                float sum = part[threadIdx.x];
-#pragma unroll
-                for (int w = 1; w < K2_FWD_WARPS; ++w) sum += part[w * 64 + threadIdx.x];  // fixed order
-                zs[r * NC + c] = sum + __ldg(p.bias + c);
-            }
-        }
-        __syncthreads();
-    }
-    if (warp != 0) return;
-
-    heads_row_epilogue(p, zs, ls, row0, lane, p.loss_part + (int64_t)blockIdx.x * 2 * T);
 }
 
 // ---- forward v3: one warp = K2_FWD_ROWS rows over the whole K, no cross-warp reduction, K3 fused ----------------
