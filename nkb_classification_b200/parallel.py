@@ -84,13 +84,20 @@ class Communicator:
         if self.world > 1 and not dist.is_initialized():
             raise RuntimeError("torch.distributed must be initialised first (it carries the IPC handles)")
         hbuf = (ctypes.c_uint8 * IPC_HANDLE_BYTES)()
-        check(lib().nkbk_peer_init(self.rank, self.world, device.index or 0, int(max_f32), int(max_i64), hbuf))
-        ok = True
+        rc = lib().nkbk_peer_init(self.rank, self.world, device.index or 0, int(max_f32), int(max_i64), hbuf)
+        if self.world == 1:
+            check(rc)
+        ok = rc == 0
         if self.world > 1:
+            # every rank walks through both exchanges whatever happened locally (no IPC support in this container,
+            # no P2P path between the devices, ...), so that all of them reach the same decision without deadlock
             handles: List[Optional[bytes]] = [None] * self.world
-            dist.all_gather_object(handles, bytes(hbuf))
-            raw = (ctypes.c_uint8 * (IPC_HANDLE_BYTES * self.world)).from_buffer_copy(b"".join(handles))
-            ok = lib().nkbk_peer_connect(raw) == 0
+            dist.all_gather_object(handles, bytes(hbuf) if ok else None)
+            if all(h is not None for h in handles):
+                raw = (ctypes.c_uint8 * (IPC_HANDLE_BYTES * self.world)).from_buffer_copy(b"".join(handles))
+                ok = lib().nkbk_peer_connect(raw) == 0
+            else:
+                ok = False
             flags = [None] * self.world
             dist.all_gather_object(flags, ok)          # also the barrier nkbk_peer_connect asks for
             ok = all(flags)
