@@ -87,3 +87,28 @@ def test_sharded_sums_reassemble_global_result_gloo(tmp_path):
     world, port = 2, _free_port()
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / f"ok{r}").exists() for r in range(world))
+
+
+def _peer_fallback_worker(rank, world, port, out_dir):
+    """Without a CUDA device nkbk_peer_init fails on every rank: the collective set-up must still terminate on all
+    ranks with the same answer (False -> the caller keeps the NCCL transport), and must not be retried."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nkb_classification_b200 import _lib
+    from nkb_classification_b200.parallel import Communicator
+    comm = Communicator()
+    comm.rank, comm.world = rank, world
+    ok = comm.init_peer(torch.device("cuda", 0), 1000, 10)
+    assert ok is False and comm._peer_failed and not comm.peer_active
+    assert comm.init_peer(torch.device("cuda", 0), 1000, 10) is False      # no second collective round
+    assert _lib.lib().nkbk_peer_world() == 0
+    dist.barrier()
+    dist.destroy_process_group()
+    open(os.path.join(out_dir, f"peer_ok{rank}"), "w").write("ok")
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="exercises the no-CUDA fallback of the K4' set-up")
+def test_peer_setup_falls_back_collectively_gloo(tmp_path):
+    world, port = 2, _free_port()
+    mp.spawn(_peer_fallback_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"peer_ok{r}").exists() for r in range(world))
