@@ -11,7 +11,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libnkbk.so"
+LIB_PATH = Path(os.environ["NKBK_LIB_PATH"]) if os.environ.get("NKBK_LIB_PATH") else _PKG / "libnkbk.so"  # (A/B builds)
 
 NKBK_OK = 0
 NKBK_E_ARG, NKBK_E_SHAPE, NKBK_E_CUDA, NKBK_E_NCCL, NKBK_E_UNSUPPORTED = -1, -2, -3, -4, -5

@@ -110,15 +110,16 @@ __device__ __forceinline__ void k1_process_band(const K1Params& p, const int cro
     // bit j set: destination column of (lane, j) on destination row yd lies inside a CoarseDropout hole
     auto hole_mask = [&](int yd) -> uint32_t {
         uint32_t m = 0;
-        if (!AUG) return m;
-        for (int h = 0; h < nholes; ++h) {
-            const int x1 = __ldg(holes + 4 * h + 0), y1 = __ldg(holes + 4 * h + 1);
-            const int x2 = __ldg(holes + 4 * h + 2), y2 = __ldg(holes + 4 * h + 3);
-            if (yd < y1 || yd >= y2) continue;
+        if constexpr (AUG) {
+            for (int h = 0; h < nholes; ++h) {
+                const int x1 = __ldg(holes + 4 * h + 0), y1 = __ldg(holes + 4 * h + 1);
+                const int x2 = __ldg(holes + 4 * h + 2), y2 = __ldg(holes + 4 * h + 3);
+                if (yd < y1 || yd >= y2) continue;
 #pragma unroll
-            for (int j = 0; j < JMAX; ++j) {
-                const int xd = xd0 + xstep * j;
-                m |= uint32_t(xd >= x1 && xd < x2) << j;
+                for (int j = 0; j < JMAX; ++j) {
+                    const int xd = xd0 + xstep * j;
+                    m |= uint32_t(xd >= x1 && xd < x2) << j;
+                }
             }
         }
         return m;

@@ -105,8 +105,22 @@ class _FusedHeads(torch.autograd.Function):
         return (demb, None, None, None, *grads[: ctx.n_params])
 
 
-def pack_T(pack: HeadPack) -> int:
+def pack_T(pack) -> int:
     return len(pack.classes)
+
+
+class _TaskPack:
+    """One head of a HeadPack seen as a single-task pack (row slices of the packed buffers are contiguous)."""
+
+    def __init__(self, pack: HeadPack, t: int):
+        a, b = pack.seg[t], pack.seg[t + 1]
+        self.W_cat, self.b_cat = pack.W_cat[a:b], pack.b_cat[a:b]
+        self.D, self.classes, self.seg = pack.D, [b - a], [0, b - a]
+        self.names = None if pack.names is None else [pack.names[t]]
+        self._lin = pack.linears[t]
+
+    def params(self):
+        return [self._lin.weight, self._lin.bias]
 
 
 class FusedHeads:
@@ -155,13 +169,55 @@ class FusedHeads:
             self.pack.repack()
         labels = self.labels_tensor(target, emb.device)
         if train and self.model.training and max(self.pack.dropout_p) > 0.0:
-            # Documented deviation: one dropout mask shared by all heads instead of an independent
-            # mask per head (model.py:106).  Same marginal distribution per head; p = 0 / eval is exact.
-            emb = torch.nn.functional.dropout(emb, p=max(self.pack.dropout_p), training=True)
+            if pack_T(self.pack) > 1:
+                return self._per_head_dropout(emb, labels, train)
+            emb = torch.nn.functional.dropout(emb, p=self.pack.dropout_p[0], training=True)   # model.py:35
         loss = _FusedHeads.apply(emb, self.state, labels, train, *self.pack.params())
         bufs, pred = self.state["last"]
         return HeadsOutput(loss=loss, logits=bufs.logits, probs=bufs.probs, pred=pred, seg=self.pack.seg,
                            names=self.pack.names)
+
+    def _per_head_dropout(self, emb: torch.Tensor, labels: torch.Tensor, train: bool) -> HeadsOutput:
+        """Training with ``classifier_dropout > 0`` and several heads: every head applies its OWN ``nn.Dropout`` to
+        the shared embedding (model.py:102-116), so the heads see different inputs and cannot share one GEMM.  Each
+        head then runs as a single-task fused call on its own mask, drawn with ``F.dropout`` in ModuleDict order --
+        the very calls (and, without autocast, the very Philox stream) the reference makes.  Eval and p = 0 keep the
+        single segmented launch."""
+        pack, T = self.pack, pack_T(self.pack)
+        subs = self.state.setdefault("task_states", None)
+        if subs is None:
+            subs, off = [], 0
+            for t in range(T):
+                tp = _TaskPack(pack, t)
+                C = tp.classes[0]
+                cw = self.state["class_weight"]
+                st = dict(self.state)
+                st.update(pack=tp, bufs={}, last=None,
+                          class_weight=None if cw is None else cw[pack.seg[t]:pack.seg[t + 1]].contiguous(),
+                          cm=None if self.state["cm"] is None else self.state["cm"][off: off + C * C],
+                          cm_step=None if self.state["cm_step"] is None else self.state["cm_step"][off: off + C * C])
+                st.pop("task_states", None)
+                subs.append(st)
+                off += C * C
+            self.state["task_states"] = subs
+        losses, logits, probs, preds = [], [], [], []
+        for t in range(T):
+            st = subs[t]
+            if not pack.in_sync():
+                pack.repack()
+            emb_t = torch.nn.functional.dropout(emb, p=pack.dropout_p[t], training=True)
+            l = _FusedHeads.apply(emb_t, st, labels[:, t:t + 1].contiguous(), train, *st["pack"].params())
+            bufs, pred = st["last"]
+            losses.append(l[0])
+            logits.append(bufs.logits)
+            probs.append(bufs.probs)
+            preds.append(pred)
+        total = losses[0]
+        for l in losses[1:]:
+            total = total + l                                            # losses.py:140-147: unweighted sum
+        return HeadsOutput(loss=torch.stack(losses + [total]), logits=torch.cat(logits, 1),
+                           probs=None if probs[0] is None else torch.cat(probs, 1),
+                           pred=None if preds[0] is None else torch.cat(preds, 1), seg=pack.seg, names=pack.names)
 
     # epoch-level confusion counts (already summed over ranks)
     def reset_confusion(self):

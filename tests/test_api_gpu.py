@@ -170,6 +170,49 @@ def test_loader_yields_oracle_images(cuda_device, tmp_path):
     assert np.concatenate(tg).tolist() == [c2i[r["color"]] for r in rows]
 
 
+def test_per_head_dropout_matches_the_reference_call_sequence(cuda_device):
+    """Training with classifier_dropout > 0: every head draws its own mask from the shared embedding, in ModuleDict
+    order (model.py:102-116).  With the same torch seed the fused path consumes the RNG exactly like the reference
+    modules do, so logits, losses and all gradients agree with `classifier[t](emb)` + the oracle loss."""
+    from nkb_classification_b200 import heads, model as M
+    classes = {"color": ["a", "b", "c"], "size": ["s", "l"], "kind": ["x", "y", "z", "w"]}
+    net = M.get_model({"task": "multi", "model": TinyBackbone(), "pretrained": False, "backbone_dropout": 0.0,
+                       "classifier_dropout": 0.3, "classifier_initialization": "kaiming_normal_"}, classes, cuda_device)
+    net.train()
+    fused = heads.FusedHeads(net, {"task": "multi", "type": "FocalLoss", "gamma": 1})
+    names = fused.names
+    g = torch.Generator().manual_seed(3)
+    B = 64
+    emb0 = torch.randn(B, 16, generator=g).to(cuda_device)
+    target = {n: torch.randint(0, len(classes[n]), (B,), generator=g) for n in classes}
+    # reference call sequence: Dropout -> Linear per head, oracle focal loss, autograd
+    emb_r = emb0.clone().requires_grad_(True)
+    torch.manual_seed(77)
+    zs = {n: net.classifier[n](emb_r) for n in names}
+    ref_losses = [oh.focal_loss(zs[n].double(), target[n].to(cuda_device), None, 1.0) for n in names]
+    ref_total = sum(ref_losses)
+    params = [p_ for n in names for p_ in net.classifier[n].parameters()]
+    ref_grads = torch.autograd.grad(ref_total, [emb_r] + params)
+    # fused path, same seed
+    emb_f = emb0.clone().requires_grad_(True)
+    torch.manual_seed(77)
+    out = fused(emb_f, target, train=True)
+    got_grads = torch.autograd.grad(out.loss[len(names)], [emb_f] + params)
+    for t, n in enumerate(names):
+        a, b = out.seg[t], out.seg[t + 1]
+        assert rel_err(out.logits[:, a:b].cpu().numpy(), zs[n].detach().cpu().numpy()) <= 1e-5, n
+        assert rel_err(float(out.loss[t]), float(ref_losses[t])) <= 1e-5
+    assert rel_err(float(out.loss[len(names)]), float(ref_total)) <= 1e-5
+    for gg, rg in zip(got_grads, ref_grads):
+        assert rel_err(gg.cpu().numpy(), rg.cpu().numpy()) <= 1e-5
+    # confusion counts were accumulated once per head, eval mode takes the single segmented launch again
+    assert int(fused.state["cm"].sum()) == B * len(names)
+    net.eval()
+    out_e = fused(emb0, target, train=False)
+    z_e = torch.cat([net.classifier[n](emb0) for n in names], 1)
+    assert rel_err(out_e.logits.cpu().numpy(), z_e.detach().cpu().numpy()) <= 1e-5
+
+
 def test_loader_prefetch_ring_matches_inline(cuda_device, tmp_path):
     """the producer thread + copy stream + slot ring yields exactly what the inline loader yields, in
     order, over more batches than the ring has slots; abandoning an iteration and starting a new one is safe."""
