@@ -705,16 +705,7 @@ extern "C" int nkbk_heads_step(const void* emb, int emb_dtype, int B, int D, con
         if (tc > 0) loss_parts = tc;
     }
     if (tc > 0) {
-        // done on the tensor cores; argmax / confusion counts from the logits it wrote
-        if (out_pred != nullptr || p.cm_step != nullptr) {
-            if (out_logits == nullptr) {
-                set_error("nkbk_heads_step: out_pred / cm_step on the tcgen05 path need out_logits");
-                return NKBK_E_ARG;
-            }
-            rc = nkbk_argmax_confusion(out_logits, NKBK_F32, B, NC, seg_offsets, T, p.cm_step ? labels : nullptr,
-                                       out_pred, p.cm_step ? cm_step : nullptr, stream);
-            if (rc) return rc;
-        }
+        // done on the tensor cores, argmax / confusion counts included (same fused epilogue)
     } else {
         // stage the <= 16 x D weight tile of a pass in shared memory when it fits next to the per-warp slices
         const size_t wtile = (size_t)std::min(NC, K2_FWD_NCB) * D * sizeof(float);

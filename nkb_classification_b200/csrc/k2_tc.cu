@@ -234,10 +234,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k2_tc_heads_forward(const __gri
                 __threadfence();
                 if (e == 0) sp.counters[blockIdx.x] = 0u;
                 if (row < p.B) {
-                    for (int c = 0; c < NC; ++c) {
-                        float s = 0.f;
-                        for (int k = 0; k < ks; ++k) s += __ldcg(sp.partial + ((int64_t)k * p.B + row) * NPAD + c);  // fixed order
-                        z[c] = s + __ldg(p.bias + c);
+                    // all ks partials of four classes are requested together (one L2 round trip per group instead of
+                    // one per (class, split)); the additions keep their fixed split order
+                    const float* base = sp.partial + (int64_t)row * NPAD;
+                    const int64_t kstride = (int64_t)p.B * NPAD;
+#pragma unroll
+                    for (int c0 = 0; c0 < NPAD; c0 += 4) {
+                        if (c0 >= NC) break;
+                        float4 v[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            if (k < ks) v[k] = __ldcg(reinterpret_cast<const float4*>(base + k * kstride + c0));
+                        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            if (k < ks) { s.x += v[k].x; s.y += v[k].y; s.z += v[k].z; s.w += v[k].w; }
+                        const float sv[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (c0 + i < NC) z[c0 + i] = sv[i] + __ldg(p.bias + c0 + i);
                     }
                 }
             }
@@ -291,6 +306,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k2_tc_heads_forward(const __gri
                 }
                 my_lt[t] = loss_i;
                 my_lt[T + t] = den_i;
+                // ---- K3 fused: argmax (first maximum, NaN maximal) + confusion count of this (row, task) ----
+                if (row < p.B && (p.out_pred != nullptr || p.cm_step != nullptr)) {
+                    const int c0 = p.seg.off[t], C = p.seg.off[t + 1] - c0;
+                    const float* zt = z + c0;
+                    float best = zt[0];
+                    int bi = 0;
+                    for (int j = 1; j < C; ++j) {
+                        const float v = zt[j];
+                        if (!(best != best) && (v > best || v != v)) { best = v; bi = j; }
+                    }
+                    if (p.out_pred) p.out_pred[(int64_t)row * T + t] = bi;
+                    if (p.cm_step != nullptr && p.labels != nullptr) {
+                        const int64_t y = p.labels[(int64_t)row * T + t];
+                        if (y >= 0 && y < C) {
+                            int64_t off = 0;
+                            for (int u = 0; u < t; ++u) {
+                                const int64_t Cu = p.seg.off[u + 1] - p.seg.off[u];
+                                off += Cu * Cu;
+                            }
+                            atomicAdd(p.cm_step + off + y * C + bi, 1ull);
+                        }
+                    }
+                }
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

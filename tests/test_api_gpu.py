@@ -198,13 +198,17 @@ def test_per_head_dropout_matches_the_reference_call_sequence(cuda_device):
     torch.manual_seed(77)
     out = fused(emb_f, target, train=True)
     got_grads = torch.autograd.grad(out.loss[len(names)], [emb_f] + params)
+    torch.cuda.synchronize()
     for t, n in enumerate(names):
         a, b = out.seg[t], out.seg[t + 1]
-        assert rel_err(out.logits[:, a:b].cpu().numpy(), zs[n].detach().cpu().numpy()) <= 1e-5, n
-        assert rel_err(float(out.loss[t]), float(ref_losses[t])) <= 1e-5
+        e = rel_err(out.logits[:, a:b].cpu().numpy(), zs[n].detach().cpu().numpy())
+        assert e <= 1e-5, f"logits of head {n}: rel err {e}"
+        e = rel_err(float(out.loss[t]), float(ref_losses[t]))
+        assert e <= 1e-5, f"loss of head {n}: rel err {e}"
     assert rel_err(float(out.loss[len(names)]), float(ref_total)) <= 1e-5
-    for gg, rg in zip(got_grads, ref_grads):
-        assert rel_err(gg.cpu().numpy(), rg.cpu().numpy()) <= 1e-5
+    for i, (gg, rg) in enumerate(zip(got_grads, ref_grads)):
+        e = rel_err(gg.cpu().numpy(), rg.cpu().numpy())
+        assert e <= 1e-5, f"gradient {i} (0 = emb, then weight / bias per head): rel err {e}"
     # confusion counts were accumulated once per head, eval mode takes the single segmented launch again
     assert int(fused.state["cm"].sum()) == B * len(names)
     net.eval()

@@ -273,6 +273,43 @@ def test_k5_roc_auc_counts_exact(cuda_device, N, classes, quant):
         assert np.allclose(auc, e, rtol=0, atol=1e-12)
 
 
+@pytest.mark.parametrize("emb_dtype,B,D,classes", [
+    (torch.float32, 1024, 768, (2, 3, 4, 7, 14)),     # FFMA forward v3, two class passes
+    (torch.float32, 4096, 2048, (10,)),                # bench shape
+    (torch.float32, 37, 64, (70, 3)),                  # ragged rows, > 64 classes
+    (torch.bfloat16, 1024, 768, (2, 3, 4, 7, 14)),    # tcgen05 forward, split-K
+    (torch.bfloat16, 4096, 2048, (10,)),
+    (torch.bfloat16, 300, 128, (40, 20)),
+])
+def test_fused_k3_equals_standalone_k3(cuda_device, emb_dtype, B, D, classes):
+    """nkbk_heads_step (K3 in K2's epilogue, both forward kernels) gives exactly the predictions and confusion counts
+    of nkbk_argmax_confusion run on the logits it emitted, and leaves every other output unchanged."""
+    from nkb_classification_b200 import ops
+    g = torch.Generator().manual_seed(31)
+    seg = np.concatenate([[0], np.cumsum(classes)]).tolist()
+    T = len(classes)
+    emb = torch.randn(B, D, generator=g).to(cuda_device).to(emb_dtype)
+    W = (torch.randn(seg[-1], D, generator=g) * (2.0 / D) ** 0.5).to(cuda_device)
+    b = (torch.randn(seg[-1], generator=g) * 0.05).to(cuda_device)
+    labels = torch.stack([torch.randint(0, c, (B,), generator=g) for c in classes], 1)
+    labels[::11, 0] = -100
+    labels = labels.to(cuda_device)
+    ncm = ops.confusion_len(seg)
+    plain = ops.HeadsBuffers(B, D, seg, cuda_device)
+    ops.heads_fwd_loss_bwd(emb, W, b, labels, plain, oh.LOSS_FOCAL, 1.0)
+    pred_ref, cm_ref = ops.argmax_confusion(plain.logits, seg, labels, torch.zeros(ncm, dtype=torch.int64, device=cuda_device))
+    fused = ops.HeadsBuffers(B, D, seg, cuda_device)
+    pred = torch.full((B, T), -7, dtype=torch.int32, device=cuda_device)
+    cm = torch.zeros(ncm, dtype=torch.int64, device=cuda_device)
+    ops.heads_fwd_loss_bwd(emb, W, b, labels, fused, oh.LOSS_FOCAL, 1.0, out_pred=pred, cm_step=cm)
+    ops.heads_fwd_loss_bwd(emb, W, b, labels, fused, oh.LOSS_FOCAL, 1.0, out_pred=pred, cm_step=cm)   # accumulates
+    torch.cuda.synchronize()
+    assert torch.equal(pred, pred_ref) and torch.equal(cm, 2 * cm_ref)
+    assert int(cm_ref.sum()) == B * T - len(range(0, B, 11))
+    assert torch.equal(fused.logits, plain.logits) and torch.equal(fused.reduce_buf, plain.reduce_buf)
+    assert torch.equal(fused.dlogits, plain.dlogits)
+
+
 def _torchrun(script, world, port, env_extra=None, timeout=600):
     import os
     import subprocess
