@@ -43,6 +43,8 @@ def parse_args():
                     help="dtype of the synthetic backbone output fed to K2 (bf16 = autocast path, tcgen05 forward)")
     ap.add_argument("--allreduce", default="peer", choices=["peer", "nccl"],
                     help="exchange step at N > 1: K4' fused NVLink peer-memory all-reduce + finalize, or NCCL (K4)")
+    ap.add_argument("--resize", default=None, choices=["stretch", "letterbox"],
+                    help="override the workload's geometry: A.Resize(S,S) or A.LongestMaxSize(S)+A.PadIfNeeded(S,S)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -233,7 +235,9 @@ def run_b200(args, wl):
         comm.init_from_torch_distributed(dev)
 
     out_dtype = torch.float32 if args.out_dtype == "f32" else torch.bfloat16
-    plan = T.compile_pipeline([T.Resize(wl.out_size, wl.out_size), T.Normalize(MEAN, STD), T.ToTensorV2()])
+    geo = ([T.Resize(wl.out_size, wl.out_size)] if wl.mode == "stretch" else
+           [T.LongestMaxSize(wl.out_size), T.PadIfNeeded(wl.out_size, wl.out_size, border_mode=T.BORDER_CONSTANT, value=0)])
+    plan = T.compile_pipeline(geo + [T.Normalize(MEAN, STD), T.ToTensorV2()])
     hp = hotpath.HotPath(plan, wl.classes, wl.emb_dim, wl.loss, wl.gamma, device=dev, comm=comm, out_dtype=out_dtype,
                          transport=args.allreduce)
 
@@ -392,7 +396,7 @@ def run_b200(args, wl):
     # ---- roofline of the dominant kernel (K1) ----
     peak, peak_src = measured_peak_hbm()
     elem = 4 if out_dtype == torch.float32 else 2
-    k1_bytes = k1_algorithmic_bytes(boxes_np, wl.out_size, wl.out_size, elem)
+    k1_bytes = k1_algorithmic_bytes(boxes_np, wl.out_size, wl.out_size, elem, wl.mode, wl.out_size)
     achieved = k1_bytes / (k1_ms * 1e-3) / 1e9
     traffic = None
     tp = ROOT / "profiles" / "k1_traffic.json"
@@ -441,6 +445,9 @@ def main():
     from nkb_classification_b200.synthetic import DEFAULT_WORKLOAD, WORKLOADS
 
     wl = WORKLOADS[args.workload or DEFAULT_WORKLOAD]
+    if args.resize is not None and args.resize != wl.mode:
+        import dataclasses
+        wl = dataclasses.replace(wl, mode=args.resize, name=f"{wl.name}.{args.resize}")
     if args.impl == "reference":
         run_reference(args, wl)
     else:

@@ -176,6 +176,7 @@ __device__ __forceinline__ bool fast_path_qualifies(const K1Params& p, const Cro
                                                     uint32_t& seg_bytes, uint32_t& slot_stride, int& nslot) {
     seg_start = 0; seg_bytes = 0; slot_stride = 0; nslot = 0;
     if (!g.ok) return false;
+    if (g.bx0 + 1 >= g.fw) return false;   // a 1-pixel box on the frame's last column: its window shifts left of the span
     if (((reinterpret_cast<uintptr_t>(p.frames) + (uintptr_t)g.f_off) & 15u) != 0 || (g.pitch & 15) != 0) return false;
     const uint32_t s = (uint32_t(g.bx0) * 3u) & ~15u;
     const uint32_t e_px = (uint32_t)min(g.bx0 + g.bw + 1, g.fw);

@@ -1,5 +1,5 @@
-// K1 fast path: stretch mode (A.Resize), full 32*JMAX column tiles, 16-byte
-// aligned frame rows.  Same arithmetic as k1_general.cu (bit-exact with cv2),
+// K1 fast path: A.Resize or A.LongestMaxSize + A.PadIfNeeded, full 32*JMAX column
+// tiles, 16-byte aligned frame rows.  Same arithmetic as k1_general.cu (bit-exact with cv2),
 // different data movement:
 //
 //   * every warp owns a band of output rows and a private shared-memory ring of
@@ -68,7 +68,10 @@ __device__ __forceinline__ uint32_t vtap(uint32_t b0, uint32_t h0, uint32_t b1, 
 #define K1F_MIN_BLOCKS 4
 #endif
 
-template <int JMAX, typename OutT>
+// LB = true: A.LongestMaxSize + centred A.PadIfNeeded (the geometry of every val / train pipeline in the reference's
+// configs): the resized crop covers columns [left, left + dw) and rows [top, top + dh) of the output; lanes / rows
+// outside it emit the pad value and never touch the source.
+template <int JMAX, typename OutT, bool LB>
 __global__ void __launch_bounds__(K1_WARPS * 32, K1F_MIN_BLOCKS) k1_crop_resize_normalize_tma(const K1Params p) {
     __shared__ __align__(128) uint8_t ring[K1_WARPS][K1F_RING_BYTES];
     __shared__ __align__(8) uint64_t bars[K1_WARPS][K1F_MAX_SLOTS];
@@ -85,13 +88,16 @@ __global__ void __launch_bounds__(K1_WARPS * 32, K1F_MIN_BLOCKS) k1_crop_resize_
     const CropGeom g = load_geom(p, crop);
     uint32_t seg_start, seg_bytes, slot_stride;
     int nslot;
-    if (!fast_path_qualifies(p, g, seg_start, seg_bytes, slot_stride, nslot)) {
-        // unaligned frame rows, a box wider than the ring, or an invalid box: same arithmetic, direct loads
+    int dw = p.out_w, dh = p.out_h, top = 0, left = 0;
+    bool fast = fast_path_qualifies(p, g, seg_start, seg_bytes, slot_stride, nslot);
+    if (LB && fast) fast = letterbox_geometry(g.bh, g.bw, p.max_size, p.out_h, p.out_w, dh, dw, top, left);
+    if (!fast) {
+        // unaligned frame rows, a box wider than the ring, an invalid box or a letterbox that does not fit: same
+        // arithmetic, direct loads
         k1_process_band<JMAX, OutT, true, false>(p, crop, g, y_begin, nrows, ox0,
                                                  blockIdx.y == 0 && blockIdx.z == 0 && warp == 0);
         return;
     }
-    const int dw = p.out_w, dh = p.out_h;
 
     // ---- per-warp barriers ----
     const uint32_t bar0 = smem_u32(&bars[warp][0]);
@@ -104,17 +110,25 @@ __global__ void __launch_bounds__(K1_WARPS * 32, K1F_MIN_BLOCKS) k1_crop_resize_
 
     // ---- horizontal tables: smem byte offset of the window, funnel shift, packed coefficients ----
     uint32_t soa[JMAX], sk8[JMAX], cf[JMAX];
+    uint32_t vmask = (1u << JMAX) - 1u;   // LB: columns of this lane that receive resized pixels (the rest is border)
     {
         const double sxs = axis_scale(dw, g.bw);
+        if (LB) vmask = 0;
 #pragma unroll
         for (int j = 0; j < JMAX; ++j) {
-            int s, c0, c1;
-            axis_coef(ox0 + 32 * j, sxs, g.bw, true, s, c0, c1);
+            int s = 0, c0 = 0, c1 = 0;
+            const int dx = ox0 + 32 * j - left;
+            const bool valid = !LB || (dx >= 0 && dx < dw);
+            if (valid) axis_coef(dx, sxs, g.bw, true, s, c0, c1);
             int px = g.bx0 + s;
             uint32_t c = uint32_t(c0) | (uint32_t(c1) << 16);
             if (px + 1 >= g.fw) {  // window would leave the frame row: shift it left, weight moves to tap 1
                 px -= 1;
                 c = uint32_t(c0) << 16;
+            }
+            if (LB) {
+                vmask |= uint32_t(valid) << j;
+                if (!valid) c = 0u;   // border column: reads the box's first window, weights zero (value replaced below)
             }
             const uint32_t so = uint32_t(px) * 3u - seg_start;
             soa[j] = so & ~3u;
@@ -127,12 +141,15 @@ __global__ void __launch_bounds__(K1_WARPS * 32, K1F_MIN_BLOCKS) k1_crop_resize_
     int my_r0 = -1, my_r1 = -1;
     uint32_t my_b0 = 0, my_b1 = 0;
     if (lane < nrows) {
-        int s, c0, c1;
-        axis_coef(y_begin + lane, axis_scale(dh, g.bh), g.bh, false, s, c0, c1);
-        my_r0 = min(max(s, 0), g.bh - 1);
-        my_r1 = min(max(s + 1, 0), g.bh - 1);
-        my_b0 = uint32_t(c0) << 16;  // pre-shifted: umulhi(b << 16, h) == (b * h) >> 16
-        my_b1 = uint32_t(c1) << 16;
+        const int dy = y_begin + lane - top;
+        if (!LB || (dy >= 0 && dy < dh)) {   // LB: border rows keep r0 = -1 and never enter the fetch list
+            int s, c0, c1;
+            axis_coef(dy, axis_scale(dh, g.bh), g.bh, false, s, c0, c1);
+            my_r0 = min(max(s, 0), g.bh - 1);
+            my_r1 = min(max(s + 1, 0), g.bh - 1);
+            my_b0 = uint32_t(c0) << 16;  // pre-shifted: umulhi(b << 16, h) == (b * h) >> 16
+            my_b1 = uint32_t(c1) << 16;
+        }
     }
 
     // ---- fetch list: the strictly increasing sequence of source rows this band consumes ----
@@ -208,12 +225,23 @@ __global__ void __launch_bounds__(K1_WARPS * 32, K1F_MIN_BLOCKS) k1_crop_resize_
         const int r1 = __shfl_sync(0xffffffffu, my_r1, yy);
         const uint32_t b0 = __shfl_sync(0xffffffffu, my_b0, yy);
         const uint32_t b1 = __shfl_sync(0xffffffffu, my_b1, yy);
+        if (LB && r0 < 0) {   // letterbox border row: the normalised pad value, no source row involved
+#pragma unroll
+            for (int j = 0; j < JMAX; ++j) {
+                store_out<OutT>(o + 32 * j, p.padf[0]);
+                store_out<OutT>(o + plane + 32 * j, p.padf[1]);
+                store_out<OutT>(o + 2 * plane + 32 * j, p.padf[2]);
+            }
+            o += out_w;
+            continue;
+        }
         auto vertical = [&](const uint32_t (&Ht)[JMAX][3], const uint32_t (&Hb)[JMAX][3]) {
 #pragma unroll
             for (int j = 0; j < JMAX; ++j) {
-                const uint32_t v0 = vtap(b0, Ht[j][0], b1, Hb[j][0]);
-                const uint32_t v1 = vtap(b0, Ht[j][1], b1, Hb[j][1]);
-                const uint32_t v2 = vtap(b0, Ht[j][2], b1, Hb[j][2]);
+                uint32_t v0 = vtap(b0, Ht[j][0], b1, Hb[j][0]);
+                uint32_t v1 = vtap(b0, Ht[j][1], b1, Hb[j][1]);
+                uint32_t v2 = vtap(b0, Ht[j][2], b1, Hb[j][2]);
+                if (LB && !(vmask >> j & 1)) { v0 = p.padu[0]; v1 = p.padu[1]; v2 = p.padu[2]; }
                 store_out<OutT>(o + 32 * j, __fmul_rn(__fsub_rn((float)v0, m0f), d0f));
                 store_out<OutT>(o + plane + 32 * j, __fmul_rn(__fsub_rn((float)v1, m1f), d1f));
                 store_out<OutT>(o + 2 * plane + 32 * j, __fmul_rn(__fsub_rn((float)v2, m2f), d2f));
@@ -239,8 +267,13 @@ __global__ void __launch_bounds__(K1_WARPS * 32, K1F_MIN_BLOCKS) k1_crop_resize_
 
 template <int JMAX>
 static void launch_fast_j(const K1Params& p, dim3 grid, cudaStream_t st, bool f32) {
-    if (f32) k1_crop_resize_normalize_tma<JMAX, float><<<grid, K1_WARPS * 32, 0, st>>>(p);
-    else k1_crop_resize_normalize_tma<JMAX, __nv_bfloat16><<<grid, K1_WARPS * 32, 0, st>>>(p);
+    if (p.mode == NKBK_MODE_LETTERBOX) {
+        if (f32) k1_crop_resize_normalize_tma<JMAX, float, true><<<grid, K1_WARPS * 32, 0, st>>>(p);
+        else k1_crop_resize_normalize_tma<JMAX, __nv_bfloat16, true><<<grid, K1_WARPS * 32, 0, st>>>(p);
+    } else {
+        if (f32) k1_crop_resize_normalize_tma<JMAX, float, false><<<grid, K1_WARPS * 32, 0, st>>>(p);
+        else k1_crop_resize_normalize_tma<JMAX, __nv_bfloat16, false><<<grid, K1_WARPS * 32, 0, st>>>(p);
+    }
 }
 
 // Returns false when no fast instantiation exists for this column-tile width.

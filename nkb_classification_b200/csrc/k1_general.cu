@@ -171,10 +171,11 @@ static int k1_preprocess_impl(const void* frames_base, const int64_t* frame_desc
     const bool f32 = out_dtype == NKBK_F32;
     p.rows_per_warp_fast = p.rows_per_warp;
 
-    // ---- fast path: A.Resize, output width a whole number of 32*J column tiles, no uint8 side output ----
+    // ---- fast path: A.Resize or LongestMaxSize + PadIfNeeded, output width a whole number of 32*J column tiles,
+    // no uint8 side output, no train-time augmentations ----
     // Crops whose frame rows are not 16-byte aligned or whose boxes are too wide for the shared-memory ring are
     // left untouched by the TMA kernel and produced by the general kernel in a small-grid fix-up pass.
-    if (mode == NKBK_MODE_STRETCH && out_u8 == nullptr && out_w % 32 == 0 && aug == nullptr) {
+    if (out_u8 == nullptr && out_w % 32 == 0 && aug == nullptr) {
         const int cols = out_w / 32;
         int fj = 0;
         for (int j = 8; j >= 4; --j)

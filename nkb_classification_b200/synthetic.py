@@ -77,12 +77,21 @@ def synth_boxes(wl: Workload, seed: int = 4321) -> Tuple[np.ndarray, np.ndarray]
     return np.asarray(boxes, dtype=np.int32).reshape(-1, 4), np.asarray(fidx, dtype=np.int32)
 
 
-def k1_algorithmic_bytes(boxes: np.ndarray, out_h: int, out_w: int, out_elem_bytes: int) -> int:
-    """per crop 3*min(w,2*out_w)*min(h,2*out_h) source bytes a 2-tap filter can touch
+def k1_algorithmic_bytes(boxes: np.ndarray, out_h: int, out_w: int, out_elem_bytes: int, mode: str = "stretch",
+                         max_size: int = 0) -> int:
+    """per crop 3*min(w,2*dw)*min(h,2*dh) source bytes a 2-tap filter can touch (dw x dh = the
+    resized size: the whole output for A.Resize, the letterboxed extent for LongestMaxSize + PadIfNeeded)
     + 3*out_h*out_w*sizeof(out) written + 16 bytes of box."""
     b = np.asarray(boxes, dtype=np.int64).reshape(-1, 4)
-    w = np.minimum(b[:, 2] - b[:, 0], 2 * out_w)
-    h = np.minimum(b[:, 3] - b[:, 1], 2 * out_h)
+    bw, bh = b[:, 2] - b[:, 0], b[:, 3] - b[:, 1]
+    if mode == "letterbox":
+        scale = (max_size or min(out_h, out_w)) / np.maximum(bw, bh).astype(np.float64)
+        dw = np.where(scale != 1.0, np.rint(bw * scale), bw).astype(np.int64)
+        dh = np.where(scale != 1.0, np.rint(bh * scale), bh).astype(np.int64)
+    else:
+        dw, dh = np.full_like(bw, out_w), np.full_like(bh, out_h)
+    w = np.minimum(bw, 2 * dw)
+    h = np.minimum(bh, 2 * dh)
     return int((3 * w * h).sum() + b.shape[0] * (3 * out_h * out_w * out_elem_bytes + 16))
 
 

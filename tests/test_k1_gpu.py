@@ -289,6 +289,29 @@ def test_k1_whole_image_configs(cuda_device, name, hw, kw):
         assert np.array_equal(u8.cpu().numpy(), frames)  # identity resize
 
 
+@pytest.mark.parametrize("mode", ["stretch", "letterbox"])
+def test_k1_fast_path_last_column_boxes(cuda_device, mode):
+    """Boxes that start on the last column of a frame whose row offset is 16-byte aligned there (the 2-tap window is
+    shifted left of the staged span): the TMA kernel must hand them to the direct-load routine.  Also 2-pixel boxes on
+    the edge, in both geometries, through the fast path (no uint8 side output)."""
+    from nkb_classification_b200 import transforms as T
+    rng = np.random.default_rng(23)
+    W = 17 + 16 * 3            # 65: column 64 -> byte offset 192, a multiple of 16
+    frames = rng.integers(0, 256, (2, 40, W, 3), dtype=np.uint8)
+    boxes = [(W - 1, 0, W, 40), (W - 1, 5, W, 6), (W - 2, 0, W, 40), (16, 3, 17, 30), (0, 0, W, 40), (48, 10, 49, 35)]
+    fidx = [0, 1, 0, 1, 0, 1]
+    plan = make_plan(T, mode=mode, out_h=64, out_w=64, pad=(9, 8, 7))
+    # pitch must be 16-byte aligned for the TMA path: pack the frames with a padded pitch
+    pitch = (W * 3 + 15) // 16 * 16
+    flat = np.zeros((2, 40, pitch), dtype=np.uint8)
+    flat[:, :, : W * 3] = frames.reshape(2, 40, W * 3)
+    desc = torch.tensor([[f * 40 * pitch, 40, W, pitch] for f in range(2)], dtype=torch.int64, device=cuda_device)
+    out, _ = run_k1(cuda_device, torch.from_numpy(flat.reshape(-1)).to(cuda_device), boxes, fidx, plan, want_u8=False,
+                    frame_desc=desc)
+    _, ef32 = preprocess_batch_c(frames, boxes, fidx, oracle_plan(plan))
+    assert_same_f32(out, ef32)
+
+
 def _aug_samples(batch):
     """transforms.AugmentBatch -> the oracle's per-sample parameter objects."""
     out = []
