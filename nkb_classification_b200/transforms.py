@@ -253,8 +253,7 @@ def draw_augmentations(spec: AugmentSpec, n: int, out_h: int, out_w: int, rng=No
                     vs = rng.uniform(spec.val_limit[0], spec.val_limit[1])
                     hsv_shift[i] = (hs, ss, vs)
                     if hs != 0 or ss != 0 or vs != 0:    # `shift_hsv` returns the image untouched for all-zero shifts
-                        f |= AUG_HSV
-                        hsv_lut[i] = hsv_luts(hs, ss, vs)
+                        f |= AUG_HSV                     # (its tables are built for the whole batch below)
             elif name == "CoarseDropout":
                 if rng.random() < spec.cd_p:
                     k = rng.randint(spec.holes[0], spec.holes[1])
@@ -270,6 +269,18 @@ def draw_augmentations(spec: AugmentSpec, n: int, out_h: int, out_w: int, rng=No
                         holes[i, h] = (x1, y1, x1 + hw, y1 + hh)
                     f |= k << 8
         flags[i] = f
+    if has_hsv:
+        on = np.nonzero(flags & AUG_HSV)[0]
+        if on.size:   # hsv_luts() for every flagged sample at once (same arithmetic: int16 ramp + float64 shift)
+            ramp = np.arange(0, 256, dtype=np.int16)[None, :]
+            sh = hsv_shift[on]
+            hue = np.mod(ramp + sh[:, 0:1], 180).astype(np.uint8)
+            sat = np.clip(ramp + sh[:, 1:2], 0, 255).astype(np.uint8)
+            val = np.clip(ramp + sh[:, 2:3], 0, 255).astype(np.uint8)
+            ident = np.arange(256, dtype=np.uint8)[None, :]
+            hsv_lut[on, 0] = np.where(sh[:, 0:1] != 0, hue, ident)
+            hsv_lut[on, 1] = np.where(sh[:, 1:2] != 0, sat, ident)
+            hsv_lut[on, 2] = np.where(sh[:, 2:3] != 0, val, ident)
     lanes = cv2_hsv_simd_lanes() if has_hsv else 0
     return AugmentBatch(flags, alpha, beta, holes, spec.fill, bright, hsv_shift, hsv_lut,
                         (out_w // lanes) * lanes if lanes else 0)
