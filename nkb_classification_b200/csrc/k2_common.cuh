@@ -10,8 +10,11 @@ constexpr int K2_FWD_ROWS = 4;     // rows per CTA
 constexpr int K2_FWD_NCB = 16;     // classes per pass
 constexpr int K2_V3_WARPS = 4;     // forward v3: warps per CTA, each owning K2_FWD_ROWS rows over the full K
 constexpr int K2_V3_PD = 4;        // forward v3: 128-column chunks of embedding loads in flight per warp
-constexpr int K2_DW_WARPS = 4;
-constexpr int K2_DW_ROWS = 128;    // rows per dW chunk (32 per warp)
+#ifndef NKBK_DW_WARPS
+#define NKBK_DW_WARPS 8
+#endif
+constexpr int K2_DW_WARPS = NKBK_DW_WARPS;
+constexpr int K2_DW_ROWS = 32 * NKBK_DW_WARPS;    // rows per dW chunk (32 per warp)
 constexpr int K2_DW_COLS = 128;    // columns per dW CTA (4 per lane)
 constexpr int K2_DW_NCB = 16;      // classes per dW pass
 

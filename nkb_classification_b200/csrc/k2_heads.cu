@@ -13,7 +13,7 @@
 //                      the logits in the warp's private shared-memory slice; per-(row,
 //                      task) lanes then do softmax / loss / dlogits and the fused K3
 //                      (argmax + confusion counts).  No cross-warp reduction.
-//   k2_heads_dw        CTA = 128 rows x 128 columns, 4 warps x 32 rows, thread =
+//   k2_heads_dw        CTA = 256 rows x 128 columns, 8 warps x 32 rows, thread =
 //                      4 columns x NCP classes in registers, dlogits broadcast
 //                      from shared memory; fixed-order cross-warp tree; the last
 //                      CTA to finish a column block sums the per-chunk partials
@@ -347,7 +347,7 @@ __device__ __forceinline__ float warp_fixed_sum(const float* base, int n, int64_
 
 // ---- dW / db ---------------------------------------------------------------
 template <typename ET, int NCP>
-__global__ void __launch_bounds__(K2_DW_WARPS * 32, 4) k2_heads_dw(
+__global__ void __launch_bounds__(K2_DW_WARPS * 32, 16 / K2_DW_WARPS) k2_heads_dw(
     const ET* __restrict__ emb, const float* __restrict__ dlogits, int B, int D, int NC, int T, int cls0, int pass,
     float* __restrict__ dw_part, float* __restrict__ db_part, const float* __restrict__ loss_part, int fwd_blocks,
     unsigned int* __restrict__ counters, float* __restrict__ reduce_buf) {
