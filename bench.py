@@ -302,7 +302,9 @@ def run_b200(args, wl):
     # execute.  All work of all K steps still happens inside the timed region; both streams are joined before e1.
     # The heads stream has the higher priority: its short kernels take SM slots as K1's CTAs retire instead of queueing
     # behind the whole K1 grid, so K2/K3/K4 of a batch really run under the K1 of the next one.
-    s_pre, s_heads = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev, priority=-1)
+    prio = os.environ.get("NKBK_BENCH_HEADS_PRIORITY", "high")   # experiment knob: high | same | low
+    s_pre = torch.cuda.Stream(device=dev, priority=-1 if prio == "low" else 0)
+    s_heads = torch.cuda.Stream(device=dev, priority=-1 if prio == "high" else 0)
     cur = torch.cuda.current_stream(dev)
 
     def pipelined(k):

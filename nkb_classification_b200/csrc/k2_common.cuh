@@ -8,8 +8,14 @@ constexpr int K2_MAX_TASKS = 64;
 constexpr int K2_MAX_NC = 1024;
 constexpr int K2_FWD_ROWS = 4;     // rows per CTA
 constexpr int K2_FWD_NCB = 16;     // classes per pass
-constexpr int K2_V3_WARPS = 4;     // forward v3: warps per CTA, each owning K2_FWD_ROWS rows over the full K
-constexpr int K2_V3_PD = 4;        // forward v3: 128-column chunks of embedding loads in flight per warp
+#ifndef NKBK_V3_WARPS
+#define NKBK_V3_WARPS 4
+#endif
+#ifndef NKBK_V3_PD
+#define NKBK_V3_PD 4
+#endif
+constexpr int K2_V3_WARPS = NKBK_V3_WARPS;  // forward v3: warps per CTA, each owning K2_FWD_ROWS rows over the full K
+constexpr int K2_V3_PD = NKBK_V3_PD;        // forward v3: 128-column chunks of embedding loads in flight per warp
 #ifndef NKBK_DW_WARPS
 #define NKBK_DW_WARPS 8
 #endif
