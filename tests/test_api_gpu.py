@@ -1,6 +1,7 @@
 """The reference-facing API on the GPU: criterion objects, the data loader, train/val epochs and
 inference(), each checked against the CPU oracle on the same inputs."""
 import json
+from pathlib import Path
 from types import SimpleNamespace
 
 import numpy as np
@@ -359,6 +360,81 @@ def test_train_epoch_updates_heads_like_the_oracle(cuda_device, tmp_path):
         assert rel_err(new_state[f"classifier.{n}.1.bias"].cpu().numpy(), bs[t].detach().numpy()) <= 2e-5
     assert rel_err(new_state["emb_model.proj.weight"].cpu().numpy(), bb.proj.weight.detach().numpy()) <= 2e-5
     torch.jit.script(model)  # still scriptable after the heads were packed (train.py:66)
+
+
+def test_reference_train_config_end_to_end(cuda_device, tmp_path):
+    """The whole drop-in flow on the reference's own training recipe (configs/multitask_config.py shape): letterbox
+    + every train-time augmentation fused in K1, classifier_dropout 0.1 (per-head masks), focal gamma 1, bf16
+    autocast, Adam + cosine schedule, weighted sampling; then validation, compute_metrics and inference().  Checks
+    that it learns a separable toy problem and that every reference-facing structure has the reference's keys."""
+    import random
+    import cv2
+    import pandas as pd
+    from nkb_classification_b200 import dataset as D, engine, inference as I, logging as L, losses, metrics as Mx
+    from nkb_classification_b200 import model as M, transforms as T, utils
+    rng = np.random.default_rng(3)
+    rows = []
+    for i in range(96):   # colour decides "color", brightness decides "size": learnable from pooled pixels
+        color, size = int(rng.integers(0, 3)), int(rng.integers(0, 2))
+        img = rng.integers(0, 60, (int(rng.integers(40, 70)), int(rng.integers(40, 90)), 3), dtype=np.uint8)
+        img[..., 2 - color] += np.uint8(90 + 80 * size)     # cv2 writes BGR
+        cv2.imwrite(str(tmp_path / f"t{i}.png"), img)
+        rows.append({"path": f"t{i}.png", "fold": "train" if i < 72 else "val", "color": ["red", "green", "blue"][color],
+                     "size": ["s", "l"][size]})
+    pd.DataFrame(rows).to_csv(tmp_path / "ann.csv", index=False)
+    geo = [T.LongestMaxSize(32, always_apply=True),
+           T.PadIfNeeded(32, 32, always_apply=True, border_mode=T.BORDER_CONSTANT, value=0)]
+    tail = [T.Normalize(mean=MEAN, std=STD), T.ToTensorV2()]
+    train_pipeline = T.Compose(geo + [
+        T.HorizontalFlip(p=0.5), T.VerticalFlip(p=0.5),
+        T.RandomBrightnessContrast(brightness_limit=(-0.05, 0.05), contrast_limit=(0.05, -0.05), p=0.5),
+        T.HueSaturationValue(hue_shift_limit=0, sat_shift_limit=10, val_shift_limit=10, p=0.5),
+        T.CoarseDropout(max_holes=2, min_holes=1, max_height=0.2, min_height=0.05, max_width=0.2, min_width=0.05,
+                        fill_value=[0, 0.5, 1], p=0.5)] + tail)
+    val_pipeline = T.Compose(geo + tail)
+    base = {"type": "AnnotatedMultitaskDataset", "annotations_file": str(tmp_path / "ann.csv"),
+            "target_names": ["size", "color"], "image_base_dir": str(tmp_path), "batch_size": 24, "num_workers": 2,
+            "device": str(cuda_device)}
+    random.seed(11)
+    torch.manual_seed(11)
+    train_loader = D.get_dataset(dict(base, fold="train", shuffle=True, weighted_sampling=True), train_pipeline)
+    val_loader = D.get_dataset(dict(base, fold="val", shuffle=False), val_pipeline)
+    classes = train_loader.dataset.classes
+    cfg = cfg_ns(enable_mixed_presicion=True, target_names=["color", "size"])
+    net = M.get_model({"task": "multi", "model": TinyBackbone(), "pretrained": False, "backbone_dropout": 0.0,
+                       "classifier_dropout": 0.1, "classifier_initialization": "kaiming_normal_"}, classes, cuda_device)
+    opt = utils.get_optimizer(net, {"type": "adam", "lr": 0.05, "backbone_lr": 0.02})
+    sched = utils.get_scheduler(opt, {"type": "cosine", "n_epochs": 8})
+    crit = losses.get_loss(cfg.criterion, cuda_device)
+    scaler = torch.amp.GradScaler("cuda", enabled=False)
+    first = last = None
+    for epoch in range(8):
+        log = L.BaseLogger(cfg, classes)
+        res = engine.train_epoch(net, train_loader, opt, sched, scaler, crit, cuda_device, cfg, log)
+        m = Mx.compute_metrics(cfg, res)
+        loss = float(np.mean(res["running_loss"]["loss"]))
+        assert np.isfinite(loss)
+        first = loss if first is None else first
+        last = loss
+    assert last < 0.6 * first, (first, last)
+    vres = engine.val_epoch(net, val_loader, crit, cuda_device, cfg, L.BaseLogger(cfg, classes))
+    vm = Mx.compute_metrics(cfg, vres)
+    assert set(vm) == {"color", "size", "loss", "epoch_acc"} and set(vm["color"]) == {"epoch_acc", "epoch_roc_auc", "epoch_loss"}
+    assert vm["epoch_acc"] > 0.8, vm
+    assert set(vres["confusion"]) == {"color", "size"} and int(vres["confusion"]["color"].sum()) == 24
+    # inference() on the validation images reproduces val_epoch's predictions
+    (tmp_path / "inf").mkdir()
+    for r in rows[72:]:
+        (tmp_path / "inf" / r["path"]).write_bytes((tmp_path / r["path"]).read_bytes())
+    inf_loader = D.get_inference_dataset({"folder_path": str(tmp_path / "inf"), "batch_size": 16, "num_workers": 2,
+                                          "device": str(cuda_device)}, val_pipeline)
+    I.inference(net, inf_loader, classes, str(tmp_path), cuda_device, cfg)
+    out = pd.read_csv(tmp_path / "inference_annotations.csv")
+    assert len(out) == 24 and {"color", "size", "path"} <= set(out.columns)
+    by_path = {Path(p_).name: (c, s_) for p_, c, s_ in zip(out["path"], out["color"], out["size"])}
+    idx2 = {n: {v: k for k, v in train_loader.dataset.class_to_idx[n].items()} for n in ("color", "size")}
+    for r, pc, ps in zip(rows[72:], vres["predictions"]["color"], vres["predictions"]["size"]):
+        assert by_path[r["path"]] == (idx2["color"][pc], idx2["size"][ps])
 
 
 def test_inference_writes_reference_csv(cuda_device, tmp_path):
