@@ -34,3 +34,20 @@ def cuda_device(nkbk_lib):
     if not torch.cuda.is_available():
         pytest.fail("this test is marked gpu but no CUDA device is visible")
     return torch.device("cuda:0")
+
+
+@pytest.fixture(autouse=True)
+def _seed_everything():
+    """Every test starts from the same RNG state (model initialisation, shuffles, augmentation draws), so a result
+    never depends on which tests ran before it."""
+    import random
+
+    import numpy as np
+    random.seed(1234)
+    np.random.seed(1234)
+    try:
+        import torch
+        torch.manual_seed(1234)
+    except Exception:  # pragma: no cover
+        pass
+    yield
