@@ -45,6 +45,9 @@ def parse_args():
                     help="exchange step at N > 1: K4' fused NVLink peer-memory all-reduce + finalize, or NCCL (K4)")
     ap.add_argument("--resize", default=None, choices=["stretch", "letterbox"],
                     help="override the workload's geometry: A.Resize(S,S) or A.LongestMaxSize(S)+A.PadIfNeeded(S,S)")
+    ap.add_argument("--train-aug", action="store_true",
+                    help="K1 with the reference's train-time augmentations fused (configs/singletask_config.py:162-201); "
+                         "parameters are drawn once on the host before the timed region")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -188,6 +191,7 @@ def workload_config(wl, out_dtype, n_gpus, transport="peer"):
         "frames_per_gpu": wl.frames, "frame": f"{wl.frame_w}x{wl.frame_h}x3 u8", "boxes_per_frame": wl.boxes_per_frame,
         "crops_per_gpu_per_step": wl.crops, "out": f"3x{wl.out_size}x{wl.out_size} {out_dtype}", "resize": wl.mode,
         "emb_dim": wl.emb_dim, "heads": list(wl.classes), "loss": wl.loss, "gamma": wl.gamma,
+        "train_aug": bool(getattr(wl, "train_aug", False)),
         "backbone": "excluded (out of scope; synthetic embeddings)",
         "l2": "inputs larger than L2 (frames + output >> 126 MB per step); no flush needed",
         "parallelism": f"dp{n_gpus} (frames sharded per rank; head grads + confusion counts all-reduced by "
@@ -237,7 +241,14 @@ def run_b200(args, wl):
     out_dtype = torch.float32 if args.out_dtype == "f32" else torch.bfloat16
     geo = ([T.Resize(wl.out_size, wl.out_size)] if wl.mode == "stretch" else
            [T.LongestMaxSize(wl.out_size), T.PadIfNeeded(wl.out_size, wl.out_size, border_mode=T.BORDER_CONSTANT, value=0)])
-    plan = T.compile_pipeline(geo + [T.Normalize(MEAN, STD), T.ToTensorV2()])
+    aug_ops = []
+    if args.train_aug:
+        aug_ops = [T.HorizontalFlip(p=0.5), T.VerticalFlip(p=0.5),
+                   T.RandomBrightnessContrast(brightness_limit=(-0.2, 0.2), contrast_limit=(0.1, -0.5), p=0.5),
+                   T.HueSaturationValue(hue_shift_limit=0, sat_shift_limit=10, val_shift_limit=50, p=0.5),
+                   T.CoarseDropout(max_holes=4, min_holes=1, max_height=0.2, min_height=0.05, max_width=0.2,
+                                   min_width=0.05, fill_value=[0, 0.5, 1], p=0.5)]
+    plan = T.compile_pipeline(geo + aug_ops + [T.Normalize(MEAN, STD), T.ToTensorV2()])
     hp = hotpath.HotPath(plan, wl.classes, wl.emb_dim, wl.loss, wl.gamma, device=dev, comm=comm, out_dtype=out_dtype,
                          transport=args.allreduce)
 
@@ -256,6 +267,13 @@ def run_b200(args, wl):
     labels = labels_h.to(dev)
     Ws, bs = make_heads(wl)
     W_cat, b_cat = torch.cat(Ws).contiguous().to(dev), torch.cat(bs).contiguous().to(dev)
+
+    aug = None
+    if args.train_aug:
+        import random as _random
+        aug = plan.draw(n, _random.Random(99 + rank))
+        _pre = hp.preprocess
+        hp.preprocess = lambda fr, bx, fi, frame_desc=None: _pre(fr, bx, fi, frame_desc, aug)   # same call sites below
 
     def step():
         hp.preprocess(frames, boxes, fidx)
@@ -450,6 +468,10 @@ def main():
     if args.resize is not None and args.resize != wl.mode:
         import dataclasses
         wl = dataclasses.replace(wl, mode=args.resize, name=f"{wl.name}.{args.resize}")
+    if args.train_aug:
+        import dataclasses
+        wl = dataclasses.replace(wl, name=f"{wl.name}.train_aug")
+        object.__setattr__(wl, "train_aug", True)
     if args.impl == "reference":
         run_reference(args, wl)
     else:

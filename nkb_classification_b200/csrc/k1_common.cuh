@@ -67,12 +67,17 @@ __host__ __device__ __forceinline__ int k1_div_rhe(int n, int d) {  // round-hal
     const int q = n / d, r = n - q * d, t = 2 * r;
     return q + ((t > d || (t == d && (q & 1))) ? 1 : 0);
 }
-__host__ __device__ __forceinline__ void k1_rgb2hsv(int r, int g, int b, int& h, int& s, int& v) {
+// OpenCV's division tables: sdiv_table[v] = cvRound((255 << 12) / v), hdiv_table180[d] = cvRound((180 << 12) / (6 d)).
+__host__ __device__ __forceinline__ int k1_hsv_sdiv(int v) { return v ? k1_div_rhe(255 << 12, v) : 0; }
+__host__ __device__ __forceinline__ int k1_hsv_hdiv(int d) { return d ? k1_div_rhe((180 << 12) / 6, d) : 0; }
+
+// `tab`: optional [512] = sdiv_table | hdiv_table180 (the kernel keeps them in shared memory); NULL = compute them.
+__host__ __device__ __forceinline__ void k1_rgb2hsv(int r, int g, int b, int& h, int& s, int& v, const int* tab) {
     v = r > g ? r : g; v = v > b ? v : b;
     int vmin = r < g ? r : g; vmin = vmin < b ? vmin : b;
     const int diff = v - vmin;
-    const int sd = v ? k1_div_rhe(255 << 12, v) : 0;
-    const int hd = diff ? k1_div_rhe((180 << 12) / 6, diff) : 0;
+    const int sd = tab ? tab[v] : k1_hsv_sdiv(v);
+    const int hd = tab ? tab[256 + diff] : k1_hsv_hdiv(diff);
     s = (diff * sd + (1 << 11)) >> 12;
     int hh = (v == r) ? (g - b) : ((v == g) ? (b - r + 2 * diff) : (r - g + 4 * diff));
     hh = (hh * hd + (1 << 11)) >> 12;   // arithmetic shift, as in OpenCV
@@ -99,15 +104,12 @@ __host__ __device__ __forceinline__ void k1_hsv2rgb(int h, int s, int v, bool tr
 #endif
     int sector = (int)pre;
     sector = sector >= 6 ? sector - 6 : sector;
-    float bb, gg, rr;   // sector_data = {1,3,0},{1,0,2},{3,0,1},{0,2,1},{0,1,3},{2,1,0} -> (b, g, r) from tab0..3
-    switch (sector) {
-        case 0: bb = t1; gg = t3; rr = vf; break;
-        case 1: bb = t1; gg = vf; rr = t2; break;
-        case 2: bb = t3; gg = vf; rr = t1; break;
-        case 3: bb = vf; gg = t2; rr = t1; break;
-        case 4: bb = vf; gg = t1; rr = t3; break;
-        default: bb = t2; gg = t1; rr = vf; break;
-    }
+    // sector_data = {1,3,0},{1,0,2},{3,0,1},{0,2,1},{0,1,3},{2,1,0} -> (b, g, r) from tab0..3 (= vf, t1, t2, t3);
+    // written as selects so that the lanes of a warp (which sit in different sectors) do not diverge
+    const float t0 = vf, u1 = t1, u2 = t2, u3 = t3;
+    const float bb = sector <= 1 ? u1 : (sector == 2 ? u3 : (sector == 5 ? u2 : t0));
+    const float gg = sector == 0 ? u3 : (sector <= 2 ? t0 : (sector == 3 ? u2 : u1));
+    const float rr = (sector == 0 || sector == 5) ? t0 : (sector == 1 ? u2 : (sector == 4 ? u3 : u1));
 #ifdef __CUDA_ARCH__
     const float r255 = __fmul_rn(rr, 255.f), g255 = __fmul_rn(gg, 255.f), b255 = __fmul_rn(bb, 255.f);
     const int ri = trunc ? __float2int_rz(r255) : __float2int_rn(r255);
@@ -124,9 +126,10 @@ __host__ __device__ __forceinline__ void k1_hsv2rgb(int h, int s, int v, bool tr
 }
 // lut: [3][256] = hue, sat, val tables of this sample
 template <typename LoadByte>
-__host__ __device__ __forceinline__ void k1_hsv_shift(uint32_t& r, uint32_t& g, uint32_t& b, bool trunc, LoadByte ld) {
+__host__ __device__ __forceinline__ void k1_hsv_shift(uint32_t& r, uint32_t& g, uint32_t& b, bool trunc, LoadByte ld,
+                                                      const int* div_tab = nullptr) {
     int h, s, v;
-    k1_rgb2hsv((int)r, (int)g, (int)b, h, s, v);
+    k1_rgb2hsv((int)r, (int)g, (int)b, h, s, v, div_tab);
     k1_hsv2rgb((int)ld(h), (int)ld(256 + s), (int)ld(512 + v), trunc, r, g, b);
 }
 

@@ -39,6 +39,16 @@ bool launch_k1_fast(const K1Params& p, int jmax, dim3 grid, cudaStream_t st, boo
 template <int JMAX, typename OutT, bool GENERAL, bool WRITE_U8, bool AUG = false>
 __global__ void __launch_bounds__(K1_WARPS * 32) k1_crop_resize_normalize(const K1Params p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // HueSaturationValue: OpenCV's two division tables, built once per CTA (4 integer divisions per thread)
+    __shared__ int hsv_div_tab[AUG ? 512 : 1];
+    __shared__ __align__(16) uint8_t hsv_lut_s[AUG ? K1_WARPS * 768 : 16];   // per warp: the current crop's 3 x 256 tables
+    if (AUG && p.aug_hsv_lut != nullptr) {
+        for (int i = threadIdx.x; i < 256; i += K1_WARPS * 32) {
+            hsv_div_tab[i] = k1_hsv_sdiv(i);
+            hsv_div_tab[256 + i] = k1_hsv_hdiv(i);
+        }
+        __syncthreads();
+    }
     const int y_begin = (blockIdx.y * K1_WARPS + warp) * p.rows_per_warp;
     if (y_begin >= p.out_h) return;
     const int nrows = min(p.rows_per_warp, p.out_h - y_begin);
@@ -46,7 +56,9 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k1_crop_resize_normalize(const 
     for (int crop = blockIdx.x; crop < p.n; crop += gridDim.x) {
         const CropGeom g = load_geom(p, crop);
         k1_process_band<JMAX, OutT, GENERAL, WRITE_U8, AUG>(p, crop, g, y_begin, nrows, ox0,
-                                                            blockIdx.y == 0 && blockIdx.z == 0 && warp == 0);
+                                                            blockIdx.y == 0 && blockIdx.z == 0 && warp == 0,
+                                                            AUG ? hsv_div_tab : nullptr,
+                                                            AUG ? hsv_lut_s + warp * 768 : nullptr);
     }
 }
 
@@ -254,7 +266,7 @@ extern "C" int nkbk_debug_hsv_shift(const uint8_t* rgb_in, int64_t n, const uint
     NKBK_CHECK_ARG(n >= 0 && (n == 0 || (rgb_in && lut768 && rgb_out)), "nkbk_debug_hsv_shift: bad argument");
     for (int64_t i = 0; i < n; ++i) {
         uint32_t r = rgb_in[3 * i], g = rgb_in[3 * i + 1], b = rgb_in[3 * i + 2];
-        k1_hsv_shift(r, g, b, trunc != 0, [&](int k) { return (uint32_t)lut768[k]; });
+        k1_hsv_shift(r, g, b, trunc != 0, [&](int k) { return (uint32_t)lut768[k]; }, nullptr);
         rgb_out[3 * i] = (uint8_t)r; rgb_out[3 * i + 1] = (uint8_t)g; rgb_out[3 * i + 2] = (uint8_t)b;
     }
     return NKBK_OK;

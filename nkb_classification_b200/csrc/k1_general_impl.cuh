@@ -61,7 +61,8 @@ __device__ __forceinline__ void convert_row(uint32_t (&H)[JMAX][3], const RawRow
 // lands on the mirrored rows / columns of the output.
 template <int JMAX, typename OutT, bool GENERAL, bool WRITE_U8, bool AUG = false>
 __device__ __forceinline__ void k1_process_band(const K1Params& p, const int crop, const CropGeom& g, const int y_begin,
-                                                const int nrows, const int ox0, const bool count_bad) {
+                                                const int nrows, const int ox0, const bool count_bad,
+                                                const int* hsv_div_tab = nullptr, uint8_t* hsv_lut_smem = nullptr) {
     static_assert(GENERAL || !WRITE_U8, "uint8 side output only in the general variant");
     static_assert(GENERAL || !AUG, "augmentations only in the general variant");
     const int lane = threadIdx.x & 31;
@@ -96,7 +97,17 @@ __device__ __forceinline__ void k1_process_band(const K1Params& p, const int cro
     const int xd0 = hflip ? p.out_w - 1 - ox0 : ox0;          // destination column of j = 0
     // the colour ops on one pixel, in the reference's order: RandomBrightnessContrast, HueSaturationValue, then the
     // CoarseDropout fill.  px is in OUTPUT channel order (RGB after the optional BGR swap).
-    const uint8_t* hsv_lut = (AUG && (aflags & K1_AUG_HSV)) ? p.aug_hsv_lut + (int64_t)crop * 768 : nullptr;
+    // this crop's hue / sat / val tables: staged once per band in the warp's 768 bytes of shared memory
+    const uint8_t* hsv_lut = nullptr;
+    if (AUG && (aflags & K1_AUG_HSV)) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(p.aug_hsv_lut + (int64_t)crop * 768);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(hsv_lut_smem);
+        __syncwarp();   // the previous crop's readers are done
+#pragma unroll
+        for (int i = 0; i < 6; ++i) dst[lane + 32 * i] = __ldg(src + lane + 32 * i);
+        __syncwarp();
+        hsv_lut = hsv_lut_smem;
+    }
     auto augment3 = [&](uint32_t (&px)[3], bool in_hole, int xd) {   // xd: destination column of the pixel
         if (!AUG) return;
         if (aflags & K1_AUG_BC) {
@@ -104,7 +115,8 @@ __device__ __forceinline__ void k1_process_band(const K1Params& p, const int cro
             for (int c = 0; c < 3; ++c) px[c] = k1_brightness_contrast(px[c], a_alpha, a_beta);
         }
         if (hsv_lut != nullptr)
-            k1_hsv_shift(px[0], px[1], px[2], xd < p.aug_hsv_trunc_cols, [&](int i) { return (uint32_t)__ldg(hsv_lut + i); });
+            k1_hsv_shift(px[0], px[1], px[2], xd < p.aug_hsv_trunc_cols,
+                         [&](int i) { return (uint32_t)hsv_lut[i]; }, hsv_div_tab);
         if (in_hole) { px[0] = p.aug_fill[0]; px[1] = p.aug_fill[1]; px[2] = p.aug_fill[2]; }
     };
     // bit j set: destination column of (lane, j) on destination row yd lies inside a CoarseDropout hole

@@ -499,6 +499,8 @@ class DeviceCropLoader:
             meta = dict(boxes=torch.from_numpy(boxes).to(dev, non_blocking=True),
                         fidx=torch.from_numpy(fidx).to(dev, non_blocking=True),
                         desc=desc.to(dev, non_blocking=True))
+            if aug is not None:
+                ops.upload_augment(aug, dev)      # train pipelines: parameters ride the copy stream too
             slot.copied.record(self._copy_stream)
         meta.update(slot=k, total=total, aug=aug, target=collate_targets([s[2] for s in samples]))
         return meta
@@ -508,7 +510,10 @@ class DeviceCropLoader:
         slot = self._slots[meta["slot"]]
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(slot.copied)
-        for t in (meta["boxes"], meta["fidx"], meta["desc"]):
+        shared = [meta["boxes"], meta["fidx"], meta["desc"]]
+        if meta["aug"] is not None:
+            shared += [t for t in ops.upload_augment(meta["aug"], self.device) if t is not None]
+        for t in shared:
             t.record_stream(cur)                 # allocated on the copy stream, read on this one
         img = ops.preprocess_crops(slot.dev[:meta["total"]], meta["boxes"], meta["fidx"], self.plan,
                                    out_dtype=self.out_dtype, frame_desc=meta["desc"], aug=meta["aug"])

@@ -113,19 +113,8 @@ def preprocess_crops(
     if len(aug.flags) != n:
         raise ValueError(f"augmentation parameters for {len(aug.flags)} samples, batch has {n}")
     dev = frames.device
-    # four small H2D copies (12 + 16 * max_holes bytes per sample); the kernel is enqueued behind them on this stream
-    a_flags = torch.from_numpy(np.ascontiguousarray(aug.flags, dtype=np.int32)).to(dev, non_blocking=True)
-    a_alpha = torch.from_numpy(np.ascontiguousarray(aug.alpha, dtype=np.float32)).to(dev, non_blocking=True)
-    a_beta = torch.from_numpy(np.ascontiguousarray(aug.beta, dtype=np.float32)).to(dev, non_blocking=True)
-    a_holes = torch.from_numpy(np.ascontiguousarray(aug.holes, dtype=np.int32)).to(dev, non_blocking=True)
+    a_flags, a_alpha, a_beta, a_holes, a_hsv = upload_augment(aug, dev)
     fill = (c_uint8 * 3)(*[int(v) for v in aug.fill])
-    a_hsv = None
-    if getattr(aug, "hsv_lut", None) is not None:
-        if aug.hsv_lut.shape != (n, 3, 256) or aug.hsv_lut.dtype != np.uint8:
-            raise ValueError("hsv_lut must be uint8 [n, 3, 256]")
-        a_hsv = torch.from_numpy(np.ascontiguousarray(aug.hsv_lut)).to(dev, non_blocking=True)
-    elif np.any(np.asarray(aug.flags) & 8):
-        raise ValueError("a sample has the HueSaturationValue flag but the batch carries no hsv_lut")
     rc = lib().nkbk_preprocess_crops_aug(
         _ptr(frames), _ptr(frame_desc), n_frames, _ptr(boxes), _ptr(frame_idx), n, plan.mode, plan.out_h, plan.out_w,
         plan.max_size, pad, m, d, int(plan.channel_swap), _ptr(a_flags), _ptr(a_alpha), _ptr(a_beta), _ptr(a_holes),
@@ -134,6 +123,30 @@ def preprocess_crops(
     )
     check(rc)
     return out
+
+
+def upload_augment(aug, device):
+    """Device copies of one batch's augmentation parameters (flags, alpha, beta*255, holes, HSV tables): 12 + 16 *
+    max_holes (+ 768) bytes per sample, uploaded once per batch on the CURRENT stream and cached on the batch object
+    (the loader calls this from its producer thread on the copy stream, so K1 never waits for it)."""
+    dev = torch.device(device)
+    cached = getattr(aug, "_dev", None)
+    if cached is not None and cached[0] == dev:
+        return cached[1]
+    n = len(aug.flags)
+    hsv = None
+    if getattr(aug, "hsv_lut", None) is not None:
+        if aug.hsv_lut.shape != (n, 3, 256) or aug.hsv_lut.dtype != np.uint8:
+            raise ValueError("hsv_lut must be uint8 [n, 3, 256]")
+        hsv = torch.from_numpy(np.ascontiguousarray(aug.hsv_lut)).to(dev, non_blocking=True)
+    elif np.any(np.asarray(aug.flags) & 8):
+        raise ValueError("a sample has the HueSaturationValue flag but the batch carries no hsv_lut")
+    t = (torch.from_numpy(np.ascontiguousarray(aug.flags, dtype=np.int32)).to(dev, non_blocking=True),
+         torch.from_numpy(np.ascontiguousarray(aug.alpha, dtype=np.float32)).to(dev, non_blocking=True),
+         torch.from_numpy(np.ascontiguousarray(aug.beta, dtype=np.float32)).to(dev, non_blocking=True),
+         torch.from_numpy(np.ascontiguousarray(aug.holes, dtype=np.int32)).to(dev, non_blocking=True), hsv)
+    aug._dev = (dev, t)
+    return t
 
 
 def debug_axis_table(dsize: int, ssize: int, horizontal: bool):
