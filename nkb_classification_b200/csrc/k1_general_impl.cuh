@@ -119,6 +119,27 @@ __device__ __forceinline__ void k1_process_band(const K1Params& p, const int cro
                          [&](int i) { return (uint32_t)hsv_lut[i]; }, hsv_div_tab);
         if (in_hole) { px[0] = p.aug_fill[0]; px[1] = p.aug_fill[1]; px[2] = p.aug_fill[2]; }
     };
+    const int trunc_cols = AUG ? p.aug_hsv_trunc_cols : 0;
+    const uint32_t fill0 = p.aug_fill[0], fill1 = p.aug_fill[1], fill2 = p.aug_fill[2];
+    auto augment_row = [&](uint32_t (&P)[JMAX][3], uint32_t hm) {
+        if (aflags & K1_AUG_BC) {
+#pragma unroll
+            for (int j = 0; j < JMAX; ++j)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) P[j][c] = k1_brightness_contrast(P[j][c], a_alpha, a_beta);
+        }
+        if (hsv_lut != nullptr) {
+#pragma unroll
+            for (int j = 0; j < JMAX; ++j)
+                k1_hsv_shift(P[j][0], P[j][1], P[j][2], xd0 + xstep * j < trunc_cols,
+                             [&](int i) { return (uint32_t)hsv_lut[i]; }, hsv_div_tab);
+        }
+        if (hm != 0u) {
+#pragma unroll
+            for (int j = 0; j < JMAX; ++j)
+                if (hm >> j & 1) { P[j][0] = fill0; P[j][1] = fill1; P[j][2] = fill2; }
+        }
+    };
     // bit j set: destination column of (lane, j) on destination row yd lies inside a CoarseDropout hole
     auto hole_mask = [&](int yd) -> uint32_t {
         uint32_t m = 0;
@@ -294,27 +315,32 @@ __device__ __forceinline__ void k1_process_band(const K1Params& p, const int cro
             ib = r1;
         }
 
+        // the row's pixels first, then each colour op over the whole row under ONE warp-uniform test (a test per
+        // element costs a BSSY / BRA / BSYNC triple each), then Normalize + stores
+        uint32_t P[JMAX][3];
 #pragma unroll
         for (int j = 0; j < JMAX; ++j) {
-            uint32_t px[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 const uint32_t t0 = __umulhi(b0, Ha[j][c]);
                 const uint32_t t1 = __umulhi(b1, Hb[j][c]);
-                px[c] = (t0 + t1 + 2u) >> 2;
-                if (GENERAL && !(vmask >> j & 1)) px[c] = p.padu[c];
+                P[j][c] = (t0 + t1 + 2u) >> 2;
+                if (GENERAL && !(vmask >> j & 1)) P[j][c] = p.padu[c];
             }
-            if (AUG) augment3(px, hmask >> j & 1, xd0 + xstep * j);
-            const float f0 = __fmul_rn(__fsub_rn((float)px[0], m0), d0);
-            const float f1 = __fmul_rn(__fsub_rn((float)px[1], m1), d1);
-            const float f2 = __fmul_rn(__fsub_rn((float)px[2], m2), d2);
+        }
+        if (AUG) augment_row(P, hmask);
+#pragma unroll
+        for (int j = 0; j < JMAX; ++j) {
+            const float f0 = __fmul_rn(__fsub_rn((float)P[j][0], m0), d0);
+            const float f1 = __fmul_rn(__fsub_rn((float)P[j][1], m1), d1);
+            const float f2 = __fmul_rn(__fsub_rn((float)P[j][2], m2), d2);
             if (!GENERAL || (wmask >> j & 1)) {
                 const int xs = AUG ? xstep * j : 32 * j;
                 store_out<OutT>(o + xs, f0);
                 store_out<OutT>(o + plane + xs, f1);
                 store_out<OutT>(o + 2 * plane + xs, f2);
                 if (WRITE_U8) {
-                    u[3 * xs + 0] = (uint8_t)px[0]; u[3 * xs + 1] = (uint8_t)px[1]; u[3 * xs + 2] = (uint8_t)px[2];
+                    u[3 * xs + 0] = (uint8_t)P[j][0]; u[3 * xs + 1] = (uint8_t)P[j][1]; u[3 * xs + 2] = (uint8_t)P[j][2];
                 }
             }
         }
