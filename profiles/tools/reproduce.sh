@@ -1,0 +1,35 @@
+#!/usr/bin/env bash
+# How every number under profiles/ was produced (run from the repo root on a B200 box, e.g. through gpurun).
+# Nothing printed under ncu is used as a bench value: the bench lines come from the plain runs.
+set -euo pipefail
+mkdir -p gpurun_out
+
+# --- 1 GPU: default line (value, serial_value, roofline, e2e, cpu_baseline) and the reference arm
+python bench.py                                   > gpurun_out/bench_default.log
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.log
+
+# --- variants: bf16 output + bf16 embeddings (tcgen05 heads), the other BASELINE shapes, letterbox, train pipeline
+python bench.py --out-dtype bf16 --emb-dtype bf16 --steps 50 --warmup 5 --no-cpu-baseline --no-e2e
+for w in cfg3_1080p_20 cfg2_multitask_256 cfg4_vit_5heads cfg1_single_224; do
+  python bench.py --workload $w --steps 50 --warmup 5 --no-cpu-baseline --no-e2e
+done
+python bench.py --resize letterbox --steps 50 --warmup 5 --no-cpu-baseline --no-e2e
+python bench.py --train-aug --steps 50 --warmup 5 --no-cpu-baseline --no-e2e
+python bench.py --train-aug --resize letterbox --steps 50 --warmup 5 --no-cpu-baseline --no-e2e
+
+# --- ncu: launch list (share of the step) and one full capture of the top kernels
+ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches.csv \
+    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e
+ncu --set full --clock-control none --import-source on -k regex:"k1_crop|k2_heads_forward|k2_heads_dw" -c 3 \
+    -o gpurun_out/k1_k2 -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e
+#   read back with:  ncu -i gpurun_out/k1_k2.ncu-rep --page details --csv   (and --page raw / --page source)
+
+# --- N GPUs (one rank per GPU; K4' peer transport by default, --allreduce nccl for the NCCL baseline)
+for n in 2 4 8; do
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29555 \
+      bench.py --gpus $n --steps 100 --warmup 10 > gpurun_out/bench_${n}gpu.log || true
+done
+
+# --- parity
+python -m pytest tests -x -q -m gpu
+python profiles/tools/hsv_gpu_probe.py

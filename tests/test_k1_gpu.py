@@ -255,6 +255,53 @@ def test_k1_full_size_batch_properties(cuda_device):
         assert np.array_equal(u8[f * 64].cpu().numpy(), fn[f][y0:y1, x0:x1])
 
 
+@pytest.mark.parametrize("mode", ["stretch", "letterbox"])
+def test_k1_full_size_letterbox_and_train_pipeline(cuda_device, mode):
+    """BASELINE config 5 shape (4096 crops of 224^2 out of 64 x 1080p frames) through (a) the TMA kernel in the given
+    geometry and (b) the reference's full train pipeline: 64 sampled crops of each against the oracle, bit for bit;
+    size-independent properties on the whole batch: determinism, and `flags = 0` reproducing the val pipeline."""
+    import random
+    from nkb_classification_b200 import transforms as T
+    dev = cuda_device
+    g = torch.Generator(device="cpu").manual_seed(99)
+    frames = torch.randint(0, 256, (64, 1080, 1920, 3), dtype=torch.uint8, generator=g)
+    rng = np.random.default_rng(77)
+    boxes, fidx = [], []
+    for f in range(64):
+        for _ in range(64):
+            w, h = int(rng.integers(48, 481)), int(rng.integers(48, 481))
+            x0, y0 = int(rng.integers(0, 1920 - w + 1)), int(rng.integers(0, 1080 - h + 1))
+            boxes.append((x0, y0, x0 + w, y0 + h))
+            fidx.append(f)
+    fr, fn = frames.to(dev), frames.numpy()
+    pick = sorted(set(rng.integers(0, 4096, 64).tolist()) | {0, 4095})
+    val_plan = make_plan(T, mode=mode)
+    out_val, _ = run_k1(dev, fr, boxes, fidx, val_plan, want_u8=False)            # TMA kernel, both geometries
+    _, ev32 = preprocess_batch_c(fn, [boxes[i] for i in pick], [fidx[i] for i in pick], oracle_plan(val_plan))
+    assert_same_f32(out_val[pick], ev32)
+    geo = ([T.Resize(224, 224)] if mode == "stretch" else
+           [T.LongestMaxSize(224), T.PadIfNeeded(224, 224, border_mode=0, value=0)])
+    plan = T.compile_pipeline(geo + [
+        T.HorizontalFlip(p=0.5), T.VerticalFlip(p=0.5),
+        T.RandomBrightnessContrast(brightness_limit=(-0.2, 0.2), contrast_limit=(0.1, -0.5), p=0.5),
+        T.HueSaturationValue(hue_shift_limit=0, sat_shift_limit=10, val_shift_limit=50, p=0.5),
+        T.CoarseDropout(max_holes=4, min_holes=1, max_height=0.2, min_height=0.05, max_width=0.2, min_width=0.05,
+                        fill_value=[0, 0.5, 1], p=0.5),
+        T.Normalize(MEAN, STD), T.ToTensorV2()])
+    batch = plan.draw(4096, random.Random(5))
+    out1, _ = run_k1(dev, fr, boxes, fidx, plan, want_u8=False, aug=batch)
+    out2, _ = run_k1(dev, fr, boxes, fidx, plan, want_u8=False, aug=batch)
+    assert torch.equal(out1, out2)
+    augs = _aug_samples(batch)
+    _, ef32 = opre.preprocess_batch(fn, [boxes[i] for i in pick], [fidx[i] for i in pick], oracle_plan(plan),
+                                    impl="cv2", augs=[augs[i] for i in pick])
+    assert_same_f32(out1[pick], ef32)
+    ident = plan.draw(4096, random.Random(6))
+    ident.flags[:] = 0
+    out0, _ = run_k1(dev, fr, boxes, fidx, plan, want_u8=False, aug=ident)
+    assert torch.equal(out0, out_val)
+
+
 def test_k1_empty_batch(cuda_device):
     from nkb_classification_b200 import ops, transforms as T
     plan = make_plan(T, out_h=16, out_w=16)
