@@ -6,7 +6,11 @@ namespace nkbk {
 
 constexpr int K2_MAX_TASKS = 64;
 constexpr int K2_MAX_NC = 1024;
-constexpr int K2_FWD_ROWS = 4;     // rows per CTA
+#ifndef NKBK_FWD_ROWS
+#define NKBK_FWD_ROWS 4
+#endif
+constexpr int K2_FWD_ROWS = NKBK_FWD_ROWS;     // rows per warp of the forward / per CTA of the loss-on-logits kernel (2 | 4)
+static_assert(K2_FWD_ROWS == 2 || K2_FWD_ROWS == 4, "the transposing reduction handles 32 or 64 partial sums");
 constexpr int K2_FWD_NCB = 16;     // classes per pass
 #ifndef NKBK_V3_WARPS
 #define NKBK_V3_WARPS 4

@@ -283,17 +283,22 @@ __global__ void __launch_bounds__(K2_V3_WARPS * 32) k2_heads_forward_v3(const K2
                 }
             }
         }
-        // 64 partial sums -> lane L owns entries L and 32 + L  (entry = r * 16 + c)
-        float lo[32], hi[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) { lo[i] = acc[i]; hi[i] = acc[32 + i]; }
-        const float s_lo = warp_reduce_scatter32(lo, lane);
-        const float s_hi = warp_reduce_scatter32(hi, lane);
+        // 32 * (ROWS / 2) partial sums -> lane L owns entry L (and 32 + L with 4 rows)  (entry = r * 16 + c)
         const int c = cb + (lane & 15), r = lane >> 4;
-        if (c < NC) {
-            const float b = __ldg(p.bias + c);
-            zs[r * NC + c] = s_lo + b;
-            zs[(r + 2) * NC + c] = s_hi + b;
+        const float b = c < NC ? __ldg(p.bias + c) : 0.f;
+        {
+            float lo[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) lo[i] = acc[i];
+            const float s_lo = warp_reduce_scatter32(lo, lane);
+            if (c < NC) zs[r * NC + c] = s_lo + b;
+        }
+        if constexpr (K2_FWD_ROWS == 4) {
+            float hi[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) hi[i] = acc[32 + i];
+            const float s_hi = warp_reduce_scatter32(hi, lane);
+            if (c < NC) zs[(r + 2) * NC + c] = s_hi + b;
         }
     }
     if (!active) return;   // (WS: inactive warps only took part in the staging barriers)
