@@ -64,6 +64,17 @@ __device__ __forceinline__ uint32_t vtap(uint32_t b0, uint32_t h0, uint32_t b1, 
     return (__umulhi(b0, h0) + __umulhi(b1, h1) + 2u) >> 2;
 }
 
+// (a - m) * d and (b - m) * d: sub.rn.f32x2 + mul.rn.f32x2 (SASS FADD2 / FMUL2, sm_100); the scalars broadcast.
+__device__ __forceinline__ void normalize2(float a, float b, float m, float d, float& ra, float& rb) {
+    unsigned long long x, mm, dd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a), "f"(b));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(mm) : "f"(m));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(dd) : "f"(d));
+    asm("sub.rn.f32x2 %0, %0, %1;" : "+l"(x) : "l"(mm));
+    asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(x) : "l"(dd));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(ra), "=f"(rb) : "l"(x));
+}
+
 #ifndef K1F_MIN_BLOCKS
 #define K1F_MIN_BLOCKS 4
 #endif
@@ -236,15 +247,27 @@ __global__ void __launch_bounds__(K1_WARPS * 32, K1F_MIN_BLOCKS) k1_crop_resize_
             continue;
         }
         auto vertical = [&](const uint32_t (&Ht)[JMAX][3], const uint32_t (&Hb)[JMAX][3]) {
+            // Normalize two columns per instruction: (v - m) * d as FADD2 + FMUL2 (packed fp32, IEEE round-to-nearest
+            // per half: the same two separately rounded operations, half the issue slots)
+            const float mf[3] = {m0f, m1f, m2f}, df[3] = {d0f, d1f, d2f};
 #pragma unroll
-            for (int j = 0; j < JMAX; ++j) {
-                uint32_t v0 = vtap(b0, Ht[j][0], b1, Hb[j][0]);
-                uint32_t v1 = vtap(b0, Ht[j][1], b1, Hb[j][1]);
-                uint32_t v2 = vtap(b0, Ht[j][2], b1, Hb[j][2]);
-                if (LB && !(vmask >> j & 1)) { v0 = p.padu[0]; v1 = p.padu[1]; v2 = p.padu[2]; }
-                store_out<OutT>(o + 32 * j, __fmul_rn(__fsub_rn((float)v0, m0f), d0f));
-                store_out<OutT>(o + plane + 32 * j, __fmul_rn(__fsub_rn((float)v1, m1f), d1f));
-                store_out<OutT>(o + 2 * plane + 32 * j, __fmul_rn(__fsub_rn((float)v2, m2f), d2f));
+            for (int c = 0; c < 3; ++c) {
+                OutT* oc = o + c * plane;
+#pragma unroll
+                for (int j = 0; j < JMAX; j += 2) {
+                    uint32_t va = vtap(b0, Ht[j][c], b1, Hb[j][c]);
+                    if (LB && !(vmask >> j & 1)) va = p.padu[c];
+                    if (j + 1 < JMAX) {
+                        uint32_t vb = vtap(b0, Ht[j + 1][c], b1, Hb[j + 1][c]);
+                        if (LB && !(vmask >> (j + 1) & 1)) vb = p.padu[c];
+                        float ra, rb;
+                        normalize2((float)va, (float)vb, mf[c], df[c], ra, rb);
+                        store_out<OutT>(oc + 32 * j, ra);
+                        store_out<OutT>(oc + 32 * (j + 1), rb);
+                    } else {
+                        store_out<OutT>(oc + 32 * j, __fmul_rn(__fsub_rn((float)va, mf[c]), df[c]));
+                    }
+                }
             }
         };
         // Ht must hold source row r0, Hb row r1 (r1 == r0 only when the tap is clamped at an edge)
