@@ -63,6 +63,22 @@ __device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
     return v;
 }
 
+// ---- packed fp32 (sm_100 FFMA2): two independent IEEE fused multiply-adds per instruction ------------------------
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+// acc.lo = fma(a.lo, s, acc.lo); acc.hi = fma(a.hi, s, acc.hi)   (the scalar is a broadcast operand in SASS)
+__device__ __forceinline__ void ffma2_bcast(unsigned long long& acc, unsigned long long a, float s) {
+    unsigned long long s2;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(s2) : "f"(s));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(s2));
+}
+
 // Transposing warp reduction: on entry every lane holds 32 partial sums v[0..31];
 // on exit lane L holds in v[0] the warp-wide total of partial sum number L.
 __device__ __forceinline__ float warp_reduce_scatter32(float (&v)[32], int lane) {
@@ -223,9 +239,14 @@ __global__ void __launch_bounds__(K2_V3_WARPS * 32) k2_heads_forward_v3(const K2
     const int nchunks = (D + 127) / 128;
 
     for (int cb = 0; cb < NC; cb += K2_FWD_NCB) {
-        float acc[K2_FWD_ROWS * K2_FWD_NCB];
+        // accumulators as fp32 pairs over adjacent rows: acc2[rp][c] = (row 2 rp, row 2 rp + 1) of class c; one FFMA2
+        // per (row pair, class, k) with the weight as the broadcast operand -- per accumulator the same chain of IEEE
+        // fmas (k ascending) as the scalar form, in half the instructions
+        unsigned long long acc2[K2_FWD_ROWS / 2][K2_FWD_NCB];
 #pragma unroll
-        for (int i = 0; i < K2_FWD_ROWS * K2_FWD_NCB; ++i) acc[i] = 0.f;
+        for (int rp = 0; rp < K2_FWD_ROWS / 2; ++rp)
+#pragma unroll
+            for (int i = 0; i < K2_FWD_NCB; ++i) acc2[rp][i] = 0ull;
         float4 e[K2_V3_PD][K2_FWD_ROWS];
         auto load_chunk = [&](float4 (&dst)[K2_FWD_ROWS], int chunk) {
             const int k = chunk * 128 + lane * 4;
@@ -255,6 +276,14 @@ __global__ void __launch_bounds__(K2_V3_WARPS * 32) k2_heads_forward_v3(const K2
                 const int chunk = c0 + u;
                 if (chunk < nchunks) {  // warp-uniform
                     const int k = min(chunk * 128 + lane * 4, D - 4);  // lanes past D hold zeros in e: any valid W address
+                    unsigned long long ex[K2_FWD_ROWS / 2], ey[K2_FWD_ROWS / 2], ez[K2_FWD_ROWS / 2], ew[K2_FWD_ROWS / 2];
+#pragma unroll
+                    for (int rp = 0; rp < K2_FWD_ROWS / 2; ++rp) {
+                        ex[rp] = pack_f32x2(e[u][2 * rp].x, e[u][2 * rp + 1].x);
+                        ey[rp] = pack_f32x2(e[u][2 * rp].y, e[u][2 * rp + 1].y);
+                        ez[rp] = pack_f32x2(e[u][2 * rp].z, e[u][2 * rp + 1].z);
+                        ew[rp] = pack_f32x2(e[u][2 * rp].w, e[u][2 * rp + 1].w);
+                    }
 #pragma unroll
                     for (int ch = 0; ch < K2_FWD_NCB; ch += 8) {
                         if (cb + ch >= NC) break;  // warp-uniform
@@ -268,13 +297,11 @@ __global__ void __launch_bounds__(K2_V3_WARPS * 32) k2_heads_forward_v3(const K2
                         for (int c = 0; c < 8; ++c) {
                             if (cb + ch + c < NC) {  // warp-uniform: padded classes skip their FFMAs
 #pragma unroll
-                                for (int r = 0; r < K2_FWD_ROWS; ++r) {
-                                    float a = acc[r * K2_FWD_NCB + ch + c];
-                                    a = fmaf(e[u][r].x, w[c].x, a);
-                                    a = fmaf(e[u][r].y, w[c].y, a);
-                                    a = fmaf(e[u][r].z, w[c].z, a);
-                                    a = fmaf(e[u][r].w, w[c].w, a);
-                                    acc[r * K2_FWD_NCB + ch + c] = a;
+                                for (int rp = 0; rp < K2_FWD_ROWS / 2; ++rp) {
+                                    ffma2_bcast(acc2[rp][ch + c], ex[rp], w[c].x);
+                                    ffma2_bcast(acc2[rp][ch + c], ey[rp], w[c].y);
+                                    ffma2_bcast(acc2[rp][ch + c], ez[rp], w[c].z);
+                                    ffma2_bcast(acc2[rp][ch + c], ew[rp], w[c].w);
                                 }
                             }
                         }
@@ -283,6 +310,12 @@ __global__ void __launch_bounds__(K2_V3_WARPS * 32) k2_heads_forward_v3(const K2
                 }
             }
         }
+        float acc[K2_FWD_ROWS * K2_FWD_NCB];
+#pragma unroll
+        for (int rp = 0; rp < K2_FWD_ROWS / 2; ++rp)
+#pragma unroll
+            for (int i = 0; i < K2_FWD_NCB; ++i)
+                unpack_f32x2(acc2[rp][i], acc[(2 * rp) * K2_FWD_NCB + i], acc[(2 * rp + 1) * K2_FWD_NCB + i]);
         // 32 * (ROWS / 2) partial sums -> lane L owns entry L (and 32 + L with 4 rows)  (entry = r * 16 + c)
         const int c = cb + (lane & 15), r = lane >> 4;
         const float b = c < NC ? __ldg(p.bias + c) : 0.f;
@@ -387,23 +420,23 @@ __global__ void __launch_bounds__(K2_DW_WARPS * 32, 16 / K2_DW_WARPS) k2_heads_d
     }
     __syncthreads();
 
-    float acc[NCP][4];
+    // accumulators as fp32 pairs: acc2[c][0] = columns (k0, k0+1), acc2[c][1] = (k0+2, k0+3); one FFMA2 (packed fp32
+    // FMA, sm_100) updates a pair with the dlogit broadcast -- the same IEEE fma per column, half the instructions
+    unsigned long long acc2[NCP][2];
 #pragma unroll
-    for (int c = 0; c < NCP; ++c) acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f;
+    for (int c = 0; c < NCP; ++c) acc2[c][0] = acc2[c][1] = 0ull;
     auto consume = [&](const float4 (&src)[RB], int r_start) {   // rows past r_hi hold e = 0 (and dl = 0)
 #pragma unroll
         for (int i = 0; i < RB; ++i) {
-            const float4 e = src[i];
+            const unsigned long long e01 = pack_f32x2(src[i].x, src[i].y), e23 = pack_f32x2(src[i].z, src[i].w);
 #pragma unroll
             for (int c4 = 0; c4 < NCP; c4 += 4) {
                 const float4 g = *reinterpret_cast<const float4*>(&dl[r_start + i][c4]);
                 const float gg[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    acc[c4 + q][0] = fmaf(gg[q], e.x, acc[c4 + q][0]);
-                    acc[c4 + q][1] = fmaf(gg[q], e.y, acc[c4 + q][1]);
-                    acc[c4 + q][2] = fmaf(gg[q], e.z, acc[c4 + q][2]);
-                    acc[c4 + q][3] = fmaf(gg[q], e.w, acc[c4 + q][3]);
+                    ffma2_bcast(acc2[c4 + q][0], e01, gg[q]);
+                    ffma2_bcast(acc2[c4 + q][1], e23, gg[q]);
                 }
             }
         }
@@ -414,6 +447,12 @@ __global__ void __launch_bounds__(K2_DW_WARPS * 32, 16 / K2_DW_WARPS) k2_heads_d
         if (b + 2 < 32 / RB) load_batch(eb[0], r_lo + (b + 2) * RB);
         consume(eb[1], r_lo + (b + 1) * RB);
         if (b + 3 < 32 / RB) load_batch(eb[1], r_lo + (b + 3) * RB);
+    }
+    float acc[NCP][4];
+#pragma unroll
+    for (int c = 0; c < NCP; ++c) {
+        unpack_f32x2(acc2[c][0], acc[c][0], acc[c][1]);
+        unpack_f32x2(acc2[c][1], acc[c][2], acc[c][3]);
     }
     // db partial of this chunk (column block 0 only), before dl is overwritten
     if (blockIdx.x == 0 && threadIdx.x < ncls) {
