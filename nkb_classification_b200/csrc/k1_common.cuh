@@ -71,13 +71,17 @@ __host__ __device__ __forceinline__ int k1_div_rhe(int n, int d) {  // round-hal
 __host__ __device__ __forceinline__ int k1_hsv_sdiv(int v) { return v ? k1_div_rhe(255 << 12, v) : 0; }
 __host__ __device__ __forceinline__ int k1_hsv_hdiv(int d) { return d ? k1_div_rhe((180 << 12) / 6, d) : 0; }
 
-// `tab`: optional [512] = sdiv_table | hdiv_table180 (the kernel keeps them in shared memory); NULL = compute them.
+// `tab`: [512] = sdiv_table | hdiv_table180 (the kernel keeps them in shared memory); on the host NULL = compute them.
 __host__ __device__ __forceinline__ void k1_rgb2hsv(int r, int g, int b, int& h, int& s, int& v, const int* tab) {
     v = r > g ? r : g; v = v > b ? v : b;
     int vmin = r < g ? r : g; vmin = vmin < b ? vmin : b;
     const int diff = v - vmin;
+#ifdef __CUDA_ARCH__
+    const int sd = tab[v], hd = tab[256 + diff];          // device callers always pass the tables
+#else
     const int sd = tab ? tab[v] : k1_hsv_sdiv(v);
     const int hd = tab ? tab[256 + diff] : k1_hsv_hdiv(diff);
+#endif
     s = (diff * sd + (1 << 11)) >> 12;
     int hh = (v == r) ? (g - b) : ((v == g) ? (b - r + 2 * diff) : (r - g + 4 * diff));
     hh = (hh * hd + (1 << 11)) >> 12;   // arithmetic shift, as in OpenCV
