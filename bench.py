@@ -191,7 +191,7 @@ def workload_config(wl, out_dtype, n_gpus, transport="peer"):
         "frames_per_gpu": wl.frames, "frame": f"{wl.frame_w}x{wl.frame_h}x3 u8", "boxes_per_frame": wl.boxes_per_frame,
         "crops_per_gpu_per_step": wl.crops, "out": f"3x{wl.out_size}x{wl.out_size} {out_dtype}", "resize": wl.mode,
         "emb_dim": wl.emb_dim, "heads": list(wl.classes), "loss": wl.loss, "gamma": wl.gamma,
-        "train_aug": bool(getattr(wl, "train_aug", False)),
+        "train_aug": wl.train_aug,
         "backbone": "excluded (out of scope; synthetic embeddings)",
         "l2": "inputs larger than L2 (frames + output >> 126 MB per step); no flush needed",
         "parallelism": f"dp{n_gpus} (frames sharded per rank; head grads + confusion counts all-reduced by "
@@ -470,8 +470,7 @@ def main():
         wl = dataclasses.replace(wl, mode=args.resize, name=f"{wl.name}.{args.resize}")
     if args.train_aug:
         import dataclasses
-        wl = dataclasses.replace(wl, name=f"{wl.name}.train_aug")
-        object.__setattr__(wl, "train_aug", True)
+        wl = dataclasses.replace(wl, name=f"{wl.name}.train_aug", train_aug=True)
     if args.impl == "reference":
         run_reference(args, wl)
     else:

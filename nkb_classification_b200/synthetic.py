@@ -29,6 +29,7 @@ class Workload:
     loss: str              # "FocalLoss" | "CrossEntropyLoss"
     gamma: float
     whole_image: bool = False   # box = full frame (configs 1, 2)
+    train_aug: bool = False     # K1 with the reference's train-time augmentations fused (bench --train-aug)
 
     @property
     def crops(self) -> int:
