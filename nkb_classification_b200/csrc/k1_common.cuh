@@ -148,6 +148,17 @@ __device__ __forceinline__ void store_out<__nv_bfloat16>(__nv_bfloat16* p, float
     __stcs(reinterpret_cast<unsigned short*>(p), __bfloat16_as_ushort(__float2bfloat16_rn(v)));
 }
 
+// (a - m) * d and (b - m) * d: sub.rn.f32x2 + mul.rn.f32x2 (SASS FADD2 / FMUL2, sm_100); the scalars broadcast.
+__device__ __forceinline__ void normalize2(float a, float b, float m, float d, float& ra, float& rb) {
+    unsigned long long x, mm, dd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a), "f"(b));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(mm) : "f"(m));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(dd) : "f"(d));
+    asm("sub.rn.f32x2 %0, %0, %1;" : "+l"(x) : "l"(mm));
+    asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(x) : "l"(dd));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(ra), "=f"(rb) : "l"(x));
+}
+
 struct CropGeom {
     int bx0, by0, bw, bh, fw, fh;
     int64_t f_off, pitch;

@@ -64,17 +64,6 @@ __device__ __forceinline__ uint32_t vtap(uint32_t b0, uint32_t h0, uint32_t b1, 
     return (__umulhi(b0, h0) + __umulhi(b1, h1) + 2u) >> 2;
 }
 
-// (a - m) * d and (b - m) * d: sub.rn.f32x2 + mul.rn.f32x2 (SASS FADD2 / FMUL2, sm_100); the scalars broadcast.
-__device__ __forceinline__ void normalize2(float a, float b, float m, float d, float& ra, float& rb) {
-    unsigned long long x, mm, dd;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a), "f"(b));
-    asm("mov.b64 %0, {%1, %1};" : "=l"(mm) : "f"(m));
-    asm("mov.b64 %0, {%1, %1};" : "=l"(dd) : "f"(d));
-    asm("sub.rn.f32x2 %0, %0, %1;" : "+l"(x) : "l"(mm));
-    asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(x) : "l"(dd));
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(ra), "=f"(rb) : "l"(x));
-}
-
 #ifndef K1F_MIN_BLOCKS
 #define K1F_MIN_BLOCKS 4
 #endif
