@@ -50,6 +50,9 @@ def parse_args():
                          "parameters are drawn once on the host before the timed region")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay of the step")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the fixed-global-batch (strong scaling) leg")
+    ap.add_argument("--no-variants", action="store_true", help="N = 1: skip the other named configurations")
     return ap.parse_args()
 
 
@@ -197,21 +200,215 @@ def workload_config(wl, out_dtype, n_gpus, transport="peer"):
         "parallelism": f"dp{n_gpus} (frames sharded per rank; head grads + confusion counts all-reduced by "
                        + ("one fused push/sum/finalize kernel over NVLink peer memory, K4')" if transport == "peer"
                           else "NCCL, K4)"),
-        "pipelining": "value: K1 (stream A) overlaps K2/K3/K4 of another batch (stream B, higher priority), no dependency "
-                      "without the backbone; serial_value: one stream, K1 -> K2 -> K3 -> K4 back to back",
+        "launches_per_step": "2: K1, then the fused heads step (forward + loss + K3 + dW/db + exchange + finalize)",
+        "timing": "value = the faster of { eager launches on one stream, the same step replayed from a CUDA graph }; "
+                  "serial_value = eager; median of 3 repetitions of exactly K steps",
     }
 
 
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+REPS = 3   # every timed region = `reps` repetitions of exactly K steps, each bracketed by barrier + sync; the median counts
+
+
+def _plan_for(wl, train_aug):
+    from nkb_classification_b200 import transforms as T
+    geo = ([T.Resize(wl.out_size, wl.out_size)] if wl.mode == "stretch" else
+           [T.LongestMaxSize(wl.out_size), T.PadIfNeeded(wl.out_size, wl.out_size, border_mode=T.BORDER_CONSTANT, value=0)])
+    aug_ops = []
+    if train_aug:
+        aug_ops = [T.HorizontalFlip(p=0.5), T.VerticalFlip(p=0.5),
+                   T.RandomBrightnessContrast(brightness_limit=(-0.2, 0.2), contrast_limit=(0.1, -0.5), p=0.5),
+                   T.HueSaturationValue(hue_shift_limit=0, sat_shift_limit=10, val_shift_limit=50, p=0.5),
+                   T.CoarseDropout(max_holes=4, min_holes=1, max_height=0.2, min_height=0.05, max_width=0.2,
+                                   min_width=0.05, fill_value=[0, 0.5, 1], p=0.5)]
+    return T.compile_pipeline(geo + aug_ops + [T.Normalize(MEAN, STD), T.ToTensorV2()])
+
+
+class Leg:
+    """One workload instance on one rank: synthetic inputs resident in HBM + the HotPath that steps over them."""
+
+    def __init__(self, wl, dev, comm, out_dtype, emb_dtype, transport, train_aug=False, seed_rank=0, frame_range=None):
+        import torch
+        from nkb_classification_b200 import hotpath
+        from nkb_classification_b200.synthetic import synth_boxes
+        self.wl, self.dev = wl, dev
+        self.plan = _plan_for(wl, train_aug)
+        self.hp = hotpath.HotPath(self.plan, wl.classes, wl.emb_dim, wl.loss, wl.gamma, device=dev, comm=comm,
+                                  out_dtype=out_dtype, transport=transport)
+        g = torch.Generator(device=dev).manual_seed(1234 + seed_rank)
+        frames = torch.randint(0, 256, (wl.frames, wl.frame_h, wl.frame_w, 3), dtype=torch.uint8, device=dev, generator=g)
+        boxes_np, fidx_np = synth_boxes(wl, seed=4321 + seed_rank)
+        gc = torch.Generator().manual_seed(7 + seed_rank)
+        n_all = len(fidx_np)
+        emb = torch.randn(n_all, wl.emb_dim, generator=gc)
+        labels = torch.stack([torch.randint(0, c, (n_all,), generator=gc) for c in wl.classes], 1).contiguous()
+        if frame_range is not None:   # strong scaling: this rank's contiguous shard of the frames (and of their crops)
+            fb, fe = frame_range
+            mask = (fidx_np >= fb) & (fidx_np < fe)
+            frames = frames[fb:fe].contiguous()
+            boxes_np, fidx_np = boxes_np[mask], (fidx_np[mask] - fb).astype(np.int32)
+            m = torch.from_numpy(mask)
+            emb, labels = emb[m].contiguous(), labels[m].contiguous()
+        self.frames, self.boxes_np, self.fidx_np = frames, boxes_np, fidx_np
+        self.n = len(fidx_np)
+        self.boxes = torch.from_numpy(np.ascontiguousarray(boxes_np)).to(dev)
+        self.fidx = torch.from_numpy(np.ascontiguousarray(fidx_np)).to(dev)
+        self.emb = emb.to(dev).to(emb_dtype).contiguous()
+        self.labels_h = labels
+        self.labels = labels.to(dev)
+        Ws, bs = make_heads(wl)
+        self.W_cat, self.b_cat = torch.cat(Ws).contiguous().to(dev), torch.cat(bs).contiguous().to(dev)
+        self.aug = None
+        if train_aug:
+            import random as _random
+            self.aug = self.plan.draw(self.n, _random.Random(99 + seed_rank))
+
+    def k1(self, frames=None, boxes=None, fidx=None):
+        return self.hp.preprocess(self.frames if frames is None else frames, self.boxes if boxes is None else boxes,
+                                  self.fidx if fidx is None else fidx, None, self.aug)
+
+    def heads(self, labels=None):
+        return self.hp.heads_step(self.emb, self.W_cat, self.b_cat, self.labels if labels is None else labels, train=True)
+
+    def step(self):
+        self.k1()
+        return self.heads()
+
+
+def _timed(fn_k_steps, barrier, world, dev, reps=REPS):
+    """`fn_k_steps()` enqueues exactly K steps.  Returns the median over `reps` of (max over ranks of the device time)."""
+    import torch
+    import torch.distributed as dist
+    out = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        fn_k_steps()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out.append(float(t.item()))
+    return float(np.median(out)), out
+
+
+def _capture(leg, dev):
+    """One step (K1 -> fused heads step) as a CUDA graph on a side stream; None when capture is not possible."""
+    import torch
+    try:
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            leg.step()
+        torch.cuda.current_stream(dev).wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            leg.step()
+        torch.cuda.synchronize()
+        return g
+    except Exception as e:   # pragma: no cover
+        sys.stderr.write(f"[bench] CUDA graph capture failed ({e!r}); graph numbers omitted\n")
+        return None
+
+
+def _measure_leg(leg, steps, barrier, world, dev, use_graph=True):
+    """serial (eager launches, one stream), graph (the same step replayed from a CUDA graph) and per-kernel K1 time."""
+    import torch
+    from nkb_classification_b200 import _lib, ops
+    for _ in range(3):
+        leg.step()
+    barrier()
+    k1_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+
+    def eager():
+        for i in range(steps):
+            k1_ev[i][0].record()
+            leg.k1()
+            k1_ev[i][1].record()
+            leg.heads()
+
+    l0 = _lib.launch_count()
+    serial_ms, serial_all = _timed(eager, barrier, world, dev)
+    launches = (_lib.launch_count() - l0) // REPS
+    k1_ms = float(np.mean([a.elapsed_time(b) for a, b in k1_ev]))
+    path = ops.heads_last_path()
+    out = {"serial_ms": serial_ms / steps, "serial_all_ms": [t / steps for t in serial_all], "k1_ms": k1_ms,
+           "launches": int(launches), "heads_path": {_lib.PATH_FUSED: "k2_fused_step (1 launch)",
+                                                     _lib.PATH_TC_FWD: "k2_tc_heads_forward + k2_heads_dw + finalize",
+                                                     _lib.PATH_FFMA_FWD: "k2_heads_forward_v3 + k2_heads_dw + finalize"}.get(path, str(path))}
+    g = _capture(leg, dev) if use_graph else None
+    if g is not None:
+        def replay():
+            for _ in range(steps):
+                g.replay()
+        replay()
+        graph_ms, graph_all = _timed(replay, barrier, world, dev)
+        out.update(graph_ms=graph_ms / steps, graph_all_ms=[t / steps for t in graph_all])
+    return out
+
+
+def _unique_source_bytes(boxes_np, fidx_np, wl):
+    """Bytes of the UNION of the boxes of every frame (what HBM has to deliver at least once when L2 serves the overlaps)."""
+    total = 0
+    for f in np.unique(fidx_np):
+        m = np.zeros((wl.frame_h, wl.frame_w), dtype=bool)
+        for x0, y0, x1, y1 in boxes_np[fidx_np == f]:
+            m[y0:y1, x0:x1] = True
+        total += int(m.sum()) * 3
+    return total
+
+
+def _parity_check(leg_sharded, wl, dev, rank, world, out_dtype, emb_dtype):
+    """N > 1: one sharded heads step must equal rank 0's single-GPU step over the WHOLE global batch (loss and mean
+    gradients to 1e-5, confusion counts exactly), and K1 of the shard must equal the same rows of rank 0's K1 output."""
+    import torch
+    import torch.distributed as dist
+    from nkb_classification_b200.parallel import Communicator
+    hp = leg_sharded.hp
+    hp.reset_confusion()
+    img = leg_sharded.k1().clone()
+    bufs = leg_sharded.heads()
+    torch.cuda.synchronize()
+    mine = torch.cat([bufs.reduce_buf[: hp.NC * hp.D + hp.NC].double(), bufs.loss.double()])
+    cm_mine = hp.cm.clone()
+    hp.reset_confusion()
+    ref = torch.zeros_like(mine)
+    cm_ref = torch.zeros_like(cm_mine)
+    ok_img = 1.0
+    if rank == 0:
+        full = Leg(wl, dev, Communicator(), out_dtype, emb_dtype, "peer")
+        img_full = full.k1()
+        b = full.heads()
+        torch.cuda.synchronize()
+        ref = torch.cat([b.reduce_buf[: hp.NC * hp.D + hp.NC].double(), b.loss.double()])
+        cm_ref = full.hp.cm.clone()
+        if leg_sharded.aug is None:   # (augmentation draws depend on the batch length: compared without them only)
+            ok_img = float(torch.equal(img_full[: img.shape[0]], img))     # rank 0 owns the first frames
+        del full, img_full
+    dist.broadcast(ref, 0)
+    dist.broadcast(cm_ref, 0)
+    err = float(((mine - ref).abs().max() / ref.abs().max().clamp_min(1e-30)).item())
+    ok = float(err <= 1e-5 and bool(torch.equal(cm_mine, cm_ref))) * ok_img
+    t = torch.tensor([ok, -err], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return {"status": "ok" if t[0].item() == 1.0 else "MISMATCH", "max_rel_err": float(-t[1].item()),
+            "checked": "sharded loss / dW / db vs rank 0's single-GPU step over the global batch (1e-5), confusion counts "
+                       "exact, K1 output of rank 0's shard bit-exact"}
+
+
 def run_b200(args, wl):
+    import dataclasses
     import torch
     import torch.distributed as dist
 
-    from nkb_classification_b200 import _lib, hotpath, ops, transforms as T
-    from nkb_classification_b200.parallel import Communicator
-    from nkb_classification_b200.synthetic import k1_algorithmic_bytes, synth_boxes
+    from nkb_classification_b200 import _lib
+    from nkb_classification_b200.parallel import Communicator, shard_range
+    from nkb_classification_b200.synthetic import WORKLOADS, k1_algorithmic_bytes
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -238,143 +435,80 @@ def run_b200(args, wl):
         dist.init_process_group("nccl", device_id=dev)
         comm.init_from_torch_distributed(dev)
 
-    out_dtype = torch.float32 if args.out_dtype == "f32" else torch.bfloat16
-    geo = ([T.Resize(wl.out_size, wl.out_size)] if wl.mode == "stretch" else
-           [T.LongestMaxSize(wl.out_size), T.PadIfNeeded(wl.out_size, wl.out_size, border_mode=T.BORDER_CONSTANT, value=0)])
-    aug_ops = []
-    if args.train_aug:
-        aug_ops = [T.HorizontalFlip(p=0.5), T.VerticalFlip(p=0.5),
-                   T.RandomBrightnessContrast(brightness_limit=(-0.2, 0.2), contrast_limit=(0.1, -0.5), p=0.5),
-                   T.HueSaturationValue(hue_shift_limit=0, sat_shift_limit=10, val_shift_limit=50, p=0.5),
-                   T.CoarseDropout(max_holes=4, min_holes=1, max_height=0.2, min_height=0.05, max_width=0.2,
-                                   min_width=0.05, fill_value=[0, 0.5, 1], p=0.5)]
-    plan = T.compile_pipeline(geo + aug_ops + [T.Normalize(MEAN, STD), T.ToTensorV2()])
-    hp = hotpath.HotPath(plan, wl.classes, wl.emb_dim, wl.loss, wl.gamma, device=dev, comm=comm, out_dtype=out_dtype,
-                         transport=args.allreduce)
-
-    # ---- synthetic inputs, generated on the device, seeded per rank ----
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    frames = torch.randint(0, 256, (wl.frames, wl.frame_h, wl.frame_w, 3), dtype=torch.uint8, device=dev, generator=g)
-    boxes_np, fidx_np = synth_boxes(wl, seed=4321 + rank)
-    n = len(fidx_np)
-    boxes = torch.from_numpy(boxes_np).to(dev)
-    fidx = torch.from_numpy(fidx_np).to(dev)
-    gc = torch.Generator().manual_seed(7 + rank)
-    emb = torch.randn(n, wl.emb_dim, generator=gc).to(dev)
-    if args.emb_dtype == "bf16":
-        emb = emb.to(torch.bfloat16)
-    labels_h = torch.stack([torch.randint(0, c, (n,), generator=gc) for c in wl.classes], 1).contiguous()
-    labels = labels_h.to(dev)
-    Ws, bs = make_heads(wl)
-    W_cat, b_cat = torch.cat(Ws).contiguous().to(dev), torch.cat(bs).contiguous().to(dev)
-
-    aug = None
-    if args.train_aug:
-        import random as _random
-        aug = plan.draw(n, _random.Random(99 + rank))
-        _pre = hp.preprocess
-        hp.preprocess = lambda fr, bx, fi, frame_desc=None: _pre(fr, bx, fi, frame_desc, aug)   # same call sites below
-
-    def step():
-        hp.preprocess(frames, boxes, fidx)
-        return hp.heads_step(emb, W_cat, b_cat, labels, train=True)
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-
-    # ---- timed region 1: inputs resident in HBM ----
+    out_dtype = torch.float32 if args.out_dtype == "f32" else torch.bfloat16
+    emb_dtype = torch.float32 if args.emb_dtype == "f32" else torch.bfloat16
+    steps = args.steps
     sampler = ClockSampler(local_rank)
-    k1_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = _lib.launch_count()
+
+    # ---- weak leg (the headline): every rank owns wl.frames frames; inputs resident in HBM ----
+    leg = Leg(wl, dev, comm, out_dtype, emb_dtype, args.allreduce, train_aug=args.train_aug, seed_rank=rank)
+    n = leg.n
+    for _ in range(max(args.warmup, 3)):
+        leg.step()
+    barrier()
     sampler.start()
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        k1_ev[i][0].record()
-        hp.preprocess(frames, boxes, fidx)
-        k1_ev[i][1].record()
-        hp.heads_step(emb, W_cat, b_cat, labels, train=True)
-    e1.record()
-    barrier()
+    m = _measure_leg(leg, steps, barrier, world, dev, use_graph=not args.no_graph)
     sampler.stop()
-    launches = _lib.launch_count() - launches0
-    dt_ms = e0.elapsed_time(e1)
-    k1_ms = float(np.mean([a.elapsed_time(b) for a, b in k1_ev]))
-    tmax = torch.tensor([dt_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    dt_ms_max = float(tmax.item())
-    serial_value = world * n * args.steps / (dt_ms_max * 1e-3)
-    serial_ms = dt_ms_max / args.steps
+    best_ms = min(m["serial_ms"], m.get("graph_ms", float("inf")))
+    value = world * n / (best_ms * 1e-3)
+    serial_value = world * n / (m["serial_ms"] * 1e-3)
 
-    # ---- timed region 1b: the same K steps software-pipelined on two streams ----
-    # K1 of a batch and K2/K3/K4 of another batch have no data dependency (the backbone sits between them and is
-    # out of scope here), so a real loop runs preprocessing of batch i+1 while the heads/loss/metric of batch i
-    # execute.  All work of all K steps still happens inside the timed region; both streams are joined before e1.
-    # The heads stream has the higher priority: its short kernels take SM slots as K1's CTAs retire instead of queueing
-    # behind the whole K1 grid, so K2/K3/K4 of a batch really run under the K1 of the next one.
-    prio = os.environ.get("NKBK_BENCH_HEADS_PRIORITY", "high")   # experiment knob: high | same | low
-    s_pre = torch.cuda.Stream(device=dev, priority=-1 if prio == "low" else 0)
-    s_heads = torch.cuda.Stream(device=dev, priority=-1 if prio == "high" else 0)
-    cur = torch.cuda.current_stream(dev)
+    # ---- strong leg (N > 1): the SAME global batch as one GPU's step, frames sharded contiguously over the ranks ----
+    strong, parity = None, None
+    if world > 1 and not args.no_strong:
+        fb, fe = shard_range(wl.frames, rank, world)
+        sleg = Leg(wl, dev, comm, out_dtype, emb_dtype, args.allreduce, train_aug=args.train_aug, seed_rank=0,
+                   frame_range=(fb, fe))
+        parity = _parity_check(sleg, wl, dev, rank, world, out_dtype, emb_dtype)
+        sm_ = _measure_leg(sleg, steps, barrier, world, dev, use_graph=not args.no_graph)
+        # the 1-GPU time of the same global batch, measured in this very run on rank 0 while the others wait
+        t1 = torch.zeros(1, dtype=torch.float64, device=dev)
+        if rank == 0:
+            full = Leg(wl, dev, Communicator(), out_dtype, emb_dtype, "peer", train_aug=args.train_aug, seed_rank=0)
+            fm = _measure_leg(full, steps, lambda: torch.cuda.synchronize(), 1, dev, use_graph=not args.no_graph)
+            t1[0] = min(fm["serial_ms"], fm.get("graph_ms", float("inf")))
+            del full
+        dist.broadcast(t1, 0)
+        s_ms = min(sm_["serial_ms"], sm_.get("graph_ms", float("inf")))
+        gb = wl.crops
+        strong = {"global_batch": gb, "crops_per_rank": sleg.n, "value": gb / (s_ms * 1e-3), "ms_per_step": s_ms,
+                  "serial_ms_per_step": sm_["serial_ms"], "graph_ms_per_step": sm_.get("graph_ms"),
+                  "k1_ms": sm_["k1_ms"], "n1_ms_per_step": float(t1.item()),
+                  "speedup_vs_n1": float(t1.item()) / s_ms, "efficiency_vs_n1": float(t1.item()) / s_ms / world,
+                  "heads_path": sm_["heads_path"], "gpu_launches_per_step": sm_["launches"] // steps,
+                  "note": "fixed global batch = one GPU's step; frames sharded contiguously (parallel.shard_range); "
+                          "n1 = the same batch on rank 0 alone, timed in this run"}
+        del sleg
 
-    def pipelined(k):
-        s_pre.wait_stream(cur)
-        s_heads.wait_stream(cur)
-        for _ in range(k):
-            with torch.cuda.stream(s_pre):
-                hp.preprocess(frames, boxes, fidx)
-            with torch.cuda.stream(s_heads):
-                hp.heads_step(emb, W_cat, b_cat, labels, train=True)
-        cur.wait_stream(s_pre)
-        cur.wait_stream(s_heads)
-
-    pipelined(3)
-    barrier()
-    launches0 = _lib.launch_count()
-    sampler.start()
-    barrier()
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    p0.record()
-    pipelined(args.steps)
-    p1.record()
-    barrier()
-    sampler.stop()
-    launches = _lib.launch_count() - launches0
-    tp = torch.tensor([p0.elapsed_time(p1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
-    dt_ms_max = float(tp.item())
-    value = world * n * args.steps / (dt_ms_max * 1e-3)
-
-    # ---- timed region 2: end to end from pinned host memory through the public API ----
+    # ---- end to end from pinned host memory through the public API ----
     e2e = None
     if not args.no_e2e:
-        frames_h = torch.empty(frames.shape, dtype=torch.uint8).pin_memory()
-        frames_h.copy_(frames)
-        boxes_h = torch.from_numpy(boxes_np).pin_memory()
-        fidx_h = torch.from_numpy(fidx_np).pin_memory()
-        labels_p = labels_h.pin_memory()
+        cur = torch.cuda.current_stream(dev)
+        hp = leg.hp
+        frames_h = torch.empty(leg.frames.shape, dtype=torch.uint8).pin_memory()
+        frames_h.copy_(leg.frames)
+        boxes_h = torch.from_numpy(np.ascontiguousarray(leg.boxes_np)).pin_memory()
+        fidx_h = torch.from_numpy(np.ascontiguousarray(leg.fidx_np)).pin_memory()
+        labels_p = leg.labels_h.pin_memory()
         loss_h = torch.empty(hp.T + 1, dtype=torch.float32).pin_memory()
         cm_h = torch.empty(hp.cm.numel(), dtype=torch.int64).pin_memory()
         # double-buffered ingest: the H2D copy of step i+1 (copy stream) overlaps K1..K4 of step i (compute stream)
         nbuf = 2
-        frames_d = [torch.empty_like(frames) for _ in range(nbuf)]
-        boxes_d = [torch.empty_like(boxes) for _ in range(nbuf)]
-        fidx_d = [torch.empty_like(fidx) for _ in range(nbuf)]
-        labels_d = [torch.empty_like(labels) for _ in range(nbuf)]
+        frames_d = [torch.empty_like(leg.frames) for _ in range(nbuf)]
+        boxes_d = [torch.empty_like(leg.boxes) for _ in range(nbuf)]
+        fidx_d = [torch.empty_like(leg.fidx) for _ in range(nbuf)]
+        labels_d = [torch.empty_like(leg.labels) for _ in range(nbuf)]
         s_copy = torch.cuda.Stream(device=dev)
         copied = [torch.cuda.Event() for _ in range(nbuf)]
         consumed = [torch.cuda.Event() for _ in range(nbuf)]
+        e2e_steps = max(3, min(steps, 30))
 
-        def e2e_run(k):
+        def e2e_run(k=e2e_steps):
             s_copy.wait_stream(cur)
             for b in range(nbuf):
                 consumed[b].record(cur)
@@ -388,35 +522,37 @@ def run_b200(args, wl):
                     labels_d[b].copy_(labels_p, non_blocking=True)
                     copied[b].record(s_copy)
                 cur.wait_event(copied[b])
-                hp.preprocess(frames_d[b], boxes_d[b], fidx_d[b])
+                leg.k1(frames_d[b], boxes_d[b], fidx_d[b])
                 consumed[b].record(cur)
-                bufs = hp.heads_step(emb, W_cat, b_cat, labels_d[b], train=True)
+                bufs = leg.heads(labels_d[b])
                 loss_h.copy_(bufs.loss, non_blocking=True)
                 cm_h.copy_(hp.cm, non_blocking=True)
             cur.wait_stream(s_copy)
 
-        e2e_steps = max(3, min(args.steps, 30))
         e2e_run(3)
-        barrier()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        e2e_run(e2e_steps)
-        a1.record()
-        barrier()
-        t2 = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        t_ms, _ = _timed(e2e_run, barrier, world, dev, reps=2)
         h2d = frames_h.numel() + boxes_h.numel() * 4 + fidx_h.numel() * 4 + labels_p.numel() * 8
         d2h = loss_h.numel() * 4 + cm_h.numel() * 8
-        e2e = {"value": world * n * e2e_steps / (float(t2.item()) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+        e2e = {"value": world * n * e2e_steps / (t_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+               "h2d_gbs_per_rank": h2d * e2e_steps / (t_ms * 1e-3) / 1e9,
                "note": "uint8 frames + boxes + labels H2D from pinned memory (double-buffered, copy stream overlaps compute), "
                        "loss + confusion counts D2H, every step"}
+        ceil = ROOT / "profiles" / "h2d_ceiling.json"
+        if ceil.exists():
+            try:
+                c = json.loads(ceil.read_text())
+                e2e["h2d_ceiling_gbs"] = c.get(f"n{world}")
+                e2e["h2d_ceiling_source"] = c.get("_source")
+            except Exception:
+                pass
+        del frames_d, frames_h
 
-    # ---- roofline of the dominant kernel (K1) ----
+    # ---- roofline of the dominant kernel (K1): algorithmic / DRAM-level / compulsory bytes over the same launch time ----
     peak, peak_src = measured_peak_hbm()
     elem = 4 if out_dtype == torch.float32 else 2
-    k1_bytes = k1_algorithmic_bytes(boxes_np, wl.out_size, wl.out_size, elem, wl.mode, wl.out_size)
+    k1_ms = m["k1_ms"]
+    k1_bytes = k1_algorithmic_bytes(leg.boxes_np, wl.out_size, wl.out_size, elem, wl.mode, wl.out_size)
     achieved = k1_bytes / (k1_ms * 1e-3) / 1e9
     traffic = None
     tp = ROOT / "profiles" / "k1_traffic.json"
@@ -425,36 +561,72 @@ def run_b200(args, wl):
             traffic = json.loads(tp.read_text()).get(f"{wl.name}.{args.out_dtype}")
         except Exception:
             traffic = None
+    uniq = _unique_source_bytes(leg.boxes_np, leg.fidx_np, wl) + n * 3 * wl.out_size * wl.out_size * elem
     roofline = {"kernel": "k1_crop_resize_normalize", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": k1_bytes, "launch_ms": k1_ms,
-                "share_of_step": k1_ms * args.steps / dt_ms}
+                "share_of_step": k1_ms / m["serial_ms"],
+                # boxes of one frame overlap and are served from L2: what HBM actually moved, and its lower bound
+                "dram_frac": None if traffic is None else traffic / (k1_ms * 1e-3) / 1e9 / peak,
+                "unique_bytes_per_launch": uniq, "unique_bytes_frac": uniq / (k1_ms * 1e-3) / 1e9 / peak,
+                "frac_note": "frac = SURVEY 8(d) algorithmic bytes (source bytes counted per crop); dram_frac = DRAM bytes "
+                             "of the committed ncu capture (profiles/k1_traffic.json); unique_bytes_frac = union of the "
+                             "boxes per frame + output, the compulsory traffic"}
+
+    # ---- the other named configurations on the same clock (N = 1): heads path, K1 fraction, crops/s ----
+    variants = None
+    if world == 1 and not args.no_variants:
+        variants = {}
+        vlist = [("cfg4_vit_5heads.bf16", WORKLOADS["cfg4_vit_5heads"], torch.bfloat16, torch.bfloat16, False),
+                 ("cfg2_multitask_256", WORKLOADS["cfg2_multitask_256"], torch.float32, torch.float32, False),
+                 ("cfg3_1080p_20", WORKLOADS["cfg3_1080p_20"], torch.float32, torch.float32, False),
+                 ("cfg5_1080p_64x64.letterbox", dataclasses.replace(wl, mode="letterbox"), out_dtype, emb_dtype, False),
+                 ("cfg5_1080p_64x64.train_aug", wl, out_dtype, emb_dtype, True),
+                 ("cfg5_1080p_64x64.bf16", wl, torch.bfloat16, torch.bfloat16, False)]
+        for name, vwl, od, ed, aug in vlist:
+            try:
+                vleg = Leg(vwl, dev, Communicator(), od, ed, "peer", train_aug=aug)
+                vm = _measure_leg(vleg, min(steps, 20), barrier, 1, dev, use_graph=not args.no_graph)
+                vms = min(vm["serial_ms"], vm.get("graph_ms", float("inf")))
+                ve = 4 if od == torch.float32 else 2
+                vb = k1_algorithmic_bytes(vleg.boxes_np, vwl.out_size, vwl.out_size, ve, vwl.mode, vwl.out_size)
+                variants[name] = {"value": vleg.n / (vms * 1e-3), "ms_per_step": vms, "serial_ms_per_step": vm["serial_ms"],
+                                  "graph_ms_per_step": vm.get("graph_ms"), "k1_ms": vm["k1_ms"],
+                                  "k1_frac": vb / (vm["k1_ms"] * 1e-3) / 1e9 / peak, "heads_path": vm["heads_path"],
+                                  "crops_per_step": vleg.n, "out": str(od).split(".")[-1], "emb": str(ed).split(".")[-1]}
+                del vleg
+            except Exception as e:   # a variant must never take the headline down with it
+                variants[name] = {"error": repr(e)}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         procs = os.cpu_count() or 1
         sample = min(n, 4096)
-        rate, times, nfr = cpu_path_rate(wl, boxes_np, fidx_np, sample, procs, steps=1, warmup=1)
-        rate1, _, _ = cpu_path_rate(wl, boxes_np, fidx_np, min(n, 256), 1, steps=1, warmup=0)
+        rate, times, nfr = cpu_path_rate(wl, leg.boxes_np, leg.fidx_np, sample, procs, steps=1, warmup=1)
+        rate1, _, _ = cpu_path_rate(wl, leg.boxes_np, leg.fidx_np, min(n, 256), 1, steps=1, warmup=0)
         cpu = {"value": rate, "unit": UNIT, "cores": procs, "kind": "port",
                "sample": f"{sample} crops ({nfr} frames) x 1 step of {wl.name} after 1 warm-up; oracle port = cv2 "
                          f"{__import__('cv2').__version__} resize/normalize in {procs} worker processes + torch CPU fp32 "
                          f"heads/loss/backward/logger stats; albumentations absent (cv2+numpy stand in)",
                "single_core_value": rate1}
 
+    transport = leg.hp.transport
     if world > 1:
         comm.shutdown()
         dist.destroy_process_group()
     if rank != 0:
         return
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": dt_ms_max / args.steps, "serial_value": serial_value, "serial_ms_per_step": serial_ms,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": best_ms, "serial_value": serial_value, "serial_ms_per_step": m["serial_ms"],
+        "graph_ms_per_step": m.get("graph_ms"), "reps": REPS, "rep_ms_per_step": {"serial": m["serial_all_ms"],
+                                                                               "graph": m.get("graph_all_ms")},
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u8/int32->" + args.out_dtype + (", heads bf16 x bf16 -> f32 (tcgen05)" if args.emb_dtype == "bf16" else ", heads f32"),
-        "data": "synthetic", "config": workload_config(wl, args.out_dtype, world, hp.transport),
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+        "dtype": "u8/int32->" + args.out_dtype + (", heads bf16 emb x f32 W -> f32" if args.emb_dtype == "bf16" else ", heads f32"),
+        "data": "synthetic", "config": workload_config(wl, args.out_dtype, world, transport),
+        "heads_path": m["heads_path"], "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+        "gpu_launches": int(m["launches"]), "strong": strong, "parity_check": parity, "variants": variants,
         "clocks": sampler.summary(),
     }
     print(json.dumps(line), flush=True)

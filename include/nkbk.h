@@ -168,6 +168,36 @@ int nkbk_heads_step(const void* emb, int emb_dtype, int B, int D, const float* W
                     float* dlogits, float* reduce_buf, int32_t* out_pred, int64_t* cm_step, void* workspace,
                     size_t workspace_bytes, void* stream);
 
+/* The whole training step of the heads in ONE launch: nkbk_heads_step, then -- by `exchange` --
+ * nkbk_heads_finalize (NKBK_EXCHANGE_LOCAL: one GPU, or the caller all-reduces itself) or
+ * nkbk_peer_allreduce_finalize (NKBK_EXCHANGE_PEER: the K4' exchange over NVLink peer memory), with identical results.
+ * When the shape qualifies (gradients wanted, rows 16-byte aligned, NC * D small enough for register accumulators,
+ * weights + a two-stage row ring within shared memory) this is one persistent cooperative kernel that reads every
+ * embedding row from HBM once and whose epilogue IS the exchange; otherwise the same step runs as the separate launches.
+ * Replaces, per training step: model.py:41-43 / :114-116, losses.py:59-94 / :110-147 / :155-159, the backward of
+ * engine.py:55-58 through the heads, logging.py:270-281 (softmax, argmax) and metrics.py:31 (confusion counts).
+ *   cm_step / cm_total / n_cm   as nkbk_heads_finalize (cm_step is scratch that is left zeroed); n_cm = 0 to skip
+ *   out_loss   fp32 [T+1] per-task mean losses and their sum (over all ranks with NKBK_EXCHANGE_PEER)
+ * The first nkbk_heads_workspace_bytes() of `workspace` need no initialisation. */
+enum { NKBK_EXCHANGE_LOCAL = 0, NKBK_EXCHANGE_PEER = 1 };
+int nkbk_heads_train_step(const void* emb, int emb_dtype, int B, int D, const float* W_cat, const float* b_cat,
+                          const int32_t* seg_offsets, int T, const int64_t* labels, int loss_kind, float gamma,
+                          const float* class_weight, int64_t ignore_index, float* out_logits, float* out_probs,
+                          float* dlogits, float* reduce_buf, int32_t* out_pred, int64_t* cm_step, int64_t* cm_total,
+                          int64_t n_cm, float* out_loss, int exchange, void* workspace, size_t workspace_bytes,
+                          void* stream);
+
+/* Which kernels served the calling thread's last nkbk_heads_step / nkbk_heads_train_step / nkbk_heads_fwd_loss_bwd:
+ * NKBK_PATH_FUSED (k2_fused_step, one launch), NKBK_PATH_TC_FWD (tcgen05 forward + dW kernel) or NKBK_PATH_FFMA_FWD
+ * (exact-fp32 FFMA forward + dW kernel).  Lets a caller see a fallback instead of guessing it from timings. */
+enum { NKBK_PATH_FFMA_FWD = 1, NKBK_PATH_TC_FWD = 2, NKBK_PATH_FUSED = 4 };
+int nkbk_heads_last_path(void);
+
+/* Debug helper (host-synchronous): per-CTA phase time stamps of the last fused nkbk_heads_* launch made with the
+ * environment variable NKBK_FUSED_TIMING=1 (profiles/tools/k2_phases.py).  out_host: uint64 [n_ctas][12]; returns the
+ * number of CTAs written, 0 when there is nothing to report. */
+int nkbk_debug_fused_timing(uint64_t* out_host, int max_ctas);
+
 /* In place: dW, db <- sums / denom[task]; out_loss (fp32 [T+1]) <- per-task mean
  * losses and their unweighted sum (losses.py:140-147).  denom == 0 -> 0.
  * Optionally folds the (all-reduced) per-step confusion counts into the epoch

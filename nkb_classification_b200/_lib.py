@@ -18,6 +18,8 @@ NKBK_E_ARG, NKBK_E_SHAPE, NKBK_E_CUDA, NKBK_E_NCCL, NKBK_E_UNSUPPORTED = -1, -2,
 F32, BF16 = 0, 1
 MODE_STRETCH, MODE_LETTERBOX = 0, 1
 LOSS_CE, LOSS_FOCAL = 0, 1
+EXCHANGE_LOCAL, EXCHANGE_PEER = 0, 1
+PATH_FFMA_FWD, PATH_TC_FWD, PATH_FUSED = 1, 2, 4
 UNIQUE_ID_BYTES = 128
 IPC_HANDLE_BYTES = 64
 
@@ -45,6 +47,12 @@ SYMBOLS = {
     "nkbk_heads_step": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, POINTER(c_int32), c_int, c_void_p,
                                 c_int, c_float, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_size_t, c_void_p]),
+    "nkbk_heads_train_step": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, POINTER(c_int32), c_int,
+                                      c_void_p, c_int, c_float, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p,
+                                      c_size_t, c_void_p]),
+    "nkbk_heads_last_path": (c_int, []),
+    "nkbk_debug_fused_timing": (c_int, [c_void_p, c_int]),
     "nkbk_loss_workspace_bytes": (c_int64, [c_int, c_int]),
     "nkbk_loss_fwd_bwd": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_int32), c_int, c_void_p, c_int, c_float,
                                   c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

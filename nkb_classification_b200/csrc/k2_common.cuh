@@ -59,4 +59,14 @@ struct K2FwdParams {
 int launch_k2_tc_forward(const K2FwdParams& p, void* wb_workspace, cudaStream_t st);
 int64_t k2_tc_workspace_floats(int B, int D, int NC);
 
+// k2_fused.cu: the whole training step of the heads (forward, loss, K3, dW / db, cross-CTA sum and -- by mode -- the
+// finalize or the K4' exchange + finalize) as one persistent cooperative kernel.  Returns 1 when launched, 0 when the
+// shape or device does not qualify (caller takes the multi-kernel path), < 0 on error.
+enum { KF_MODE_SUMS = 0, KF_MODE_FINALIZE = 1, KF_MODE_PEER = 2 };
+int launch_k2_fused(const K2FwdParams& f, int emb_dtype, float* reduce_buf, float* ws_floats, float* out_loss,
+                    int64_t* cm_total, int64_t n_cm, int mode, cudaStream_t st);
+int64_t k2_fused_workspace_floats(int B, int D, int NC, int T);
+// which kernels served the calling thread's last heads call (nkbk_heads_last_path)
+void set_heads_path(int bits);
+
 }  // namespace nkbk

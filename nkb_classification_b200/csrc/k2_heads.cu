@@ -33,6 +33,7 @@ struct K2Layout {  // workspace carve-up, in floats
     int64_t db_part;    // [dw_chunks][NC]
     int64_t counters;   // uint32 [dw_passes * dw_xblocks]
     int64_t tc_w;       // bf16 copy of the head weights for the tcgen05 path
+    int64_t fused;      // per-CTA partials of the fused step (k2_fused.cu)
     int64_t total;
 };
 
@@ -47,7 +48,8 @@ static K2Layout k2_layout(int B, int D, int NC, int T) {
     L.db_part = L.dw_part + (int64_t)L.dw_chunks * NC * D;
     L.counters = (L.db_part + (int64_t)L.dw_chunks * NC + 3) & ~int64_t(3);
     L.tc_w = (L.counters + (int64_t)L.dw_passes * L.dw_xblocks + 3) & ~int64_t(3);
-    L.total = L.tc_w + k2_tc_workspace_floats(B, D, NC);
+    L.fused = (L.tc_w + k2_tc_workspace_floats(B, D, NC) + 3) & ~int64_t(3);
+    L.total = L.fused + k2_fused_workspace_floats(B, D, NC, T);
     return L;
 }
 
@@ -695,11 +697,19 @@ extern "C" int nkbk_heads_fwd_loss_bwd(const void* emb, int emb_dtype, int B, in
                            workspace_bytes, stream);
 }
 
-extern "C" int nkbk_heads_step(const void* emb, int emb_dtype, int B, int D, const float* W_cat, const float* b_cat,
-                               const int32_t* seg_offsets, int T, const int64_t* labels, int loss_kind, float gamma,
-                               const float* class_weight, int64_t ignore_index, float* out_logits, float* out_probs,
-                               float* dlogits, float* reduce_buf, int32_t* out_pred, int64_t* cm_step, void* workspace,
-                               size_t workspace_bytes, void* stream) {
+static thread_local int g_heads_path = 0;
+void nkbk::set_heads_path(int bits) { g_heads_path = bits; }
+extern "C" int nkbk_heads_last_path(void) { return g_heads_path; }
+
+// `mode`: KF_MODE_SUMS = the nkbk_heads_step contract (unnormalised sums in reduce_buf); KF_MODE_FINALIZE / KF_MODE_PEER =
+// nkbk_heads_train_step (finalize, or K4' exchange + finalize, applied as well).
+static int heads_step_impl(const void* emb, int emb_dtype, int B, int D, const float* W_cat, const float* b_cat,
+                           const int32_t* seg_offsets, int T, const int64_t* labels, int loss_kind, float gamma,
+                           const float* class_weight, int64_t ignore_index, float* out_logits, float* out_probs,
+                           float* dlogits, float* reduce_buf, int32_t* out_pred, int64_t* cm_step, void* workspace,
+                           size_t workspace_bytes, void* stream, int mode, float* out_loss, int64_t* cm_total,
+                           int64_t n_cm, int* fused_done) {
+    *fused_done = 0;
     K2Seg seg;
     int rc = fill_seg(seg, seg_offsets, T, "nkbk_heads_fwd_loss_bwd");
     if (rc) return rc;
@@ -738,6 +748,16 @@ extern "C" int nkbk_heads_step(const void* emb, int emb_dtype, int B, int D, con
     p.n_counters = L.dw_passes * L.dw_xblocks;
     p.B = B; p.D = D; p.NC = NC; p.loss_kind = loss_kind; p.gamma = gamma; p.ignore_index = ignore_index;
     p.seg = seg;
+    // the whole step as one persistent kernel when the shape qualifies (training calls: gradients wanted)
+    {
+        const int fz = launch_k2_fused(p, emb_dtype, reduce_buf, ws + L.fused, out_loss, cm_total, n_cm, mode, st);
+        if (fz < 0) return fz;
+        if (fz > 0) {
+            *fused_done = 1;
+            set_heads_path(NKBK_PATH_FUSED);
+            return NKBK_OK;
+        }
+    }
     // forward v3: warp = 4 rows over the whole K, private shared-memory slice per warp, K3 fused
     const size_t smem = (size_t)K2_V3_WARPS * K2_FWD_ROWS * (2 * NC + 6 * T) * sizeof(float);
     const int v3_blocks = (L.fwd_blocks + K2_V3_WARPS - 1) / K2_V3_WARPS;
@@ -768,6 +788,7 @@ extern "C" int nkbk_heads_step(const void* emb, int emb_dtype, int B, int D, con
 #undef NKBK_FWD
     }
     if (tc == 0) NKBK_CHECK_LAUNCH("k2_heads_forward_v3");
+    set_heads_path(tc > 0 ? NKBK_PATH_TC_FWD : NKBK_PATH_FFMA_FWD);
 
     if (dlogits != nullptr) {
         dim3 grid(L.dw_xblocks, L.dw_chunks);
@@ -800,6 +821,43 @@ extern "C" int nkbk_heads_step(const void* emb, int emb_dtype, int B, int D, con
         NKBK_CHECK_LAUNCH("k2_heads_reduce_loss");
     }
     return NKBK_OK;
+}
+
+extern "C" int nkbk_heads_step(const void* emb, int emb_dtype, int B, int D, const float* W_cat, const float* b_cat,
+                               const int32_t* seg_offsets, int T, const int64_t* labels, int loss_kind, float gamma,
+                               const float* class_weight, int64_t ignore_index, float* out_logits, float* out_probs,
+                               float* dlogits, float* reduce_buf, int32_t* out_pred, int64_t* cm_step, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+    int fused = 0;
+    return heads_step_impl(emb, emb_dtype, B, D, W_cat, b_cat, seg_offsets, T, labels, loss_kind, gamma, class_weight,
+                           ignore_index, out_logits, out_probs, dlogits, reduce_buf, out_pred, cm_step, workspace,
+                           workspace_bytes, stream, KF_MODE_SUMS, nullptr, nullptr, 0, &fused);
+}
+
+extern "C" int nkbk_heads_train_step(const void* emb, int emb_dtype, int B, int D, const float* W_cat,
+                                     const float* b_cat, const int32_t* seg_offsets, int T, const int64_t* labels,
+                                     int loss_kind, float gamma, const float* class_weight, int64_t ignore_index,
+                                     float* out_logits, float* out_probs, float* dlogits, float* reduce_buf,
+                                     int32_t* out_pred, int64_t* cm_step, int64_t* cm_total, int64_t n_cm,
+                                     float* out_loss, int exchange, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
+    NKBK_CHECK_ARG(exchange == NKBK_EXCHANGE_LOCAL || exchange == NKBK_EXCHANGE_PEER,
+                   "nkbk_heads_train_step: exchange=%d", exchange);
+    NKBK_CHECK_ARG(n_cm >= 0 && (n_cm == 0 || (cm_total && cm_step)), "nkbk_heads_train_step: bad confusion buffers");
+    const bool peer = exchange == NKBK_EXCHANGE_PEER && nkbk_peer_world() > 1;
+    if (exchange == NKBK_EXCHANGE_PEER && nkbk_peer_world() < 1) {
+        set_error("nkbk_heads_train_step: NKBK_EXCHANGE_PEER needs nkbk_peer_init + nkbk_peer_connect");
+        return NKBK_E_NCCL;
+    }
+    int fused = 0;
+    int rc = heads_step_impl(emb, emb_dtype, B, D, W_cat, b_cat, seg_offsets, T, labels, loss_kind, gamma, class_weight,
+                             ignore_index, out_logits, out_probs, dlogits, reduce_buf, out_pred, cm_step, workspace,
+                             workspace_bytes, stream, peer ? KF_MODE_PEER : KF_MODE_FINALIZE, out_loss, cm_total,
+                             cm_step ? n_cm : 0, &fused);
+    if (rc || fused) return rc;
+    // shapes the fused kernel does not take: the same step as separate launches
+    if (peer) return nkbk_peer_allreduce_finalize(reduce_buf, D, seg_offsets, T, out_loss, cm_total, cm_step, n_cm, stream);
+    return nkbk_heads_finalize(reduce_buf, D, seg_offsets, T, out_loss, cm_total, cm_step, n_cm, stream);
 }
 
 extern "C" int64_t nkbk_loss_workspace_bytes(int B, int T) {

@@ -21,25 +21,14 @@
 //
 // Memory is allocated by the library (cudaMalloc) and exchanged as cudaIpcMemHandle_t; torch.distributed only
 // carries the 64-byte handles.  NCCL (k4_comm.cu) remains available as the plain baseline for the same step.
-#include "k2_common.cuh"
+#include "k4_peer.cuh"
 
 #include <string.h>
 
 namespace nkbk {
 
-constexpr int PEER_MAX_WORLD = 16;
-constexpr int PEER_MAX_CTAS = 148;
-constexpr int PEER_THREADS = 256;
-constexpr int PEER_MIN_VECS_PER_CTA = 256;                  // one 16-byte vector per thread
-constexpr int PEER_TAIL_VECS = (2 * K2_MAX_TASKS + 3) / 4;  // per-CTA copy of [loss_sum T | denom T]
-constexpr unsigned long long PEER_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
-
 struct PeerParams {
-    int4* data[PEER_MAX_WORLD];          // every rank's inbox area (data[rank] is local)
-    unsigned int* flags[PEER_MAX_WORLD]; // every rank's flag area
-    unsigned int* ctl;                   // local: {step, ticket, status, -}
-    int rank, world;
-    long long slot_vecs, cap_vecs;       // slot = [cap_vecs payload | PEER_MAX_CTAS * PEER_TAIL_VECS tails]
+    PeerLinks L;
     float* reduce_buf;
     long long n_f32, vf;                 // floats / 16-byte vectors of the fp32 payload
     long long* cm_step;
@@ -49,20 +38,6 @@ struct PeerParams {
     int NC, D, vecs_per_cta;
     K2Seg seg;
 };
-
-__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long global_timer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
 
 // 16-byte vector `v` of the local payload: fp32 part first (zero padded), then the int64 counts (zero padded).
 __device__ __forceinline__ int4 peer_load_local(const PeerParams& p, long long v) {
@@ -82,19 +57,14 @@ __device__ __forceinline__ int4 peer_load_local(const PeerParams& p, long long v
     return *reinterpret_cast<int4*>(&x);
 }
 
-__device__ __forceinline__ int peer_task_of(const K2Seg& seg, int c) {
-    int t = 0;
-    while (t + 1 < seg.T && c >= seg.off[t + 1]) ++t;
-    return t;
-}
-
 __global__ void __launch_bounds__(PEER_THREADS) k4_peer_allreduce_finalize(const PeerParams p) {
     __shared__ float tail_s[2 * K2_MAX_TASKS];  // reduced [loss_sum T | denom T]
     __shared__ unsigned int step_s;
     __shared__ bool last_s;
-    const int tid = threadIdx.x, cta = blockIdx.x;
-    const int T = p.seg.T, world = p.world, rank = p.rank;
-    if (tid == 0) step_s = *reinterpret_cast<volatile unsigned int*>(p.ctl) + 1u;
+    const PeerLinks& L = p.L;
+    const int tid = threadIdx.x, cta = blockIdx.x;   // one payload slice per CTA (peer_slicing)
+    const int T = p.seg.T, world = L.world, rank = L.rank;
+    if (tid == 0) step_s = *reinterpret_cast<volatile unsigned int*>(L.ctl) + 1u;
     __syncthreads();
     const unsigned int step = step_s;
     const long long par = step & 1u;
@@ -102,8 +72,8 @@ __global__ void __launch_bounds__(PEER_THREADS) k4_peer_allreduce_finalize(const
     const long long v1 = min(v0 + (long long)p.vecs_per_cta, p.vf + p.vi);
     const long long nW = (long long)p.NC * p.D, tail0 = nW + p.NC;
     const int tail_vecs = (2 * T + 3) / 4;
-    const long long my_slot = (par * world + rank) * p.slot_vecs;  // where my data lands in every peer's inbox
-    const long long tail_off = p.cap_vecs + (long long)cta * PEER_TAIL_VECS;
+    const long long my_slot = (par * world + rank) * L.slot_vecs;  // where my data lands in every peer's inbox
+    const long long tail_off = L.cap_vecs + (long long)cta * PEER_TAIL_VECS;
 
     // ---- push: my slice (and my copy of the tail) into every peer's inbox ----
     if (world > 1) {
@@ -111,7 +81,7 @@ __global__ void __launch_bounds__(PEER_THREADS) k4_peer_allreduce_finalize(const
             const int4 x = peer_load_local(p, v);
             for (int k = 1; k < world; ++k) {
                 const int q = (rank + k) % world;  // staggered so the ranks do not all hit the same peer first
-                p.data[q][my_slot + v] = x;
+                L.data[q][my_slot + v] = x;
             }
         }
         if (tid < tail_vecs) {
@@ -121,23 +91,13 @@ __global__ void __launch_bounds__(PEER_THREADS) k4_peer_allreduce_finalize(const
             for (int k = 0; k < 4; ++k) xf[k] = (4 * tid + k < 2 * T) ? p.reduce_buf[tail0 + 4 * tid + k] : 0.f;
             for (int k = 1; k < world; ++k) {
                 const int q = (rank + k) % world;
-                p.data[q][my_slot + tail_off + tid] = *reinterpret_cast<int4*>(&x);
+                L.data[q][my_slot + tail_off + tid] = *reinterpret_cast<int4*>(&x);
             }
         }
         __syncthreads();
         if (tid < world && tid != rank) {
-            __threadfence_system();  // cumulative: orders the whole CTA's stores (joined by the barrier) before the flag
-            st_release_sys(p.flags[tid] + (par * world + rank) * PEER_MAX_CTAS + cta, step);
-            // ---- wait for rank `tid`'s counterpart CTA ----
-            const unsigned int* f = p.flags[rank] + (par * world + tid) * PEER_MAX_CTAS + cta;
-            const unsigned long long t0 = global_timer_ns();
-            unsigned int spins = 0;
-            while (ld_acquire_sys(f) != step) {
-                if ((++spins & 0x3ffu) == 0u && global_timer_ns() - t0 > PEER_TIMEOUT_NS) {
-                    atomicExch(p.ctl + 2, 1u + (unsigned int)tid);  // status: peer `tid` never arrived
-                    break;
-                }
-            }
+            peer_publish(L, tid, par, cta, step);
+            peer_wait(L, tid, par, cta, step);   // no grid-wide barrier: only this slice's counterparts
         }
         __syncthreads();
     }
@@ -148,7 +108,7 @@ __global__ void __launch_bounds__(PEER_THREADS) k4_peer_allreduce_finalize(const
         for (int r = 0; r < world; ++r) {
             float x;
             if (r == rank) x = p.reduce_buf[tail0 + tid];
-            else x = __ldcg(reinterpret_cast<const float*>(p.data[rank] + (par * world + r) * p.slot_vecs + tail_off) + tid);
+            else x = __ldcg(reinterpret_cast<const float*>(L.data[rank] + (par * world + r) * L.slot_vecs + tail_off) + tid);
             s = (r == 0) ? x : s + x;
         }
         tail_s[tid] = s;
@@ -162,7 +122,7 @@ __global__ void __launch_bounds__(PEER_THREADS) k4_peer_allreduce_finalize(const
             for (int r = 0; r < world; ++r) {
                 int4 raw;
                 if (r == rank) raw = peer_load_local(p, v);
-                else raw = __ldcg(p.data[rank] + (par * world + r) * p.slot_vecs + v);
+                else raw = __ldcg(L.data[rank] + (par * world + r) * L.slot_vecs + v);
                 const float4 x = *reinterpret_cast<float4*>(&raw);
                 if (r == 0) acc = x;
                 else { acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w; }
@@ -189,7 +149,7 @@ __global__ void __launch_bounds__(PEER_THREADS) k4_peer_allreduce_finalize(const
             for (int r = 0; r < world; ++r) {
                 int4 raw;
                 if (r == rank) raw = peer_load_local(p, v);
-                else raw = __ldcg(p.data[rank] + (par * world + r) * p.slot_vecs + v);
+                else raw = __ldcg(L.data[rank] + (par * world + r) * L.slot_vecs + v);
                 const longlong2 x = *reinterpret_cast<longlong2*>(&raw);
                 acc.x += x.x;
                 acc.y += x.y;
@@ -199,31 +159,33 @@ __global__ void __launch_bounds__(PEER_THREADS) k4_peer_allreduce_finalize(const
             if (j + 1 < p.n_cm) { p.cm_total[j + 1] += acc.y; p.cm_step[j + 1] = 0; }
         }
     }
-    if (cta == 0 && tid == 0 && p.out_loss != nullptr) {
-        float total = 0.f;
-        for (int t = 0; t < T; ++t) {
-            const float l = tail_s[T + t] > 0.f ? __fdiv_rn(tail_s[t], tail_s[T + t]) : 0.f;
-            p.out_loss[t] = l;
-            total += l;
-        }
-        p.out_loss[T] = total;
-    }
 
     // ---- the last CTA to finish advances the step counter (every CTA read it before taking a ticket) ----
     // It also publishes the global loss sums / denominators (left unnormalised: k2_heads_demb reads the
-    // denominators) -- only now, when no CTA of this rank needs the local values any more.
+    // denominators) and the mean losses -- only now, when no CTA of this rank needs the local values any more.
+    // A peer wait that timed out (status word set) poisons the losses with NaN: the step's sums are incomplete.
     __syncthreads();
     if (tid == 0) {
         __threadfence();
-        last_s = atomicAdd(p.ctl + 1, 1u) == gridDim.x - 1u;
+        last_s = atomicAdd(L.ctl + 1, 1u) == gridDim.x - 1u;
     }
     __syncthreads();
     if (last_s) {
         if (tid < 2 * T) p.reduce_buf[tail0 + tid] = tail_s[tid];
         if (tid == 0) {
-            p.ctl[1] = 0u;
+            if (p.out_loss != nullptr) {
+                const bool bad = *reinterpret_cast<volatile unsigned int*>(L.ctl + 2) != 0u;
+                float total = 0.f;
+                for (int t = 0; t < T; ++t) {
+                    const float l = tail_s[T + t] > 0.f ? __fdiv_rn(tail_s[t], tail_s[T + t]) : 0.f;
+                    p.out_loss[t] = bad ? __int_as_float(0x7fc00000) : l;
+                    total += l;
+                }
+                p.out_loss[T] = bad ? __int_as_float(0x7fc00000) : total;
+            }
+            L.ctl[1] = 0u;
             __threadfence();
-            *reinterpret_cast<volatile unsigned int*>(p.ctl) = step;
+            *reinterpret_cast<volatile unsigned int*>(L.ctl) = step;
         }
     }
 }
@@ -270,10 +232,10 @@ extern "C" int nkbk_peer_init(int rank, int world, int device, int64_t max_f32, 
     PeerState s;
     s.rank = rank; s.world = world; s.device = device; s.max_f32 = max_f32; s.max_i64 = max_i64;
     s.cap_vecs = (max_f32 + 3) / 4 + (max_i64 + 1) / 2;
-    s.slot_vecs = s.cap_vecs + (long long)PEER_MAX_CTAS * PEER_TAIL_VECS;
+    s.slot_vecs = s.cap_vecs + (long long)PEER_MAX_SLICES * PEER_TAIL_VECS;
     s.data_bytes = (size_t)2 * world * s.slot_vecs * 16;
     s.flags_off = (s.data_bytes + 255) & ~size_t(255);
-    s.ctl_off = (s.flags_off + (size_t)2 * world * PEER_MAX_CTAS * 4 + 255) & ~size_t(255);
+    s.ctl_off = (s.flags_off + (size_t)2 * world * PEER_MAX_SLICES * 4 + 255) & ~size_t(255);
     s.bytes = s.ctl_off + 256;
     void* ptr = nullptr;
     NKBK_CHECK_CUDA(cudaMalloc(&ptr, s.bytes));
@@ -322,6 +284,27 @@ extern "C" int nkbk_peer_connect(const void* handles_host) {
 
 extern "C" int nkbk_peer_world(void) { return (g_peer.on && g_peer.connected) ? g_peer.world : 0; }
 
+int nkbk::peer_links(PeerLinks& L, long long n_f32, long long n_i64, const char* who) {
+    if (!g_peer.on || !g_peer.connected) {
+        set_error("%s: peer memory not connected (nkbk_peer_init + nkbk_peer_connect)", who);
+        return NKBK_E_NCCL;
+    }
+    if (n_f32 > g_peer.max_f32 || n_i64 > g_peer.max_i64) {
+        set_error("%s: payload %lld f32 + %lld i64 exceeds the capacity given to nkbk_peer_init (%lld, %lld)", who, n_f32,
+                  n_i64, g_peer.max_f32, g_peer.max_i64);
+        return NKBK_E_SHAPE;
+    }
+    memset(&L, 0, sizeof(L));
+    for (int r = 0; r < g_peer.world; ++r) {
+        L.data[r] = reinterpret_cast<int4*>(g_peer.mapped[r]);
+        L.flags[r] = reinterpret_cast<unsigned int*>(g_peer.mapped[r] + g_peer.flags_off);
+    }
+    L.ctl = reinterpret_cast<unsigned int*>(g_peer.local + g_peer.ctl_off);
+    L.rank = g_peer.rank; L.world = g_peer.world;
+    L.slot_vecs = g_peer.slot_vecs; L.cap_vecs = g_peer.cap_vecs;
+    return NKBK_OK;
+}
+
 extern "C" int nkbk_peer_allreduce_finalize(float* reduce_buf, int D, const int32_t* seg_offsets, int T, float* out_loss,
                                             int64_t* cm_total, int64_t* cm_step, int64_t n_cm, void* stream) {
     if (!g_peer.on || !g_peer.connected) {
@@ -335,30 +318,18 @@ extern "C" int nkbk_peer_allreduce_finalize(float* reduce_buf, int D, const int3
     NKBK_CHECK_ARG(n_cm >= 0 && (n_cm == 0 || (cm_total && cm_step)), "nkbk_peer_allreduce_finalize: bad confusion buffers");
     const int NC = seg.off[T];
     const long long n_f32 = (long long)NC * D + NC + 2LL * T;
-    if (n_f32 > g_peer.max_f32 || n_cm > g_peer.max_i64) {
-        set_error("nkbk_peer_allreduce_finalize: payload %lld f32 + %lld i64 exceeds the capacity given to nkbk_peer_init "
-                  "(%lld, %lld)", n_f32, (long long)n_cm, g_peer.max_f32, g_peer.max_i64);
-        return NKBK_E_SHAPE;
-    }
-    NKBK_CHECK_ARG((reinterpret_cast<uintptr_t>(reduce_buf) & 15) == 0, "nkbk_peer_allreduce_finalize: reduce_buf must be 16-byte aligned");
     PeerParams p;
     memset(&p, 0, sizeof(p));
-    for (int r = 0; r < g_peer.world; ++r) {
-        p.data[r] = reinterpret_cast<int4*>(g_peer.mapped[r]);
-        p.flags[r] = reinterpret_cast<unsigned int*>(g_peer.mapped[r] + g_peer.flags_off);
-    }
-    p.ctl = reinterpret_cast<unsigned int*>(g_peer.local + g_peer.ctl_off);
-    p.rank = g_peer.rank; p.world = g_peer.world;
-    p.slot_vecs = g_peer.slot_vecs; p.cap_vecs = g_peer.cap_vecs;
+    rc = peer_links(p.L, n_f32, n_cm, "nkbk_peer_allreduce_finalize");
+    if (rc) return rc;
+    NKBK_CHECK_ARG((reinterpret_cast<uintptr_t>(reduce_buf) & 15) == 0, "nkbk_peer_allreduce_finalize: reduce_buf must be 16-byte aligned");
     p.reduce_buf = reduce_buf; p.n_f32 = n_f32; p.vf = (n_f32 + 3) / 4;
     p.cm_step = reinterpret_cast<long long*>(cm_step); p.cm_total = reinterpret_cast<long long*>(cm_total);
     p.n_cm = n_cm; p.vi = (n_cm + 1) / 2;
     p.out_loss = out_loss; p.NC = NC; p.D = D; p.seg = seg;
-    const long long total = p.vf + p.vi;
-    long long per = (total + PEER_MAX_CTAS - 1) / PEER_MAX_CTAS;
-    if (per < PEER_MIN_VECS_PER_CTA) per = PEER_MIN_VECS_PER_CTA;
-    p.vecs_per_cta = (int)per;
-    const int blocks = (int)((total + per - 1) / per);
+    int per = 0, blocks = 0;
+    peer_slicing(p.vf + p.vi, per, blocks);   // one slice per CTA: the same cut the fused heads step uses
+    p.vecs_per_cta = per;
     k4_peer_allreduce_finalize<<<blocks, PEER_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(p);
     NKBK_CHECK_LAUNCH("k4_peer_allreduce_finalize");
     return NKBK_OK;

@@ -62,20 +62,39 @@ class _FusedHeads(torch.autograd.Function):
         key = (B, need_grads, emb_c.dtype)
         bufs = state["bufs"].get(key)
         if bufs is None:
+            if len(state["bufs"]) >= 8:          # train / val / last-batch shapes stay cached; cap the odd ones
+                state["bufs"].pop(next(iter(state["bufs"])))
             bufs = ops.HeadsBuffers(B, pack.D, pack.seg, emb_c.device, want_logits=True, want_probs=True,
                                     want_grads=need_grads)
-            state["bufs"] = {key: bufs}
+            bufs.generation = 0
+            state["bufs"][key] = bufs
+        bufs.generation += 1                     # backward checks that nobody has overwritten these gradients
         cm, cm_step = state.get("cm"), state.get("cm_step")
         pred = None
         if state.get("want_pred", True):
             pred = torch.empty((B, pack_T(pack)), dtype=torch.int32, device=emb_c.device)
-        # K3 (argmax + confusion counts) rides in K2's forward epilogue
-        ops.heads_fwd_loss_bwd(emb_c, pack.W_cat, pack.b_cat, labels, bufs, state["loss_kind"], state["gamma"],
-                               state["class_weight"], state["ignore_index"], out_pred=pred,
-                               cm_step=cm_step if (pred is not None and labels is not None) else None)
+        do_cm = pred is not None and labels is not None and cm is not None
         comm: Communicator = state["comm"]
-        comm.exchange_finalize(bufs, cm, cm_step, state.get("transport", "peer"))
+        transport = state.get("transport", "peer")
+        one_launch = need_grads and (comm.world == 1 or transport == "peer")
+        peer = False
+        if one_launch and comm.world > 1:
+            peer = comm.init_peer(emb_c.device, bufs.reduce_buf.numel(), 0 if cm is None else cm.numel())
+            one_launch = peer
+        if one_launch:
+            # forward + loss + K3 + dW/db + exchange (K4' as the kernel's epilogue) + finalize: ONE launch
+            ops.heads_train_step(emb_c, pack.W_cat, pack.b_cat, labels, bufs, state["loss_kind"], state["gamma"],
+                                 state["class_weight"], state["ignore_index"], out_pred=pred,
+                                 cm_total=cm if do_cm else None, cm_step=cm_step if do_cm else None, peer=peer)
+        else:
+            # K3 (argmax + confusion counts) rides in K2's forward epilogue
+            ops.heads_fwd_loss_bwd(emb_c, pack.W_cat, pack.b_cat, labels, bufs, state["loss_kind"], state["gamma"],
+                                   state["class_weight"], state["ignore_index"], out_pred=pred,
+                                   cm_step=cm_step if do_cm else None)
+            comm.exchange_finalize(bufs, cm if do_cm else None, cm_step if do_cm else None,
+                                   transport)
         ctx.state, ctx.bufs, ctx.emb_dtype, ctx.need_demb = state, bufs, emb.dtype, emb.requires_grad
+        ctx.generation = bufs.generation
         ctx.n_params = len(params)
         state["last"] = (bufs, pred)
         return bufs.loss.clone()
@@ -86,11 +105,13 @@ class _FusedHeads(torch.autograd.Function):
         pack: HeadPack = state["pack"]
         if bufs.dlogits is None:
             raise RuntimeError("fused heads were run with train=False; no gradients were produced")
+        if bufs.generation != ctx.generation:
+            raise RuntimeError("the fused heads ran again (same batch shape) before this backward: its gradient "
+                               "buffers were overwritten -- call backward() before the next forward")
         T = pack_T(pack)
         # every output is a sum of per-task means; total (index T) is the usual one to differentiate
         per_task = g[:T] + g[T]
-        dev = g.device
-        rows = torch.repeat_interleave(per_task, torch.tensor(pack.classes, device=dev))      # [NC]
+        rows = per_task if T == 1 else per_task.index_select(0, state["task_of_class"])      # [NC] (no host sync)
         demb = None
         if ctx.need_demb:
             out_dtype = torch.bfloat16 if ctx.emb_dtype in (torch.float16, torch.bfloat16) else torch.float32
@@ -151,6 +172,9 @@ class FusedHeads:
             "class_weight": class_weight, "ignore_index": int(ignore_index), "comm": comm or Communicator(),
             "cm": torch.zeros(n_cm, dtype=torch.int64, device=dev) if track_confusion else None,
             "cm_step": torch.zeros(n_cm, dtype=torch.int64, device=dev) if track_confusion else None,
+            # class -> task index, resident on the device: backward scales the gradient rows without a host sync
+            "task_of_class": torch.repeat_interleave(torch.arange(len(self.pack.classes)),
+                                                     torch.tensor(self.pack.classes)).to(dev),
         }
 
     @property
@@ -192,7 +216,7 @@ class FusedHeads:
                 C = tp.classes[0]
                 cw = self.state["class_weight"]
                 st = dict(self.state)
-                st.update(pack=tp, bufs={}, last=None,
+                st.update(pack=tp, bufs={}, last=None, task_of_class=torch.zeros(C, dtype=torch.int64, device=emb.device),
                           class_weight=None if cw is None else cw[pack.seg[t]:pack.seg[t + 1]].contiguous(),
                           cm=None if self.state["cm"] is None else self.state["cm"][off: off + C * C],
                           cm_step=None if self.state["cm_step"] is None else self.state["cm_step"][off: off + C * C])

@@ -86,6 +86,17 @@ class HotPath:
             if pred is None:
                 pred = torch.empty((B, self.T), dtype=torch.int32, device=self.device)
                 self._pred = {B: pred}
+        if train and (self.comm.world == 1 or self.transport == "peer"):
+            # the whole step -- forward, loss, K3, dW / db, exchange (K4' as the kernel's epilogue), finalize -- as ONE
+            # launch (nkbk_heads_train_step); the NCCL transport keeps the separate launches below
+            peer = self.comm.world > 1 and self.comm.init_peer(self.device, bufs.reduce_buf.numel(), self.cm.numel())
+            if self.comm.world == 1 or peer:
+                ops.heads_train_step(emb, W_cat, b_cat, labels, bufs, self.loss_kind, self.gamma, self.class_weight,
+                                     self.ignore_index, out_pred=pred, cm_total=self.cm if do_cm else None,
+                                     cm_step=self.cm_step if do_cm else None, peer=peer)
+                bufs.pred = pred
+                return bufs
+            self.transport = "nccl"
         # K2 with K3 fused into its epilogue: argmax + confusion counts while the logits are on chip
         ops.heads_fwd_loss_bwd(emb, W_cat, b_cat, labels, bufs, self.loss_kind, self.gamma, self.class_weight,
                                self.ignore_index, out_pred=pred, cm_step=self.cm_step if do_cm else None)

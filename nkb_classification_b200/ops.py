@@ -268,6 +268,74 @@ def heads_fwd_loss_bwd(
     return bufs
 
 
+def _check_heads_args(emb, W_cat, b_cat, labels, bufs, class_weight, out_pred, cm_step):
+    _need_cuda("emb", emb)
+    _need_cuda("W_cat", W_cat)
+    if emb.dtype not in _DT:
+        raise ValueError(f"emb dtype {emb.dtype} not supported (float32 | bfloat16)")
+    if not emb.is_contiguous() or emb.dim() != 2:
+        raise ValueError("emb must be contiguous [B,D]")
+    B, D = emb.shape
+    if (B, D) != (bufs.B, bufs.D):
+        raise ValueError(f"emb {tuple(emb.shape)} does not match buffers ({bufs.B},{bufs.D})")
+    if W_cat.dtype != torch.float32 or b_cat.dtype != torch.float32:
+        raise ValueError("W_cat / b_cat must be float32")
+    if tuple(W_cat.shape) != (bufs.NC, D) or b_cat.numel() != bufs.NC or not W_cat.is_contiguous():
+        raise ValueError("W_cat must be contiguous [NC,D] and b_cat [NC]")
+    if labels is not None:
+        _need_cuda("labels", labels)
+        if labels.dtype != torch.int64 or not labels.is_contiguous() or labels.numel() != B * bufs.T:
+            raise ValueError("labels must be contiguous int64 [B,T]")
+    if class_weight is not None:
+        if class_weight.dtype != torch.float32 or class_weight.numel() != bufs.NC or not class_weight.is_cuda:
+            raise ValueError("class_weight must be CUDA float32 [NC]")
+    if out_pred is not None and (out_pred.dtype != torch.int32 or out_pred.numel() != B * bufs.T
+                                 or not out_pred.is_contiguous() or not out_pred.is_cuda):
+        raise ValueError("out_pred must be a contiguous CUDA int32 [B,T]")
+    if cm_step is not None:
+        if labels is None:
+            raise ValueError("cm_step needs labels")
+        if cm_step.dtype != torch.int64 or cm_step.numel() != confusion_len(bufs.seg) or not cm_step.is_cuda:
+            raise ValueError("cm_step must be CUDA int64 of confusion_len(seg) elements")
+
+
+def heads_train_step(
+    emb: torch.Tensor, W_cat: torch.Tensor, b_cat: torch.Tensor, labels: Optional[torch.Tensor], bufs: HeadsBuffers,
+    loss_kind: int = LOSS_FOCAL, gamma: float = 2.0, class_weight: Optional[torch.Tensor] = None,
+    ignore_index: int = -100, out_pred: Optional[torch.Tensor] = None, cm_total: Optional[torch.Tensor] = None,
+    cm_step: Optional[torch.Tensor] = None, peer: bool = False,
+) -> HeadsBuffers:
+    """The whole training step of the heads in one call -- forward, loss, K3, dW / db, the exchange step when
+    ``peer`` (K4' over NVLink peer memory; needs ``Communicator.init_peer``) and the finalize -- ONE persistent kernel
+    when the shape qualifies (nkbk_heads_train_step).  Afterwards ``bufs.dW()`` / ``bufs.db()`` are the (global) mean
+    gradients, ``bufs.loss`` [T+1] the mean losses, ``cm_total`` has the step's (global) confusion counts folded in."""
+    if bufs.dlogits is None:
+        raise ValueError("heads_train_step needs buffers created with want_grads=True")
+    _check_heads_args(emb, W_cat, b_cat, labels, bufs, class_weight, out_pred, cm_step)
+    n_cm = 0
+    if cm_total is not None or cm_step is not None:
+        if cm_total is None or cm_step is None or cm_total.numel() != cm_step.numel() \
+                or cm_total.dtype != torch.int64 or not cm_total.is_cuda:
+            raise ValueError("cm_total / cm_step must both be CUDA int64 of equal length")
+        n_cm = cm_total.numel()
+    seg, T, _ = _seg_array(bufs.seg)
+    B, D = emb.shape
+    rc = lib().nkbk_heads_train_step(
+        _ptr(emb), _DT[emb.dtype], B, D, _ptr(W_cat), _ptr(b_cat), seg, T, _ptr(labels), int(loss_kind), float(gamma),
+        _ptr(class_weight), int(ignore_index), _ptr(bufs.logits), _ptr(bufs.probs), _ptr(bufs.dlogits),
+        _ptr(bufs.reduce_buf), _ptr(out_pred), _ptr(cm_step), _ptr(cm_total), n_cm, _ptr(bufs.loss),
+        _lib.EXCHANGE_PEER if peer else _lib.EXCHANGE_LOCAL, _ptr(bufs.workspace), bufs.workspace.numel(),
+        _stream(emb.device),
+    )
+    check(rc)
+    return bufs
+
+
+def heads_last_path() -> int:
+    """Bit mask of the kernels that served this thread's last heads call: _lib.PATH_FUSED | PATH_TC_FWD | PATH_FFMA_FWD."""
+    return int(lib().nkbk_heads_last_path())
+
+
 def heads_finalize(bufs: HeadsBuffers, cm_total: Optional[torch.Tensor] = None,
                    cm_step: Optional[torch.Tensor] = None) -> torch.Tensor:
     """reduce_buf sums -> mean gradients in place; returns fp32 [T+1] = per-task losses + total.

@@ -80,6 +80,9 @@ class Communicator:
         if self.peer_active:
             if max_f32 <= self._peer_cap[0] and max_i64 <= self._peer_cap[1]:
                 return True
+            # grow to the running maximum of both payloads, so callers alternating between shapes (per-head dropout:
+            # large f32 / small cm, then the reverse) re-create the IPC mapping at most once per new maximum
+            max_f32, max_i64 = max(max_f32, self._peer_cap[0]), max(max_i64, self._peer_cap[1])
             self._shutdown_peer()
         if self.world > 1 and not dist.is_initialized():
             raise RuntimeError("torch.distributed must be initialised first (it carries the IPC handles)")

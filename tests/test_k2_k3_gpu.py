@@ -392,7 +392,12 @@ def test_k2_tcgen05_forward_bf16(cuda_device, B, D, classes, monkeypatch):
     labels[::19, 0] = -100
     Wb = [w.to(torch.bfloat16).double() for w in Ws]
     exp = oh.heads_loss_fwd_bwd(emb.double(), Wb, bs, labels, oh.LOSS_FOCAL, 1.0, dtype=torch.float64)
+    # training calls of qualifying shapes take the one-launch fused kernel (exact fp32 weights, tests/test_k2_fused_gpu.py);
+    # the tcgen05 forward serves forward-only calls and the shapes the fused kernel refuses -- exercised here directly
+    from nkb_classification_b200 import _lib, ops
+    monkeypatch.setenv("NKBK_DISABLE_FUSED_HEADS", "1")
     r = run_k2(cuda_device, emb, Ws, bs, labels, oh.LOSS_FOCAL, 1.0, emb_dtype=torch.bfloat16)
+    assert ops.heads_last_path() == _lib.PATH_TC_FWD, "the tcgen05 forward did not run (silent FFMA fallback)"
     for t in range(len(classes)):
         assert rel_err(r["logits"][t], exp["logits"][t].numpy()) <= 2e-5, t
         assert rel_err(r["probs"][t], exp["probs"][t].numpy()) <= 2e-5, t
@@ -400,6 +405,7 @@ def test_k2_tcgen05_forward_bf16(cuda_device, B, D, classes, monkeypatch):
     assert rel_err(r["loss"][-1], float(exp["total"])) <= 2e-5
     monkeypatch.setenv("NKBK_DISABLE_TCGEN05", "1")
     f = run_k2(cuda_device, emb, Ws, bs, labels, oh.LOSS_FOCAL, 1.0, emb_dtype=torch.bfloat16)
+    assert ops.heads_last_path() == _lib.PATH_FFMA_FWD
     monkeypatch.delenv("NKBK_DISABLE_TCGEN05")
     for t in range(len(classes)):  # FFMA path keeps W in fp32: differs by the bf16 rounding of W only
         assert rel_err(r["logits"][t], f["logits"][t]) <= 1e-2
