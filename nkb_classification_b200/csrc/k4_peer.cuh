@@ -56,7 +56,9 @@ __device__ __forceinline__ int peer_task_of(const K2Seg& seg, int c) {
 // before, and joins again afterwards.  A wait that exceeds PEER_TIMEOUT_NS raises the status word (ctl[2] = r + 1)
 // instead of hanging; the step's results are then invalid (the kernels poison the loss with NaN).
 __device__ __forceinline__ void peer_publish(const PeerLinks& L, int r, long long par, int slice, unsigned int step) {
-    __threadfence_system();  // cumulative: orders the whole CTA's stores (joined by the barrier) before the flag
+    // st.release.sys is itself the (cumulative) system-scope release: it orders the whole CTA's payload stores -- joined
+    // to this thread by the barrier -- before the flag; a separate __threadfence_system() in front only added a second
+    // round trip to the peer
     st_release_sys(L.flags[r] + (par * L.world + L.rank) * PEER_MAX_SLICES + slice, step);
 }
 __device__ __forceinline__ void peer_wait(const PeerLinks& L, int r, long long par, int slice, unsigned int step) {

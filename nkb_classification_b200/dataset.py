@@ -45,6 +45,10 @@ def _imread_bgr(path: str) -> np.ndarray:
     return img
 
 
+def _row_pitch(w: int) -> int:
+    return (w * 3 + 15) // 16 * 16      # 16-byte aligned rows: K1's TMA path applies
+
+
 def _image_size(path: str) -> Tuple[int, int]:
     from PIL import Image
 
@@ -100,6 +104,22 @@ class _DescDataset(torch.utils.data.Dataset):
 
     def __getitem__(self, idx):
         return self.path_at(idx), self.box_at(idx), self.label_at(idx)
+
+    def describe(self, indices):
+        """One batch at once: (frame id per sample [n] int64, path of every id, boxes int64 [n,4] with -1 rows for
+        whole-image samples, collated target).  Generic per-sample walk; datasets that keep arrays override it."""
+        ids_of: Dict[str, int] = {}
+        n = len(indices)
+        ids = np.empty(n, dtype=np.int64)
+        boxes = np.full((n, 4), -1, dtype=np.int64)
+        labels = []
+        for j, i in enumerate(indices):
+            p, b, l = self[i]
+            ids[j] = ids_of.setdefault(p, len(ids_of))
+            if b is not None:
+                boxes[j] = b
+            labels.append(l)
+        return ids, list(ids_of), boxes, collate_targets(labels)
 
 
 class InferDataset(_DescDataset):
@@ -291,6 +311,7 @@ class AnnotatedYOLODataset(_DescDataset):
         base = Path(image_base_dir) if image_base_dir is not None else Path("/")
         image_dirs = [base / self.yaml_data["path"] / p for p in self.yaml_data[self.fold]]
         self.list_bbox = []
+        self._frame_sizes: Dict[str, Tuple[int, int]] = {}      # every frame's (h, w): sizes the device frame cache
         for image_filename in sorted(self.get_img_files(image_dirs)):
             image_filename = Path(image_filename)
             labels_dir = image_filename.parent.parent / "labels"
@@ -304,6 +325,7 @@ class AnnotatedYOLODataset(_DescDataset):
                 lines = fp.readlines()
             img_height, img_width = _image_size(str(image_filename))
             image_size = (img_height, img_width)
+            self._frame_sizes[str(image_filename)] = image_size
             true_boxes = []
             for line in lines:
                 if not line.split():
@@ -378,20 +400,93 @@ class AnnotatedYOLODataset(_DescDataset):
     def get_labels(self):
         return np.array([label for _, _, label in self.list_bbox])
 
+    def describe(self, indices):
+        if getattr(self, "_arr_len", -1) != len(self.list_bbox):       # (re)build the sample arrays once
+            paths: Dict[str, int] = {}
+            self._pid = np.array([paths.setdefault(p, len(paths)) for p, _, _ in self.list_bbox], dtype=np.int64)
+            self._plist = list(paths)
+            self._barr = np.array([b for _, b, _ in self.list_bbox], dtype=np.int64).reshape(-1, 4)
+            self._larr = np.array([l for _, _, l in self.list_bbox], dtype=np.int64)
+            self._arr_len = len(self.list_bbox)
+        idx = np.asarray(indices, dtype=np.int64)
+        uniq, inv = np.unique(self._pid[idx], return_inverse=True)
+        return inv.astype(np.int64), [self._plist[u] for u in uniq], self._barr[idx], torch.from_numpy(self._larr[idx])
+
+    def decoded_bytes(self) -> int:
+        """Bytes the decoded frames that carry at least one sample take in the device frame cache."""
+        used = {p for p, _, _ in self.list_bbox}
+        return sum((h * _row_pitch(w) + 255) // 256 * 256 for p, (h, w) in self._frame_sizes.items() if p in used)
+
+
+class InMemoryFrames(_DescDataset):
+    """Already-decoded frames with per-box samples (synthetic benchmarks, tests, callers that decode elsewhere -- e.g. a
+    video pipeline feeding `Evaluator.classify_crops`-style many-crops-per-frame work).  ``frames``: sequence of uint8
+    HWC arrays in cv2.imread's channel order (BGR); ``boxes`` [n,4] int or None (whole frames); ``frame_idx`` [n];
+    ``labels`` [n] int or dict name -> [n].  ``read_frame`` stands in for the decode, so the loader's decode count,
+    frame cache and ROI upload apply unchanged."""
+
+    def __init__(self, frames, frame_idx, labels, boxes=None, classes=None, transform=None):
+        self.frames, self.frame_idx = frames, np.asarray(frame_idx, dtype=np.int64)
+        self.boxes = None if boxes is None else np.asarray(boxes, dtype=np.int64).reshape(-1, 4)
+        self.labels = labels
+        self.transform = transform
+        if classes is None:
+            classes = ({k: sorted(set(np.asarray(v).tolist())) for k, v in labels.items()} if isinstance(labels, dict)
+                       else sorted(set(np.asarray(labels).tolist())))
+        self.classes = classes
+        self.class_to_idx, self.idx_to_class = get_classes_configs(classes)
+        self.reads = 0
+
+    def __len__(self):
+        return len(self.frame_idx)
+
+    def path_at(self, idx):
+        return f"mem://{int(self.frame_idx[idx])}"
+
+    def box_at(self, idx):
+        return None if self.boxes is None else tuple(int(v) for v in self.boxes[idx])
+
+    def label_at(self, idx):
+        if isinstance(self.labels, dict):
+            return {k: np.array(v[idx], dtype=np.int64) for k, v in self.labels.items()}
+        return np.array(self.labels[idx], dtype=np.int64)
+
+    def get_labels(self):
+        if isinstance(self.labels, dict):
+            return np.stack([np.asarray(self.labels[k]) for k in sorted(self.labels)], 1)
+        return np.asarray(self.labels)
+
+    def read_frame(self, path: str) -> np.ndarray:
+        self.reads += 1
+        return self.frames[int(path[6:])]
+
+    def describe(self, indices):
+        idx = np.asarray(indices, dtype=np.int64)
+        uniq, inv = np.unique(self.frame_idx[idx], return_inverse=True)
+        boxes = self.boxes[idx] if self.boxes is not None else np.full((len(idx), 4), -1, dtype=np.int64)
+        if isinstance(self.labels, dict):
+            target = {k: torch.from_numpy(np.asarray(v, dtype=np.int64)[idx]) for k, v in self.labels.items()}
+        else:
+            target = torch.from_numpy(np.asarray(self.labels, dtype=np.int64)[idx])
+        return inv.astype(np.int64), [f"mem://{int(u)}" for u in uniq], boxes, target
+
+    def decoded_bytes(self) -> int:
+        return sum((f.shape[0] * _row_pitch(f.shape[1]) + 255) // 256 * 256 for f in self.frames)
+
 
 # --------------------------------------------------------------------------------------------
-# loader: decode once per frame, stage uint8, one K1 launch per batch
+# loader: decode once per frame, keep decoded frames in HBM, one K1 launch per batch
 # --------------------------------------------------------------------------------------------
 def pack_frames(frames: Sequence[np.ndarray], staging: Optional[torch.Tensor] = None):
     """Lay frames of arbitrary sizes into one pinned uint8 buffer with 16-byte aligned rows (so K1's TMA path
-    applies).  Returns (buffer tensor view, int64 [F,4] descriptors, list of (h, w))."""
+    applies).  Returns (buffer tensor view, total bytes, int64 [F,4] descriptors, list of (h, w))."""
     descs, sizes, off = [], [], 0
     for f in frames:
         h, w = f.shape[:2]
-        pitch = (w * 3 + 15) // 16 * 16
+        pitch = _row_pitch(w)
         descs.append((off, h, w, pitch))
         sizes.append((h, w))
-        off += h * pitch
+        off += (h * pitch + 255) // 256 * 256
     total = max(off, 16)
     if staging is None or staging.numel() < total:
         staging = torch.empty(int(total * 1.25) + 4096, dtype=torch.uint8)
@@ -400,7 +495,7 @@ def pack_frames(frames: Sequence[np.ndarray], staging: Optional[torch.Tensor] = 
     buf = staging.numpy()
     for f, (o, h, w, pitch) in zip(frames, descs):
         buf[o: o + h * pitch].reshape(h, pitch)[:, : w * 3] = f.reshape(h, w * 3)
-    return staging, total, torch.tensor(descs, dtype=torch.int64), sizes
+    return staging, total, torch.tensor(descs, dtype=torch.int64).reshape(-1, 4), sizes
 
 
 def collate_targets(labels: list):
@@ -413,31 +508,95 @@ def collate_targets(labels: list):
     return torch.from_numpy(np.asarray(labels, dtype=np.int64))
 
 
+class DeviceFrameCache:
+    """Decoded frames resident in HBM, keyed by path: one arena, FIFO ring eviction.
+
+    K1 addresses its sources as `base + int64 offset`, so a batch can mix frames that were uploaded epochs ago with
+    frames uploaded a moment ago: from the second epoch on a dataset that fits uploads nothing and decodes nothing
+    (180 GB of HBM hold ~25 k decoded 1080p frames).  Entries referenced by a batch that is staged but whose K1 has
+    not run yet are pinned and never evicted; a frame that cannot be placed (arena full of pinned entries, or larger
+    than the arena) simply travels with its batch like an uncached one."""
+
+    ALIGN = 256
+
+    def __init__(self, device, capacity_bytes: int):
+        from collections import OrderedDict
+        self.cap = int(capacity_bytes) // self.ALIGN * self.ALIGN
+        self.buf = torch.empty(max(self.cap, self.ALIGN), dtype=torch.uint8, device=device)   # ("cpu" in host-logic tests)
+        self.map: "OrderedDict[str, Tuple[int, int, int, int, int]]" = OrderedDict()   # path -> (off, h, w, pitch, nbytes)
+        self.head = 0
+        self.evictions = 0
+
+    def get(self, path: str):
+        return self.map.get(path)
+
+    def _evict_range(self, lo: int, hi: int, pinned) -> bool:
+        while self.map:
+            path, e = next(iter(self.map.items()))       # insertion order == ring order: the oldest sits right after head
+            if e[0] < hi and e[0] + e[4] > lo:
+                if path in pinned:
+                    return False
+                self.map.popitem(last=False)
+                self.evictions += 1
+            else:
+                break
+        return True
+
+    def alloc(self, path: str, h: int, w: int, pinned) -> Optional[Tuple[int, int, int, int, int]]:
+        pitch = _row_pitch(w)
+        n = (h * pitch + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        if n > self.cap:
+            return None
+        if self.head + n > self.cap:
+            if not self._evict_range(self.head, self.cap, pinned):
+                return None
+            self.head = 0
+        if not self._evict_range(self.head, self.head + n, pinned):
+            return None
+        e = (self.head, h, w, pitch, n)
+        self.head += n
+        self.map[path] = e
+        return e
+
+
 class _IngestSlot:
-    """One stage of the frame-ingest ring: pinned uint8 staging, its device twin, and the two events that make reuse
-    safe (`copied`: H2D finished, recorded on the copy stream; `consumed`: K1 has read the device buffer, recorded on
-    the consumer's stream)."""
+    """One stage of the frame-ingest ring: pinned uint8 staging, its device twin (frames that travel with the batch), the
+    paths the batch pins in the frame cache, and the two events that make reuse safe (`copied`: H2D finished, recorded on
+    the copy stream; `consumed`: K1 has read its sources, recorded on the consumer's stream)."""
 
     def __init__(self):
         self.staging: Optional[torch.Tensor] = None
         self.dev: Optional[torch.Tensor] = None
         self.copied: Optional[torch.cuda.Event] = None
         self.consumed: Optional[torch.cuda.Event] = None
+        self.paths: set = set()
+        self.pinned: Dict[str, torch.Tensor] = {}
 
 
 class DeviceCropLoader:
     """DataLoader stand-in: batches of sample descriptors -> K1 -> (device tensor, target).
 
-    Frame ingest: each distinct frame of a batch is decoded ONCE (thread pool), packed as uint8
-    into a pinned staging buffer with 16-byte aligned rows and copied to the device as uint8 -- the reference decodes
-    per crop and ships fp32 (dataset.py:398-409, engine.py:40).  With ``prefetch`` > 0 a producer thread runs decode +
-    pack + H2D (on its own copy stream) for the next batches while the consumer's stream runs K1 / the model on the
-    current one; a ring of ``prefetch + 2`` slots with `copied` / `consumed` events keeps buffers from being reused
-    early.  ``prefetch = 0`` does the same work inline (one slot ring, still event-guarded)."""
+    Frame ingest, against the reference's decode-per-crop + fp32 H2D (dataset.py:398-409, engine.py:40):
+
+    * each distinct frame of a batch is decoded ONCE (thread pool) and copied to the device as uint8;
+    * ``frame_cache_bytes`` > 0: decoded frames stay in a device arena keyed by path (:class:`DeviceFrameCache`), so a
+      frame is decoded and uploaded once per EPOCH at most -- whatever the sampler does -- and not at all from the second
+      epoch on when the dataset fits;
+    * frames that do not go through the cache travel as their region of interest only: the bounding rectangle of the
+      boxes the batch takes from them (``roi_upload``), so a shuffled loader never ships more than the crops need;
+    * ``group_by_frame``: batches are cut from an order that keeps the samples of a frame adjacent (frames shuffled,
+      samples shuffled inside a frame; the draws of a weighted sampler are grouped the same way) -- the reference's
+      i.i.d. shuffle is the default, because grouping changes which samples share a batch;
+    * with ``prefetch`` > 0 a producer thread runs decode + pack + H2D (on its own copy stream) for the next batches
+      while the consumer's stream runs K1 / the model; a ring of ``prefetch + 2`` slots with `copied` / `consumed`
+      events keeps buffers from being reused early.  ``prefetch = 0`` does the same work inline.
+
+    ``stats`` counts decodes, uploaded bytes, cache hits and crops since construction (or ``reset_stats()``)."""
 
     def __init__(self, dataset: _DescDataset, batch_size: int, shuffle: bool = False, sampler=None,
                  num_workers: int = 0, drop_last: bool = False, device="cuda:0", out_dtype=torch.float32,
-                 prefetch: Optional[int] = None):
+                 prefetch: Optional[int] = None, frame_cache_bytes: int = 0, roi_upload: bool = True,
+                 group_by_frame: bool = False, sort_within_batch: bool = False):
         if dataset.transform is None:
             raise ValueError("the dataset needs a Transforms(pipeline) to compile for K1")
         self.dataset, self.batch_size, self.shuffle, self.sampler = dataset, int(batch_size), shuffle, sampler
@@ -448,21 +607,46 @@ class DeviceCropLoader:
         self.prefetch = int(prefetch) if prefetch is not None else (2 if num_workers and num_workers > 0 else 0)
         self._slots = [_IngestSlot() for _ in range(self.prefetch + 2)]
         self._copy_stream: Optional[torch.cuda.Stream] = None
+        self.roi_upload, self.group_by_frame = bool(roi_upload), bool(group_by_frame)
+        # reorder the samples INSIDE a batch by frame (same samples, same batch): K1 then walks the boxes of a frame
+        # back to back and their overlapping source rows hit L2 instead of HBM.  Off by default: it changes the order in
+        # which a batch's samples (and the logger's per-sample lists) appear.
+        self.sort_within_batch = bool(sort_within_batch)
+        self.cache = DeviceFrameCache(self.device, frame_cache_bytes) if frame_cache_bytes and frame_cache_bytes > 0 else None
+        self._read = getattr(dataset, "read_frame", None) or _imread_bgr      # in-memory datasets supply their own
         # train pipelines: where the per-sample augmentation parameters come from (None = Python's global `random`,
         # which is what albumentations draws from, so `random.seed(...)` governs it as in the reference)
         self.aug_rng = None
+        self.reset_stats()
+
+    def reset_stats(self):
+        self.stats = {"batches": 0, "crops": 0, "decodes": 0, "h2d_bytes": 0, "cache_hits": 0, "cache_inserts": 0,
+                      "roi_frames": 0, "whole_frames": 0}
 
     def __len__(self):
         n = len(self.sampler) if self.sampler is not None else len(self.dataset)
         return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
 
-    def _index_batches(self) -> Iterator[List[int]]:
+    def _order(self) -> List[int]:
         if self.sampler is not None:
             order = list(iter(self.sampler))
         elif self.shuffle:
             order = torch.randperm(len(self.dataset)).tolist()
         else:
             order = list(range(len(self.dataset)))
+        if self.group_by_frame and (self.sampler is not None or self.shuffle):
+            # keep the draw (which samples, how often) and make the samples of a frame adjacent: frames in the order of
+            # their first draw -- itself random -- and samples inside a frame in draw order
+            first, groups = {}, {}
+            for pos, i in enumerate(order):
+                p = self.dataset.path_at(i)
+                first.setdefault(p, pos)
+                groups.setdefault(p, []).append(i)
+            order = [i for p in sorted(groups, key=first.get) for i in groups[p]]
+        return order
+
+    def _index_batches(self) -> Iterator[List[int]]:
+        order = self._order()
         for i in range(0, len(order), self.batch_size):
             b = order[i: i + self.batch_size]
             if len(b) < self.batch_size and self.drop_last:
@@ -473,37 +657,139 @@ class DeviceCropLoader:
     def _stage(self, indices: List[int], k: int) -> dict:
         slot = self._slots[k]
         if slot.consumed is not None:
-            slot.consumed.synchronize()          # K1 of the batch that used this slot last has read the device buffer
-        samples = [self.dataset[i] for i in indices]
-        paths = [s[0] for s in samples]
-        uniq: Dict[str, int] = {}
-        for p in paths:
-            uniq.setdefault(p, len(uniq))
-        plist = list(uniq)
-        frames = list(self.pool.map(_imread_bgr, plist)) if self.pool else [_imread_bgr(p) for p in plist]
-        slot.staging, total, desc, sizes = pack_frames(frames, slot.staging)
-        fidx = np.array([uniq[p] for p in paths], dtype=np.int32)
-        boxes = np.array([s[1] if s[1] is not None else (0, 0, sizes[fi][1], sizes[fi][0])
-                          for s, fi in zip(samples, fidx)], dtype=np.int32).reshape(-1, 4)
-        validate_boxes(boxes, fidx, sizes)
-        aug = self.plan.draw(len(samples), self.aug_rng)     # in batch order: one producer, so the stream is reproducible
+            slot.consumed.synchronize()          # K1 of the batch that used this slot last has read its sources
+        slot.paths = set()                       # ... so that batch no longer pins anything in the frame cache
+        ids, plist, raw_boxes, target = self.dataset.describe(indices)
+        n = len(ids)
+        if self.sort_within_batch and n > 1:
+            perm = np.argsort(ids, kind="stable")
+            ids, raw_boxes = ids[perm], raw_boxes[perm]
+            pt = torch.from_numpy(perm)
+            if isinstance(target, dict):
+                target = {k_: v[pt] for k_, v in target.items()}
+            elif isinstance(target, torch.Tensor):
+                target = target[pt]
+            else:
+                target = [target[i] for i in perm]
+        fidx = ids.astype(np.int32)
+        has_box = raw_boxes[:, 0] >= 0
+        cache = self.cache
+        # frames of batches that are staged but not consumed yet must survive in the cache, and so must this batch's
+        pinned = set(plist)
+        for sl in self._slots:
+            pinned |= sl.paths
+        entries: List[Optional[tuple]] = [cache.get(p) if cache is not None else None for p in plist]
+        miss = [i for i, e in enumerate(entries) if e is None]
+        self.stats["cache_hits"] += len(plist) - len(miss)
+        mpaths = [plist[i] for i in miss]
+        decoded = list(self.pool.map(self._read, mpaths)) if self.pool else [self._read(p) for p in mpaths]
+        self.stats["decodes"] += len(decoded)
+        # per frame: where K1 finds it.  origin = (x, y) of the uploaded region inside the frame (boxes are shifted by it)
+        sizes = np.zeros((len(plist), 2), dtype=np.int64)            # (h, w) of the region K1 sees
+        origin = np.zeros((len(plist), 2), dtype=np.int64)
+        for i, e in enumerate(entries):
+            if e is not None:
+                sizes[i] = (e[1], e[2])
+        order = np.argsort(fidx, kind="stable")                      # samples grouped by frame, for the ROI rectangles
+        starts = np.searchsorted(fidx[order], np.arange(len(plist) + 1))
+        to_cache, to_travel = [], []            # (frame index, pixels)
+        for i, fr in zip(miss, decoded):
+            H, W = fr.shape[:2]
+            e = cache.alloc(plist[i], H, W, pinned) if cache is not None else None
+            if e is not None:
+                entries[i], sizes[i] = e, (H, W)
+                to_cache.append((i, fr))
+                continue
+            x0, y0, x1, y1 = 0, 0, W, H
+            rows = order[starts[i]: starts[i + 1]]
+            if self.roi_upload and len(rows) and has_box[rows].all():
+                a = raw_boxes[rows]
+                x0, y0 = max(0, int(a[:, 0].min())), max(0, int(a[:, 1].min()))
+                x1, y1 = min(W, int(a[:, 2].max())), min(H, int(a[:, 3].max()))
+                if x1 - x0 < 2 or y1 - y0 < 1:          # degenerate boxes: let validate_boxes speak on the full frame
+                    x0, y0, x1, y1 = 0, 0, W, H
+            self.stats["roi_frames" if (x1 - x0, y1 - y0) != (W, H) else "whole_frames"] += 1
+            origin[i] = (x0, y0)
+            sizes[i] = (y1 - y0, x1 - x0)
+            to_travel.append((i, fr[y0:y1, x0:x1]))
+        # one pinned staging buffer: [frames going into the cache | regions travelling with the batch]
+        pieces = [fr for _, fr in to_cache] + [fr for _, fr in to_travel]
+        slot.staging, total, pdesc, _ = pack_frames(pieces, slot.staging)
         dev = self.device
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=dev)
-        if slot.dev is None or slot.dev.numel() < total:
-            slot.dev = torch.empty(int(total * 1.25) + 4096, dtype=torch.uint8, device=dev)
         if slot.copied is None:
             slot.copied = torch.cuda.Event()
+        n_cache = len(to_cache)
+        travel_lo = int(pdesc[n_cache, 0]) if len(to_travel) else total
+        travel_bytes = total - travel_lo if len(to_travel) else 0
+        boxes = raw_boxes.copy()
+        if not has_box.all():                    # whole-image samples: the box is the frame
+            nb = ~has_box
+            boxes[nb, 0], boxes[nb, 1] = 0, 0
+            boxes[nb, 2], boxes[nb, 3] = sizes[fidx[nb], 1], sizes[fidx[nb], 0]
+        boxes[:, [0, 2]] -= origin[fidx, 0:1]
+        boxes[:, [1, 3]] -= origin[fidx, 1:2]
+        boxes = boxes.astype(np.int32)
+        validate_boxes(boxes, fidx, sizes)
+        aug = self.plan.draw(n, self.aug_rng)     # in batch order: one producer, so the stream is reproducible
         with torch.cuda.stream(self._copy_stream):
-            slot.dev[:total].copy_(slot.staging[:total], non_blocking=True)
+            # (allocated on the copy stream, so the caching allocator orders its first use after whatever freed the block;
+            # the consumer records its own use in _consume)
+            if travel_bytes and (slot.dev is None or slot.dev.numel() < travel_bytes):
+                slot.dev = torch.empty(int(travel_bytes * 1.25) + 4096, dtype=torch.uint8, device=dev)
+            base = cache.buf if cache is not None else slot.dev
+            if base is None:                         # no cache and nothing travels (cannot happen: every frame is a miss)
+                slot.dev = torch.empty(4096, dtype=torch.uint8, device=dev)
+                base = slot.dev
+            for j, (i, fr) in enumerate(to_cache):
+                o, e = int(pdesc[j, 0]), entries[i]
+                cache.buf[e[0]: e[0] + e[1] * e[3]].copy_(slot.staging[o: o + e[1] * e[3]], non_blocking=True)
+                self.stats["h2d_bytes"] += e[1] * e[3]
+            if travel_bytes:
+                slot.dev[:travel_bytes].copy_(slot.staging[travel_lo:total], non_blocking=True)
+                self.stats["h2d_bytes"] += travel_bytes
+            desc = np.zeros((len(plist), 4), dtype=np.int64)
+            for i, e in enumerate(entries):
+                if e is not None:
+                    desc[i] = (e[0], e[1], e[2], e[3])           # offset inside the arena (= base)
+            for j, (i, fr) in enumerate(to_travel):
+                o, h, w, pitch = (int(x) for x in pdesc[n_cache + j])
+                # K1 addresses sources as base + int64 offset: a region in the slot's buffer is reached from the arena
+                off = (slot.dev.data_ptr() - base.data_ptr()) + (o - travel_lo)
+                desc[i] = (off, h, w, pitch)
             meta = dict(boxes=torch.from_numpy(boxes).to(dev, non_blocking=True),
                         fidx=torch.from_numpy(fidx).to(dev, non_blocking=True),
-                        desc=desc.to(dev, non_blocking=True))
+                        desc=torch.from_numpy(desc).to(dev, non_blocking=True))
+            self.stats["h2d_bytes"] += boxes.nbytes + fidx.nbytes + desc.nbytes
             if aug is not None:
                 ops.upload_augment(aug, dev)      # train pipelines: parameters ride the copy stream too
             slot.copied.record(self._copy_stream)
-        meta.update(slot=k, total=total, aug=aug, target=collate_targets([s[2] for s in samples]))
+        self.stats["cache_inserts"] += n_cache
+        self.stats["batches"] += 1
+        self.stats["crops"] += n
+        slot.paths = set(plist) if cache is not None else set()
+        # targets stay host tensors, as default_collate yields them, but in pinned memory (the reference's DataLoader
+        # pins too): the consumer's `.to(device, non_blocking=True)` is then a true asynchronous copy, not a sync
+        if torch.cuda.is_available() and self.device.type == "cuda":
+            if isinstance(target, dict):
+                target = {k_: self._pinned(slot, k_, v) for k_, v in target.items()}
+            elif isinstance(target, torch.Tensor):
+                target = self._pinned(slot, "", target)
+        meta.update(slot=k, base=base, aug=aug, target=target)
         return meta
+
+    @staticmethod
+    def _pinned(slot, key, t: torch.Tensor) -> torch.Tensor:
+        """Copy a target tensor into the slot's pinned buffer (allocated once per slot and shape: no cudaHostAlloc per
+        batch).  Safe to reuse: the slot is recycled only after its batch's K1 -- enqueued after the consumer's
+        `.to(device)` of the previous targets on the same stream -- has completed."""
+        buf = slot.pinned.get(key)
+        if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
+            buf = torch.empty_like(t).pin_memory()
+            slot.pinned[key] = buf
+        buf.copy_(t)
+        return buf
 
     # ---- consumer side: K1 on the caller's current stream ----
     def _consume(self, meta: dict):
@@ -511,11 +797,13 @@ class DeviceCropLoader:
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(slot.copied)
         shared = [meta["boxes"], meta["fidx"], meta["desc"]]
+        if slot.dev is not None:
+            shared.append(slot.dev)
         if meta["aug"] is not None:
             shared += [t for t in ops.upload_augment(meta["aug"], self.device) if t is not None]
         for t in shared:
             t.record_stream(cur)                 # allocated on the copy stream, read on this one
-        img = ops.preprocess_crops(slot.dev[:meta["total"]], meta["boxes"], meta["fidx"], self.plan,
+        img = ops.preprocess_crops(meta["base"], meta["boxes"], meta["fidx"], self.plan,
                                    out_dtype=self.out_dtype, frame_desc=meta["desc"], aug=meta["aug"])
         if slot.consumed is None:
             slot.consumed = torch.cuda.Event()
@@ -574,12 +862,29 @@ def _device_of(data: dict):
     return data.get("device", "cuda:0")
 
 
+_LOADER_KEYS = ("device", "prefetch", "frame_cache_bytes", "roi_upload", "group_by_frame", "sort_within_batch")
+
+
+def _frame_cache_bytes(data: dict, device, dataset) -> int:
+    """``frame_cache_bytes``: bytes of HBM for decoded frames; 0 = off; "auto" (default for datasets whose frames are
+    shared by many samples) = what the dataset's decoded frames need, at most half of the free device memory."""
+    shared = data["type"] in ("AnnotatedYOLODataset", "InMemoryFrames")
+    v = data.get("frame_cache_bytes", "auto" if shared else 0)
+    if v == "auto":
+        if not torch.cuda.is_available() or not hasattr(dataset, "decoded_bytes"):
+            return 0
+        free, _ = torch.cuda.mem_get_info(torch.device(device))
+        return int(min(dataset.decoded_bytes() + (1 << 20), free // 2))
+    return int(v or 0)
+
+
 def get_dataset(data, pipeline):
     """dataset.py:541-629: same ``data`` keys (type, batch_size, num_workers, shuffle, drop_last,
-    weighted_sampling, dataset kwargs); optional extra key ``device``."""
+    weighted_sampling, dataset kwargs); optional extra keys ``device``, ``prefetch``, ``frame_cache_bytes``,
+    ``roi_upload``, ``group_by_frame`` (see :class:`DeviceCropLoader`)."""
     transform = Transforms(pipeline)
     kind = data["type"]
-    kwargs = {k: v for k, v in data.items() if k not in ("device", "prefetch")}
+    kwargs = {k: v for k, v in data.items() if k not in _LOADER_KEYS}
     if kind == "GroupsDataset":
         dataset = GroupsDataset(transform=transform, **kwargs)
     elif kind == "AnnotatedMultitaskDataset":
@@ -588,12 +893,18 @@ def get_dataset(data, pipeline):
         dataset = AnnotatedSingletaskDataset(transform=transform, **kwargs)
     elif kind == "AnnotatedYOLODataset":
         dataset = AnnotatedYOLODataset(transform=transform, **kwargs)
+    elif kind == "InMemoryFrames":       # synthetic / already-decoded frames (bench.py --api engine, tests)
+        dataset = data["dataset"]
+        dataset.transform = transform
     else:
         dataset = ImageFolder(data["root"], transform=transform)
     sampler = ImbalancedDatasetSampler(dataset) if data.get("weighted_sampling", False) else None
+    dev = _device_of(data)
     return DeviceCropLoader(dataset, batch_size=data["batch_size"], shuffle=data.get("shuffle", False), sampler=sampler,
                             num_workers=data.get("num_workers", 0), drop_last=data.get("drop_last", False),
-                            device=_device_of(data), prefetch=data.get("prefetch"))
+                            device=dev, prefetch=data.get("prefetch"), frame_cache_bytes=_frame_cache_bytes(data, dev, dataset),
+                            roi_upload=data.get("roi_upload", True), group_by_frame=data.get("group_by_frame", False),
+                            sort_within_batch=data.get("sort_within_batch", False))
 
 
 def get_inference_dataset(data, pipeline):

@@ -28,9 +28,51 @@ AUTOCAST_DTYPE = torch.bfloat16  # the reference autocasts to fp16 + GradScaler;
 
 
 class TrainPbar(tqdm):
+    """engine.py:6-17 of the reference, without its per-step ``loss.item()``: the postfix is refreshed from the device
+    loss every ``cfg.loss_display_every`` steps (default 50) -- one small D2H then, none otherwise."""
+
     def __init__(self, train_loader, leave, desc, cfg):
         super().__init__(train_loader, leave=leave, desc=desc, disable=getattr(cfg, "disable_tqdm", False))
         self.cfg = cfg
+        self._every = max(1, int(getattr(cfg, "loss_display_every", 50)))
+        self._seen = 0
+
+    def update_loss(self, loss):
+        """``loss``: what the reference passes (a tensor, or the criterion's dict for task='multi')."""
+        self._seen += 1
+        if self.disable or self._seen % self._every:
+            return
+        if isinstance(loss, dict):
+            if getattr(self.cfg, "show_full_current_loss_in_terminal", False):
+                vals = torch.stack([loss[k].detach().float().reshape(()) for k in loss]).tolist()     # one D2H
+                self.set_postfix_str(", ".join(f"loss {k}: {v:.4f}" for k, v in zip(loss, vals)))
+            else:
+                self.set_postfix_str(f"Loss: {loss['loss'].item():.4f}")
+        else:
+            self.set_postfix_str(f"Loss: {loss.item():.4f}")
+
+
+def sync_backbone_grads(model, comm) -> int:
+    """Sharded training (cfg.communicator, world > 1): the fused heads step all-reduces the head gradients itself, but
+    the embedding gradient it hands back -- and hence every backbone gradient -- covers the LOCAL rows only (already
+    divided by the GLOBAL denominators).  Sum them over the ranks before the optimizer steps, or an unfrozen backbone
+    silently diverges across ranks.  SUM, not mean: the division by the global batch has happened.  One flat
+    all-reduce over torch.distributed (the backbone is stock PyTorch; wrap it in DDP instead and this finds nothing
+    to do because DDP has averaged already -- do not combine the two).  Returns the number of tensors reduced."""
+    if comm is None or comm.world <= 1:
+        return 0
+    grads = [p.grad for p in model.emb_model.parameters() if p.requires_grad and p.grad is not None]
+    if not grads:
+        return 0
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        raise RuntimeError("sharded training with a trainable backbone needs torch.distributed (it carries the backbone "
+                           "gradient all-reduce); freeze the backbone or initialise the process group")
+    flat = torch._utils._flatten_dense_tensors(grads)
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    for g, r in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+        g.copy_(r)
+    return len(grads)
 
 
 def _criterion_cfg(criterion, cfg):
@@ -70,6 +112,7 @@ def train_epoch(model, train_loader, optimizer, scheduler, scaler, criterion, de
     model.train()
     epoch_logger.init_iter_logs()
     fused = _fused_for(model, criterion, cfg)
+    base_model = getattr(model, "_orig_mod", model)
     if fused is not None:
         fused.reset_confusion()
         epoch_logger.fused = fused
@@ -86,9 +129,11 @@ def train_epoch(model, train_loader, optimizer, scheduler, scaler, criterion, de
             out = fused(emb, target, train=True)
             total = out.loss[-1] if fused.names is not None else out.loss[0]
             scaler.scale(total).backward()
+            sync_backbone_grads(base_model, getattr(cfg, "communicator", None))
             scaler.step(optimizer)
             scaler.update()
-            epoch_logger.log_fused(out, fused.labels_tensor(target, img.device))
+            epoch_logger.log_fused(out, out.labels)
+            pbar.update_loss(out.loss_like_reference())
         else:
             with _autocast(cfg):
                 preds = model(img)
@@ -99,6 +144,7 @@ def train_epoch(model, train_loader, optimizer, scheduler, scaler, criterion, de
             scaler.step(optimizer)
             scaler.update()
             epoch_logger.log_iter(preds, target, loss)
+            pbar.update_loss(loss)
 
         if cfg.log_gradients:
             total_grad = 0
@@ -133,7 +179,7 @@ def val_epoch(model, val_loader, criterion, device, cfg, epoch_logger):
             with _autocast(cfg):
                 emb = model.emb_model(img)
             out = fused(emb, target, train=False)
-            epoch_logger.log_fused(out, fused.labels_tensor(target, img.device))
+            epoch_logger.log_fused(out, out.labels)
         else:
             with _autocast(cfg):
                 preds = model(img)

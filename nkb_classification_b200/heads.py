@@ -33,6 +33,7 @@ class HeadsOutput:
     pred: Optional[torch.Tensor]    # [B, T] int32
     seg: List[int]
     names: Optional[List[str]]
+    labels: Optional[torch.Tensor] = None   # int64 [B, T] on the device (what the kernels read; reused by the logger)
 
     def preds_like_reference(self):
         """Tensor (single task) or dict name -> logits view (multi task), as model.forward returns."""
@@ -184,9 +185,9 @@ class FusedHeads:
     def labels_tensor(self, target, device) -> torch.Tensor:
         """Reference targets (Tensor [B] or dict name -> Tensor [B]) -> contiguous int64 [B, T] on the device."""
         if isinstance(target, dict):
-            cols = [target[n].to(device=device, dtype=torch.int64).reshape(-1) for n in self.pack.names]
+            cols = [target[n].to(device=device, dtype=torch.int64, non_blocking=True).reshape(-1) for n in self.pack.names]
             return torch.stack(cols, dim=1).contiguous()
-        return target.to(device=device, dtype=torch.int64).reshape(-1, 1).contiguous()
+        return target.to(device=device, dtype=torch.int64, non_blocking=True).reshape(-1, 1).contiguous()
 
     def __call__(self, emb: torch.Tensor, target, train: bool) -> HeadsOutput:
         if not self.pack.in_sync():
@@ -199,7 +200,7 @@ class FusedHeads:
         loss = _FusedHeads.apply(emb, self.state, labels, train, *self.pack.params())
         bufs, pred = self.state["last"]
         return HeadsOutput(loss=loss, logits=bufs.logits, probs=bufs.probs, pred=pred, seg=self.pack.seg,
-                           names=self.pack.names)
+                           names=self.pack.names, labels=labels)
 
     def _per_head_dropout(self, emb: torch.Tensor, labels: torch.Tensor, train: bool) -> HeadsOutput:
         """Training with ``classifier_dropout > 0`` and several heads: every head applies its OWN ``nn.Dropout`` to
@@ -241,7 +242,8 @@ class FusedHeads:
             total = total + l                                            # losses.py:140-147: unweighted sum
         return HeadsOutput(loss=torch.stack(losses + [total]), logits=torch.cat(logits, 1),
                            probs=None if probs[0] is None else torch.cat(probs, 1),
-                           pred=None if preds[0] is None else torch.cat(preds, 1), seg=pack.seg, names=pack.names)
+                           pred=None if preds[0] is None else torch.cat(preds, 1), seg=pack.seg, names=pack.names,
+                           labels=labels)
 
     # epoch-level confusion counts (already summed over ranks)
     def reset_confusion(self):

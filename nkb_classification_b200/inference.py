@@ -38,6 +38,7 @@ def inference(model: torch.nn.Module, loader, classes: Union[list, dict], save_p
     base = getattr(model, "_orig_mod", model)
     pack = HeadPack(base) if isinstance(base, (SingletaskClassifier, MultitaskClassifier)) else None
     preds_dev, paths_all = [], []
+    bufs_by_shape = {}    # one set of K2 buffers per batch shape (the last batch of a folder is usually shorter)
     for imgs, img_paths in tqdm(loader, leave=False, desc="Inference", disable=getattr(cfg, "disable_tqdm", False)):
         imgs = imgs.float().to(device)
         with torch.autocast(device_type="cuda", dtype=torch.bfloat16, enabled=cfg.enable_mixed_presicion):
@@ -47,7 +48,10 @@ def inference(model: torch.nn.Module, loader, classes: Union[list, dict], save_p
                 out = model(imgs)
         if pack is not None:
             emb = emb.contiguous()
-            bufs = ops.HeadsBuffers(emb.shape[0], pack.D, pack.seg, emb.device, want_probs=False, want_grads=False)
+            bufs = bufs_by_shape.get(emb.shape[0])
+            if bufs is None:
+                bufs = ops.HeadsBuffers(emb.shape[0], pack.D, pack.seg, emb.device, want_probs=False, want_grads=False)
+                bufs_by_shape[emb.shape[0]] = bufs
             pred = torch.empty((emb.shape[0], len(pack.seg) - 1), dtype=torch.int32, device=emb.device)
             ops.heads_fwd_loss_bwd(emb, pack.W_cat, pack.b_cat, None, bufs, out_pred=pred)   # K2 forward + fused argmax
             names = pack.names

@@ -42,9 +42,9 @@ class BaseLogger:
         """``out``: heads.HeadsOutput of this step; ``labels``: int64 [B, T] on the device."""
         self._seg, self._names = out.seg, out.names
         self._gt.append(labels)
-        self._conf.append(out.probs.clone())
-        self._pred.append(out.pred.clone())
-        self._loss.append(out.loss.detach().clone())
+        self._conf.append(out.probs.clone())      # the probabilities live in the step's reusable buffers: keep a copy
+        self._pred.append(out.pred)               # predictions and the loss vector are this step's own tensors
+        self._loss.append(out.loss.detach())
 
     # ---- reference-compatible entry (pred / true / loss as the reference passes them) ----
     def log_iter(self, pred, true, loss):
@@ -70,8 +70,13 @@ class BaseLogger:
             self._loss.append(torch.cat([l, l]))
 
     def log_images_if_needed(self, images):
+        """logging.py:283-285 of the reference keeps the WHOLE first batch on the host for the image grid of
+        ``log_images`` (8 per row).  With the batches this path is built for (thousands of crops) that is a multi-GB
+        pageable D2H per epoch, so only the first ``cfg.example_images`` (default 64 = 8 grid rows) are kept;
+        ``cfg.example_images = None`` restores the reference's whole-batch copy."""
         if self.epoch_images_example is None:
-            self.epoch_images_example = images.to("cpu")
+            k = getattr(self.cfg, "example_images", 64)
+            self.epoch_images_example = (images if k is None else images[: int(k)]).to("cpu")
 
     def get_epoch_results(self):
         """One D2H per quantity, then the reference's structure (logging.py:287-294)."""

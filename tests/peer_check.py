@@ -41,9 +41,14 @@ def main():
 
     # (classes, D, frames, crops per frame, loss, gamma): an odd reduce-buffer length, a multi-CTA payload, 1 head
     # (the second case outgrows the inbox sized for the first: exercises the collective re-initialisation)
+    # The first three take the fused heads step (the exchange is the epilogue of k2_fused_step), the fourth is too
+    # large for it and goes through the separate launches (k4_peer_allreduce_finalize); the last one shards 7 frames
+    # unevenly, so the ranks run DIFFERENT grids against the same payload slicing.
     cases = [((3, 5), 132, 6, 5, "FocalLoss", 2.0),
              ((2, 3, 4, 7, 14), 768, 16, 8, "FocalLoss", 1.0),
-             ((10,), 2048, 8, 16, "CrossEntropyLoss", 0.0)]
+             ((10,), 2048, 8, 16, "CrossEntropyLoss", 0.0),
+             ((3, 70, 2, 5), 1028, 8, 4, "FocalLoss", 2.0),
+             ((10,), 2048, 7, 40, "CrossEntropyLoss", 0.0)]
     for ci, (classes, D, F, per, loss, gamma) in enumerate(cases):
         g = torch.Generator().manual_seed(5 + ci)
         B = F * per
@@ -65,6 +70,8 @@ def main():
         for s in range(steps):
             bufs = peer.heads_step(e_loc, Wd, bd, l_loc)
             torch.cuda.synchronize()
+            from nkb_classification_b200 import _lib, ops
+            assert ops.heads_last_path() == (_lib.PATH_FFMA_FWD if D == 1028 else _lib.PATH_FUSED), "unexpected heads path"
             assert peer.transport == "peer" and comm.peer_active, "peer transport was not established"
             assert comm.peer_status() == 0, f"peer wait timed out: status {comm.peer_status()}"
             assert torch.equal(peer.cm, (s + 1) * single.cm), f"case {ci} step {s}: confusion counts differ"

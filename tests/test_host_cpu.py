@@ -109,9 +109,60 @@ def test_pack_frames_aligns_rows():
     staging, total, desc, sizes = D.pack_frames(frames)
     buf = staging.numpy()
     for f, (off, h, w, pitch) in zip(frames, desc.tolist()):
-        assert off % 16 == 0 and pitch % 16 == 0 and pitch >= w * 3
+        assert off % 256 == 0 and pitch % 16 == 0 and pitch >= w * 3
         assert np.array_equal(buf[off: off + h * pitch].reshape(h, pitch)[:, : w * 3].reshape(h, w, 3), f)
-    assert sizes == [(5, 7), (3, 16), (4, 33)] and total == sum(d[1] * d[3] for d in desc.tolist())
+    assert sizes == [(5, 7), (3, 16), (4, 33)] and total >= sum(d[1] * d[3] for d in desc.tolist())
+    assert D.pack_frames([])[2].shape == (0, 4)
+
+
+def test_frame_cache_ring_allocator():
+    """DeviceFrameCache: FIFO ring over one arena, pinned entries are never evicted, oversize frames are refused."""
+    from nkb_classification_b200 import dataset as D
+    c = D.DeviceFrameCache("cpu", 4 * 4096)              # room for four 4096-byte frames (32 x 42 px -> pitch 128)
+    h, w = 32, 42
+    assert D._row_pitch(w) == 128
+    e = [c.alloc(f"f{i}", h, w, set()) for i in range(4)]
+    assert [x[0] for x in e] == [0, 4096, 8192, 12288] and list(c.map) == ["f0", "f1", "f2", "f3"]
+    assert c.get("f2") == (8192, h, w, 128, 4096)
+    x = c.alloc("f4", h, w, set())                        # wraps: evicts the oldest
+    assert x[0] == 0 and "f0" not in c.map and c.evictions == 1 and list(c.map) == ["f1", "f2", "f3", "f4"]
+    assert c.alloc("f5", h, w, {"f1"}) is None            # the entry in the way is pinned: refused, nothing evicted
+    assert list(c.map) == ["f1", "f2", "f3", "f4"]
+    y = c.alloc("f5", h, w, {"f3"})
+    assert y[0] == 4096 and list(c.map) == ["f2", "f3", "f4", "f5"]
+    assert c.alloc("big", 1000, 1000, set()) is None      # larger than the arena
+    z = c.alloc("tall", 64, 42, set())                    # 8192 bytes at head 8192: evicts f2 and f3
+    assert z[0] == 8192 and list(c.map) == ["f4", "f5", "tall"]
+
+
+def test_group_by_frame_keeps_the_draw_and_groups_it():
+    from nkb_classification_b200 import dataset as D, transforms as T
+    rng = np.random.default_rng(0)
+    fidx = np.repeat(np.arange(6), 5)
+    ds = D.InMemoryFrames([None] * 6, fidx, labels=rng.integers(0, 3, 30), boxes=np.tile([0, 0, 8, 8], (30, 1)),
+                          transform=D.Transforms(plain_pipeline(T)))
+    torch.manual_seed(0)
+    plain = D.DeviceCropLoader(ds, batch_size=7, shuffle=True, device="cpu")
+    grouped = D.DeviceCropLoader(ds, batch_size=7, shuffle=True, device="cpu", group_by_frame=True)
+    torch.manual_seed(3)
+    a = plain._order()
+    torch.manual_seed(3)
+    b = grouped._order()
+    assert sorted(a) == sorted(b) == list(range(30))      # same samples, each once
+    frames_b = [int(fidx[i]) for i in b]
+    runs = [f for k, f in enumerate(frames_b) if k == 0 or frames_b[k - 1] != f]
+    assert len(runs) == 6                                  # every frame is one contiguous run
+    first = []
+    for i in a:
+        if int(fidx[i]) not in first:
+            first.append(int(fidx[i]))
+    assert runs == first                                   # frames in the order of their first draw
+    smp = D.ImbalancedDatasetSampler(ds)
+    w = D.DeviceCropLoader(ds, batch_size=7, sampler=smp, device="cpu", group_by_frame=True)
+    torch.manual_seed(5)
+    drawn = sorted(iter(smp))
+    torch.manual_seed(5)
+    assert sorted(w._order()) == drawn                     # the weighted draw (with its repeats) is kept
 
 
 def test_factories_raise_like_the_reference():

@@ -112,3 +112,43 @@ def test_peer_setup_falls_back_collectively_gloo(tmp_path):
     world, port = 2, _free_port()
     mp.spawn(_peer_fallback_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / f"peer_ok{r}").exists() for r in range(world))
+
+
+def _backbone_sync_worker(rank, world, port, out_dir):
+    """engine.sync_backbone_grads: with a trainable backbone the embedding gradient the fused heads return covers the
+    LOCAL rows (already divided by the GLOBAL denominators), so the backbone gradients must be SUMMED over the ranks:
+    after it every rank holds the gradient of the unsharded batch."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from types import SimpleNamespace
+    from nkb_classification_b200.engine import sync_backbone_grads
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(12, 5, generator=g, dtype=torch.float64)
+    w_head = torch.randn(5, 3, generator=g, dtype=torch.float64)
+
+    def make():
+        torch.manual_seed(0)
+        m = torch.nn.Module()
+        m.emb_model = torch.nn.Linear(5, 5).double()
+        m.frozen = torch.nn.Linear(2, 2)
+        return m
+
+    full = make()
+    (full.emb_model(x) @ w_head).sum().div(12).backward()               # the unsharded mean loss
+    mine = make()
+    lo, hi = rank * 6, rank * 6 + 6
+    (mine.emb_model(x[lo:hi]) @ w_head).sum().div(12).backward()        # local rows, GLOBAL denominator
+    comm = SimpleNamespace(world=world, rank=rank)
+    assert sync_backbone_grads(mine, comm) == 2                         # weight + bias; the module without grads is skipped
+    for a, b in zip(mine.emb_model.parameters(), full.emb_model.parameters()):
+        assert torch.allclose(a.grad, b.grad, rtol=1e-12, atol=1e-15)
+    assert sync_backbone_grads(mine, SimpleNamespace(world=1, rank=0)) == 0
+    dist.barrier()
+    dist.destroy_process_group()
+    open(os.path.join(out_dir, f"bb_ok{rank}"), "w").write("ok")
+
+
+def test_backbone_gradients_are_summed_over_ranks_gloo(tmp_path):
+    world, port = 2, _free_port()
+    mp.spawn(_backbone_sync_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"bb_ok{r}").exists() for r in range(world))
