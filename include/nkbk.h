@@ -187,6 +187,12 @@ int nkbk_heads_train_step(const void* emb, int emb_dtype, int B, int D, const fl
                           int64_t n_cm, float* out_loss, int exchange, void* workspace, size_t workspace_bytes,
                           void* stream);
 
+/* Optional hint for the NEXT nkbk_heads_* call of this thread: an identifier of the contents of W_cat that changes
+ * whenever the weights change (e.g. torch's tensor version counter) and is never 0.  The tcgen05 forward keeps a bf16
+ * copy of the weights in the caller's workspace; with the hint it re-packs that copy only when the version differs from
+ * the one the workspace holds -- a validation or inference loop packs once.  Without the hint every call re-packs. */
+void nkbk_heads_weights_version(int64_t version);
+
 /* Which kernels served the calling thread's last nkbk_heads_step / nkbk_heads_train_step / nkbk_heads_fwd_loss_bwd:
  * NKBK_PATH_FUSED (k2_fused_step, one launch), NKBK_PATH_TC_FWD (tcgen05 forward + dW kernel) or NKBK_PATH_FFMA_FWD
  * (exact-fp32 FFMA forward + dW kernel).  Lets a caller see a fallback instead of guessing it from timings. */
@@ -194,7 +200,7 @@ enum { NKBK_PATH_FFMA_FWD = 1, NKBK_PATH_TC_FWD = 2, NKBK_PATH_FUSED = 4 };
 int nkbk_heads_last_path(void);
 
 /* Debug helper (host-synchronous): per-CTA phase time stamps of the last fused nkbk_heads_* launch made with the
- * environment variable NKBK_FUSED_TIMING=1 (profiles/tools/k2_phases.py).  out_host: uint64 [n_ctas][12]; returns the
+ * environment variable NKBK_FUSED_TIMING=1 (profiles/tools/k2_phases.py).  out_host: uint64 [n_ctas][16]; returns the
  * number of CTAs written, 0 when there is nothing to report. */
 int nkbk_debug_fused_timing(uint64_t* out_host, int max_ctas);
 
@@ -224,6 +230,16 @@ int nkbk_loss_fwd_bwd(const void* logits, int dtype, int B, int ld, const int32_
                       const int64_t* labels, int loss_kind, float gamma, const float* class_weight,
                       int64_t ignore_index, float* out_probs, float* dlogits, float* out_loss, void* workspace,
                       size_t workspace_bytes, void* stream);
+
+/* The UNREDUCED loss: FocalLoss(reduction="sum" | "none") of the reference (losses.py:87-94).
+ *   out_row_loss  fp32 [B][T]: the loss term of every (row, task) -- -alpha (1 - pt)^gamma log pt, or the weighted
+ *                 cross-entropy term -- 0 for rows whose label is ignore_index (or outside [0, C_t))
+ *   dlogits       optional fp32 [B][NC] = d(row loss of the row)/d(logit), NOT divided by anything
+ *   workspace     >= nkbk_loss_workspace_bytes(B, T)
+ * "sum" is the sum of the row terms, "none" their vector over the kept rows; both are a few bytes of host glue. */
+int nkbk_loss_rows(const void* logits, int dtype, int B, int ld, const int32_t* seg_offsets, int T,
+                   const int64_t* labels, int loss_kind, float gamma, const float* class_weight, int64_t ignore_index,
+                   float* out_row_loss, float* dlogits, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------
  * K3  per-task argmax + confusion-matrix accumulation

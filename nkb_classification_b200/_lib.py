@@ -52,10 +52,13 @@ SYMBOLS = {
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p,
                                       c_size_t, c_void_p]),
     "nkbk_heads_last_path": (c_int, []),
+    "nkbk_heads_weights_version": (None, [c_int64]),
     "nkbk_debug_fused_timing": (c_int, [c_void_p, c_int]),
     "nkbk_loss_workspace_bytes": (c_int64, [c_int, c_int]),
     "nkbk_loss_fwd_bwd": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_int32), c_int, c_void_p, c_int, c_float,
                                   c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "nkbk_loss_rows": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_int32), c_int, c_void_p, c_int, c_float,
+                               c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "nkbk_heads_finalize": (c_int, [c_void_p, c_int, POINTER(c_int32), c_int, c_void_p, c_void_p, c_void_p, c_int64,
                                     c_void_p]),
     "nkbk_heads_demb": (c_int, [c_void_p, c_void_p, c_void_p, POINTER(c_int32), c_int, c_int, c_int, c_void_p, c_void_p,

@@ -44,6 +44,7 @@ struct K2FwdParams {
     float* dlogits;
     int32_t* out_pred;     // optional [B][T]: per-task argmax (K3 fused into the forward epilogue)
     unsigned long long* cm_step;  // optional confusion counts to add to (needs labels)
+    float* row_loss;       // optional [B][T]: the loss term of every (row, task), 0 where ignored (nkbk_loss_rows)
     float* loss_part;      // [fwd_blocks][2T]
     unsigned int* counters;  // zeroed here for the dW kernel that follows
     int n_counters;
@@ -58,6 +59,9 @@ struct K2FwdParams {
 // will write (0 = shape not supported, caller falls back to the FFMA kernel), < 0 on error.
 int launch_k2_tc_forward(const K2FwdParams& p, void* wb_workspace, cudaStream_t st);
 int64_t k2_tc_workspace_floats(int B, int D, int NC);
+// nkbk_heads_weights_version: the hint covers exactly one heads call, whichever kernels end up serving it
+void set_weights_version(int64_t v);
+int64_t take_weights_version();
 
 // k2_fused.cu: the whole training step of the heads (forward, loss, K3, dW / db, cross-CTA sum and -- by mode -- the
 // finalize or the K4' exchange + finalize) as one persistent cooperative kernel.  Returns 1 when launched, 0 when the

@@ -50,7 +50,7 @@ constexpr int KF_TILE_ROWS = 8;         // rows per ring stage (4 when shared me
 constexpr int KF_STAGES = 2;
 constexpr int KF_NCB = 16;              // classes per forward pass
 constexpr int KF_MAX_SMEM_HIST = 4096;  // confusion bins privatised per CTA in shared memory
-constexpr int KF_TIMING_SLOTS = 12;
+constexpr int KF_TIMING_SLOTS = 16;
 constexpr int KF_Y_IGN = 0x40000000;    // shared-memory label code: the label equals ignore_index (K3 still counts it)
 constexpr int KF_MAX_ACC = 64;          // dW accumulator registers per thread: 4 * NCP * KQ
 
@@ -827,13 +827,17 @@ __global__ void __launch_bounds__(KF_THREADS, 1) k2_fused_step(const KFParams p)
         }
     }
     __syncthreads();
+    if (p.timing != nullptr && tid == 0) p.timing[blockIdx.x * KF_TIMING_SLOTS + 12] = (unsigned long long)clock64();
     if (tid < world && tid != rank)
         for (int sl = blockIdx.x; sl < nsl; sl += G_ctas) peer_publish(L, tid, par, sl, step);
+    if (p.timing != nullptr && tid == 0) p.timing[blockIdx.x * KF_TIMING_SLOTS + 13] = (unsigned long long)clock64();
+
     // wait + rank-ordered sum + finalize, slice by slice (all pushes of this CTA are out: no wait can block a push)
     bool have_gtail = false;
     for (int sl = blockIdx.x; sl < nsl; sl += G_ctas) {
         if (tid < world && tid != rank) peer_wait(L, tid, par, sl, step);
         __syncthreads();
+        if (p.timing != nullptr && tid == 0 && sl == (int)blockIdx.x) p.timing[blockIdx.x * KF_TIMING_SLOTS + 14] = (unsigned long long)clock64();
         if (!have_gtail) {   // global loss sums / denominators in rank order: identical in every CTA of every rank
             const long long tail_off = L.cap_vecs + (long long)sl * PEER_TAIL_VECS;
             if (tid < 2 * T) {
@@ -884,6 +888,10 @@ __global__ void __launch_bounds__(KF_THREADS, 1) k2_fused_step(const KFParams p)
     }
     // the last CTA to finish publishes the losses (NaN when a peer wait timed out) and advances the step counter
     __syncthreads();
+    if (p.timing != nullptr && tid == 0) {
+        p.timing[blockIdx.x * KF_TIMING_SLOTS + 10] = (unsigned long long)clock64();
+        p.timing[blockIdx.x * KF_TIMING_SLOTS + 11] = kf_globaltimer();
+    }
     if (tid == 0) {
         __threadfence();
         last_s = atomicAdd(L.ctl + 1, 1u) == gridDim.x - 1u;
@@ -1067,8 +1075,9 @@ int launch_k2_fused(const K2FwdParams& f, int emb_dtype, float* reduce_buf, floa
 }  // namespace nkbk
 
 // Debug helper (host-synchronous): the per-CTA phase stamps of the last fused launch made with NKBK_FUSED_TIMING=1.
-// out_host: [n_ctas][12] = {globaltimer ns at entry, clock64 at: entry, tables done, weights in, pass 1 done, epilogue
-// done, pass 2 done, partials written, grid barrier passed, reduce set up, finalize done, globaltimer ns at exit}.
+// out_host: [n_ctas][16] = {globaltimer ns at entry, clock64 at: entry, tables done, weights in, pass 1 done, epilogue
+// done, pass 2 done, partials written, grid barrier passed, reduce set up, kernel work done, globaltimer ns at exit,
+// then (exchange over peer memory only) clock64 at: pushes done, flags published, first slice's peers arrived, -}.
 // Returns the number of CTAs written (0 when no timed launch happened on the current device).
 extern "C" int nkbk_debug_fused_timing(uint64_t* out_host, int max_ctas) {
     int dev = 0;

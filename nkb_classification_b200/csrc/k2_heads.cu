@@ -165,6 +165,7 @@ __device__ __forceinline__ void heads_row_epilogue(const K2FwdParams& p, const f
         }
         qs[idx] = q;
         ys[idx] = yf;
+        if (p.row_loss != nullptr && row < p.B) p.row_loss[(int64_t)row * T + t] = loss_i;
         lt[r * 2 * T + t] = loss_i;
         lt[r * 2 * T + T + t] = den_i;
     }
@@ -710,6 +711,7 @@ static int heads_step_impl(const void* emb, int emb_dtype, int B, int D, const f
                            size_t workspace_bytes, void* stream, int mode, float* out_loss, int64_t* cm_total,
                            int64_t n_cm, int* fused_done) {
     *fused_done = 0;
+    const int64_t w_version = take_weights_version();   // consumed here, so that it can never leak into a later call
     K2Seg seg;
     int rc = fill_seg(seg, seg_offsets, T, "nkbk_heads_fwd_loss_bwd");
     if (rc) return rc;
@@ -742,6 +744,7 @@ static int heads_step_impl(const void* emb, int emb_dtype, int B, int D, const f
     p.emb = emb; p.W = W_cat; p.bias = b_cat; p.labels = labels; p.class_weight = class_weight;
     p.out_logits = out_logits; p.out_probs = out_probs; p.dlogits = dlogits;
     p.out_pred = out_pred;
+    p.row_loss = nullptr;
     p.cm_step = (cm_step != nullptr && labels != nullptr) ? reinterpret_cast<unsigned long long*>(cm_step) : nullptr;
     p.loss_part = ws + L.loss_part;
     p.counters = reinterpret_cast<unsigned int*>(ws + L.counters);
@@ -764,6 +767,7 @@ static int heads_step_impl(const void* emb, int emb_dtype, int B, int D, const f
     int loss_parts = L.fwd_blocks;  // rows of the per-warp loss / denominator partial table
     int tc = 0;
     if (emb_dtype == NKBK_BF16) {   // bf16 embeddings: tcgen05 / TMEM / TMA forward when the shape allows
+        set_weights_version(w_version);
         tc = launch_k2_tc_forward(p, ws + L.tc_w, st);
         if (tc < 0) return tc;
         if (tc > 0) loss_parts = tc;
@@ -893,7 +897,7 @@ extern "C" int nkbk_loss_fwd_bwd(const void* logits, int dtype, int B, int ld, c
     K2FwdParams p;
     p.emb = nullptr; p.W = nullptr; p.bias = nullptr; p.labels = labels; p.class_weight = class_weight;
     p.out_logits = nullptr; p.out_probs = out_probs; p.dlogits = dlogits; p.loss_part = ws;
-    p.out_pred = nullptr; p.cm_step = nullptr;
+    p.out_pred = nullptr; p.cm_step = nullptr; p.row_loss = nullptr;
     p.counters = nullptr; p.n_counters = 0;
     p.B = B; p.D = 0; p.NC = NC; p.loss_kind = loss_kind; p.gamma = gamma; p.ignore_index = ignore_index; p.seg = seg;
     const size_t smem = (size_t)(K2_FWD_ROWS * (2 * NC + 6 * T)) * sizeof(float);
@@ -906,6 +910,39 @@ extern "C" int nkbk_loss_fwd_bwd(const void* logits, int dtype, int B, int ld, c
     if (nb > 148 * 8) nb = 148 * 8;
     k2_loss_normalise<<<nb, 256, 0, st>>>(dlogits, B, NC, seg, sums, out_loss);
     NKBK_CHECK_LAUNCH("k2_loss_normalise");
+    return NKBK_OK;
+}
+
+extern "C" int nkbk_loss_rows(const void* logits, int dtype, int B, int ld, const int32_t* seg_offsets, int T,
+                              const int64_t* labels, int loss_kind, float gamma, const float* class_weight,
+                              int64_t ignore_index, float* out_row_loss, float* dlogits, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+    K2Seg seg;
+    int rc = fill_seg(seg, seg_offsets, T, "nkbk_loss_rows");
+    if (rc) return rc;
+    const int NC = seg.off[T];
+    NKBK_CHECK_ARG(B >= 0 && ld >= NC, "nkbk_loss_rows: B=%d ld=%d NC=%d", B, ld, NC);
+    NKBK_CHECK_ARG(dtype == NKBK_F32 || dtype == NKBK_BF16, "nkbk_loss_rows: dtype=%d", dtype);
+    NKBK_CHECK_ARG(loss_kind == NKBK_LOSS_CE || loss_kind == NKBK_LOSS_FOCAL, "nkbk_loss_rows: loss_kind=%d", loss_kind);
+    NKBK_CHECK_ARG(out_row_loss && workspace && labels, "nkbk_loss_rows: NULL out_row_loss/workspace/labels");
+    if (B == 0) return NKBK_OK;
+    NKBK_CHECK_ARG(logits != nullptr, "nkbk_loss_rows: NULL logits");
+    if ((int64_t)workspace_bytes < nkbk_loss_workspace_bytes(B, T)) {
+        set_error("nkbk_loss_rows: workspace %zu < %lld bytes", workspace_bytes, (long long)nkbk_loss_workspace_bytes(B, T));
+        return NKBK_E_ARG;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int blocks = (B + K2_FWD_ROWS - 1) / K2_FWD_ROWS;
+    K2FwdParams p;
+    p.emb = nullptr; p.W = nullptr; p.bias = nullptr; p.labels = labels; p.class_weight = class_weight;
+    p.out_logits = nullptr; p.out_probs = nullptr; p.dlogits = dlogits; p.loss_part = static_cast<float*>(workspace);
+    p.out_pred = nullptr; p.cm_step = nullptr; p.row_loss = out_row_loss;
+    p.counters = nullptr; p.n_counters = 0;
+    p.B = B; p.D = 0; p.NC = NC; p.loss_kind = loss_kind; p.gamma = gamma; p.ignore_index = ignore_index; p.seg = seg;
+    const size_t smem = (size_t)(K2_FWD_ROWS * (2 * NC + 6 * T)) * sizeof(float);
+    if (dtype == NKBK_F32) k2_loss_on_logits<float><<<blocks, 32, smem, st>>>(p, static_cast<const float*>(logits), ld);
+    else k2_loss_on_logits<__nv_bfloat16><<<blocks, 32, smem, st>>>(p, static_cast<const __nv_bfloat16*>(logits), ld);
+    NKBK_CHECK_LAUNCH("k2_loss_on_logits");
     return NKBK_OK;
 }
 

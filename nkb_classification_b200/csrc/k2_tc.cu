@@ -431,6 +431,23 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tw, const K2FwdPa
     return NKBK_OK;
 }
 
+constexpr int TC_PACK_CACHE = 16;
+struct TcPackEntry {
+    const void* wb = nullptr;
+    const void* W = nullptr;
+    int64_t version = 0;
+    int NC = 0, D = 0, ctas = 0;
+};
+static TcPackEntry g_pack_cache[TC_PACK_CACHE];
+static unsigned g_pack_next = 0;
+static thread_local int64_t g_weights_version = 0;
+void set_weights_version(int64_t v) { g_weights_version = v; }
+int64_t take_weights_version() {
+    const int64_t v = g_weights_version;
+    g_weights_version = 0;
+    return v;
+}
+
 int launch_k2_tc_forward(const K2FwdParams& p, void* ws_v, cudaStream_t st) {
     const int npad = tc_npad(p.NC);
     if (npad == 0 || p.seg.T > TC_MAX_TASKS || p.D % TC_BK != 0 || p.B < 1) return 0;
@@ -447,7 +464,18 @@ int launch_k2_tc_forward(const K2FwdParams& p, void* ws_v, cudaStream_t st) {
     CUtensorMap ta, tw;
     if (!make_tmap_bf16_2d(&ta, p.emb, (uint64_t)p.B, (uint64_t)p.D, TC_BM)) return 0;
     if (!make_tmap_bf16_2d(&tw, wb, (uint64_t)npad, (uint64_t)p.D, (uint32_t)npad)) return 0;
-    {
+    // The bf16 copy of the weights lives in the caller's workspace.  When the caller has told us which version of the
+    // weights this is (nkbk_heads_weights_version: e.g. torch's tensor version counter, bumped by every optimizer step)
+    // and the workspace already holds that version, the re-pack is skipped: validation / inference loops pack once.
+    bool packed = false;
+    const int64_t ver = g_weights_version;
+    g_weights_version = 0;                        // a version hint covers one call
+    if (ver != 0)
+        for (int i = 0; i < TC_PACK_CACHE; ++i)
+            if (g_pack_cache[i].wb == wb && g_pack_cache[i].W == p.W && g_pack_cache[i].version == ver &&
+                g_pack_cache[i].NC == p.NC && g_pack_cache[i].D == p.D && g_pack_cache[i].ctas >= ctas)
+                packed = true;
+    if (!packed) {
         const int64_t n = (int64_t)npad * p.D;
         int blocks = (int)((n + 255) / 256);
         if (blocks > 148 * 4) blocks = 148 * 4;
@@ -455,6 +483,13 @@ int launch_k2_tc_forward(const K2FwdParams& p, void* ws_v, cudaStream_t st) {
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { set_error("launch of k2_tc_pack_weights failed: %s", cudaGetErrorString(e)); return NKBK_E_CUDA; }
         count_launch();
+        if (ver != 0) {
+            TcPackEntry& e2 = g_pack_cache[g_pack_next++ % TC_PACK_CACHE];
+            e2.wb = wb; e2.W = p.W; e2.version = ver; e2.NC = p.NC; e2.D = p.D; e2.ctas = ctas;
+        } else {
+            for (int i = 0; i < TC_PACK_CACHE; ++i)
+                if (g_pack_cache[i].wb == wb) g_pack_cache[i].wb = nullptr;   // overwritten with an unknown version
+        }
     }
     dim3 grid(ctas, ks);
     int rc;
@@ -469,3 +504,5 @@ int launch_k2_tc_forward(const K2FwdParams& p, void* ws_v, cudaStream_t st) {
 }
 
 }  // namespace nkbk
+
+extern "C" void nkbk_heads_weights_version(int64_t version) { nkbk::set_weights_version(version); }

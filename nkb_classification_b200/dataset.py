@@ -781,15 +781,9 @@ class DeviceCropLoader:
 
     @staticmethod
     def _pinned(slot, key, t: torch.Tensor) -> torch.Tensor:
-        """Copy a target tensor into the slot's pinned buffer (allocated once per slot and shape: no cudaHostAlloc per
-        batch).  Safe to reuse: the slot is recycled only after its batch's K1 -- enqueued after the consumer's
-        `.to(device)` of the previous targets on the same stream -- has completed."""
-        buf = slot.pinned.get(key)
-        if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
-            buf = torch.empty_like(t).pin_memory()
-            slot.pinned[key] = buf
-        buf.copy_(t)
-        return buf
+        """A fresh pinned copy per batch (torch's caching host allocator recycles the blocks): callers may keep the
+        targets of earlier batches, as they can with the reference's DataLoader, so the buffer must not be reused."""
+        return t.pin_memory()
 
     # ---- consumer side: K1 on the caller's current stream ----
     def _consume(self, meta: dict):

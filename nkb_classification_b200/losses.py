@@ -55,6 +55,30 @@ class _FusedLoss(torch.autograd.Function):
         return (dl * per_col).to(ctx.in_dtype), None, None, None, None, None, None
 
 
+class _FusedRowLoss(torch.autograd.Function):
+    """Per-row loss terms [B] (single task) from logits; backward scales the kernel's unnormalised dlogits row-wise."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, loss_kind, gamma, class_weight, ignore_index):
+        need_grad = logits.requires_grad
+        z = logits.detach()
+        if z.dtype not in (torch.float32, torch.bfloat16):
+            z = z.float()
+        z = z.contiguous()
+        rows, dl = ops.loss_rows(z, [0, z.shape[1]], labels, loss_kind, gamma, class_weight, ignore_index,
+                                 want_grad=need_grad)
+        ctx.in_dtype = logits.dtype
+        ctx.save_for_backward(dl)
+        return rows[:, 0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (dl,) = ctx.saved_tensors
+        if dl is None:
+            return (None,) * 6
+        return (dl * g[:, None]).to(ctx.in_dtype), None, None, None, None, None
+
+
 def _as_labels_2d(y: Tensor, device) -> Tensor:
     y = y.to(device=device, dtype=torch.int64)
     return y.reshape(-1, 1).contiguous()
@@ -79,27 +103,37 @@ class _SingleTaskLoss(nn.Module):
         cw = self._class_weight
         if cw is not None and cw.device != x.device:
             cw = cw.to(x.device)
+        reduction = getattr(self, "reduction", "mean")
+        if reduction != "mean":          # losses.py:87-94 of the reference: "sum" / "none" over the rows that are kept
+            y2 = _as_labels_2d(y, x.device)
+            rows = _FusedRowLoss.apply(x, y2, self.kind, float(self.gamma), cw, int(self.ignore_index))
+            if reduction == "sum":
+                return rows.sum()
+            keep = y2[:, 0] != self.ignore_index       # (boolean indexing synchronises, as the reference's x[mask] does)
+            if not bool(keep.any()):
+                return torch.zeros((), device=x.device)   # the reference returns a CPU tensor(0.) here
+            return rows[keep]
         out = _FusedLoss.apply(x, _as_labels_2d(y, x.device), [0, x.shape[1]], self.kind, float(self.gamma), cw,
                                int(self.ignore_index))
         return out[0]
 
 
 class FocalLoss(_SingleTaskLoss):
-    """Same constructor as the reference's FocalLoss (losses.py:23-50); only reduction='mean' is fused."""
+    """Same constructor and reductions as the reference's FocalLoss (losses.py:23-94): "mean" (what get_loss builds) is
+    one fused launch; "sum" / "none" take the per-row terms of nkbk_loss_rows."""
     kind = LOSS_FOCAL
 
     def __init__(self, alpha: Optional[Tensor] = None, gamma: float = DEFAULT_FOCAL_GAMMA, reduction: str = "mean",
                  ignore_index: int = -100):
         if reduction not in ("mean", "sum", "none"):
             raise ValueError('Reduction must be one of: "mean", "sum", "none".')
-        if reduction != "mean":
-            raise NotImplementedError("only reduction='mean' (what get_loss builds) is implemented")
         super().__init__(alpha, gamma, ignore_index)
         self.alpha = alpha
         self.reduction = reduction
 
     def __repr__(self):
-        return f"FocalLoss(alpha={self.alpha!r}, gamma={self.gamma!r}, ignore_index={self.ignore_index!r}, reduction='mean')"
+        return (f"FocalLoss(alpha={self.alpha!r}, gamma={self.gamma!r}, ignore_index={self.ignore_index!r}, "
+                f"reduction={self.reduction!r})")
 
 
 class CrossEntropyLoss(_SingleTaskLoss):

@@ -225,8 +225,11 @@ def heads_fwd_loss_bwd(
     emb: torch.Tensor, W_cat: torch.Tensor, b_cat: torch.Tensor, labels: Optional[torch.Tensor], bufs: HeadsBuffers,
     loss_kind: int = LOSS_FOCAL, gamma: float = 2.0, class_weight: Optional[torch.Tensor] = None,
     ignore_index: int = -100, out_pred: Optional[torch.Tensor] = None, cm_step: Optional[torch.Tensor] = None,
+    weights_version: Optional[int] = None,
 ) -> HeadsBuffers:
     """Forward + loss terms + dlogits + unnormalised dW/db into ``bufs`` (see nkbk_heads_step).
+    ``weights_version``: what identifies the current contents of ``W_cat`` (default: its torch version counter); lets
+    the tcgen05 forward keep its bf16 copy of the weights across calls (nkbk_heads_weights_version).
     ``out_pred`` int32 [B,T] / ``cm_step`` int64 confusion counts (accumulated; needs labels): K3 fused into the
     forward epilogue -- same results as a separate :func:`argmax_confusion` on ``bufs.logits``, one launch fewer."""
     _need_cuda("emb", emb)
@@ -258,6 +261,9 @@ def heads_fwd_loss_bwd(
             raise ValueError("cm_step needs labels")
         if cm_step.dtype != torch.int64 or cm_step.numel() != confusion_len(bufs.seg) or not cm_step.is_cuda:
             raise ValueError("cm_step must be CUDA int64 of confusion_len(seg) elements")
+    if emb.dtype == torch.bfloat16:
+        v = W_cat._version if weights_version is None else int(weights_version)
+        lib().nkbk_heads_weights_version(int(v) + 1)            # (never 0: 0 means "unknown")
     rc = lib().nkbk_heads_step(
         _ptr(emb), _DT[emb.dtype], B, D, _ptr(W_cat), _ptr(b_cat), seg, T, _ptr(labels), int(loss_kind), float(gamma),
         _ptr(class_weight), int(ignore_index), _ptr(bufs.logits), _ptr(bufs.probs), _ptr(bufs.dlogits),
@@ -441,6 +447,32 @@ def loss_fwd_bwd(logits: torch.Tensor, seg_offsets: Sequence[int], labels: torch
                                   float(gamma), _ptr(class_weight), int(ignore_index), _ptr(pr), _ptr(dl), _ptr(loss),
                                   _ptr(ws), ws.numel(), _stream(dev)))
     return loss, dl, pr
+
+
+def loss_rows(logits: torch.Tensor, seg_offsets: Sequence[int], labels: torch.Tensor, loss_kind: int,
+              gamma: float = 2.0, class_weight: Optional[torch.Tensor] = None, ignore_index: int = -100,
+              want_grad: bool = True):
+    """Unreduced loss (nkbk_loss_rows): returns (row_loss [B,T] fp32, dlogits [B,NC] fp32 | None), nothing divided."""
+    _need_cuda("logits", logits)
+    _need_cuda("labels", labels)
+    if logits.dtype not in _DT or logits.dim() != 2 or logits.stride(1) != 1:
+        raise ValueError("logits must be [B,ld] float32 | bfloat16 with unit inner stride")
+    seg, T, NC = _seg_array(seg_offsets)
+    B = logits.shape[0]
+    ld = logits.stride(0) if B > 1 else logits.shape[1]
+    if labels.dtype != torch.int64 or not labels.is_contiguous() or labels.numel() != B * T:
+        raise ValueError("labels must be contiguous int64 [B,T]")
+    if class_weight is not None and (class_weight.dtype != torch.float32 or class_weight.numel() != NC
+                                     or not class_weight.is_cuda):
+        raise ValueError("class_weight must be CUDA float32 [NC]")
+    dev = logits.device
+    rows = torch.empty((B, T), dtype=torch.float32, device=dev)
+    dl = torch.empty((B, NC), dtype=torch.float32, device=dev) if want_grad else None
+    ws = torch.empty(max(16, int(lib().nkbk_loss_workspace_bytes(B, T))), dtype=torch.uint8, device=dev)
+    check(lib().nkbk_loss_rows(_ptr(logits), _DT[logits.dtype], B, ld, seg, T, _ptr(labels), int(loss_kind), float(gamma),
+                               _ptr(class_weight), int(ignore_index), _ptr(rows), _ptr(dl), _ptr(ws), ws.numel(),
+                               _stream(dev)))
+    return rows, dl
 
 
 # --------------------------------------------------------------------------

@@ -44,7 +44,7 @@ def main():
                 flush.fill_(1)
                 ops.heads_train_step(emb, W, b, labels, bufs, 0, 0.0, out_pred=pred, cm_total=cm, cm_step=cs)
                 torch.cuda.synchronize()
-                out = np.zeros((148, 12), dtype=np.uint64)
+                out = np.zeros((148, 16), dtype=np.uint64)
                 n = _lib.lib().nkbk_debug_fused_timing(out.ctypes.data_as(ctypes.c_void_p), 148)
                 if n == 0:
                     break

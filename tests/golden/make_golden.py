@@ -114,6 +114,30 @@ def make_heads():
     print("heads_golden.npz", len(out), "arrays")
 
 
+def make_focal_reductions():
+    """The reference's FocalLoss with reduction="sum" / "none" (losses.py:87-94): values and logit gradients."""
+    g = torch.Generator().manual_seed(77)
+    B, C = 41, 6
+    z = torch.randn(B, C, generator=g, dtype=torch.float64)
+    y = torch.randint(0, C, (B,), generator=g)
+    y[::7] = -100
+    alpha = torch.rand(C, generator=g, dtype=torch.float64) + 0.5
+    gvec = torch.rand(int((y != -100).sum()), generator=g, dtype=torch.float64)      # upstream gradient for "none"
+    out = {"z": z.numpy(), "y": y.numpy(), "alpha": alpha.numpy(), "gvec": gvec.numpy()}
+    for gamma in (0.5, 1.0, 2.0):
+        for with_alpha in (False, True):
+            for red in ("sum", "none"):
+                crit = ref_losses.FocalLoss(alpha=alpha if with_alpha else None, gamma=gamma, reduction=red)
+                x = z.clone().requires_grad_(True)
+                val = crit(x, y)
+                (val if red == "sum" else (val * gvec).sum()).backward()
+                key = f"g{gamma}.a{int(with_alpha)}.{red}"
+                out[key + ".loss"] = val.detach().numpy()
+                out[key + ".dz"] = x.grad.numpy()
+    np.savez_compressed(HERE / "focal_reductions_golden.npz", **out)
+    print("focal_reductions_golden.npz", len(out), "arrays")
+
+
 def make_metrics():
     g = np.random.default_rng(7)
     N = 400
@@ -234,6 +258,10 @@ def make_pixels():
 
 
 if __name__ == "__main__":
+    if "--focal-reductions-only" in sys.argv:      # (added in round 2: leaves the other fixtures byte-identical)
+        make_focal_reductions()
+        sys.exit(0)
     make_heads()
+    make_focal_reductions()
     make_metrics()
     make_pixels()

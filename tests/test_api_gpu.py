@@ -487,3 +487,31 @@ def test_val_epoch_bf16_autocast_uses_tensor_core_heads(cuda_device, tmp_path):
         assert np.abs(np.asarray(res["confidences"][n]) - ref_all["probs"][t].numpy()).max() <= 2e-2
         cm = res["confusion"][n]
         assert cm.sum() == len(rows) and np.array_equal(cm, om.confusion_matrix(res["ground_truth"][n], res["predictions"][n], cm.shape[0]))
+
+
+@pytest.mark.parametrize("gamma", [0.5, 1.0, 2.0])
+@pytest.mark.parametrize("with_alpha", [False, True])
+def test_focal_loss_sum_and_none_match_reference_golden(cuda_device, golden_dir, gamma, with_alpha):
+    """FocalLoss(reduction="sum" | "none") (losses.py:87-94 of the reference): values and logit gradients against
+    fixtures produced by the reference's own FocalLoss (tests/golden/make_golden.py: make_focal_reductions)."""
+    from nkb_classification_b200 import losses
+    g = np.load(golden_dir / "focal_reductions_golden.npz")
+    z0 = torch.from_numpy(g["z"]).float().to(cuda_device)
+    y = torch.from_numpy(g["y"]).to(cuda_device)
+    alpha = torch.from_numpy(g["alpha"]).float() if with_alpha else None
+    gvec = torch.from_numpy(g["gvec"]).float().to(cuda_device)
+    for red in ("sum", "none"):
+        key = f"g{gamma}.a{int(with_alpha)}.{red}"
+        crit = losses.FocalLoss(alpha=alpha, gamma=gamma, reduction=red).to(cuda_device)
+        z = z0.clone().requires_grad_(True)
+        val = crit(z, y)
+        exp = torch.from_numpy(g[key + ".loss"])
+        assert val.shape == exp.shape
+        scale = float(exp.abs().max())
+        assert float((val.detach().cpu().double() - exp).abs().max()) <= 1e-5 * scale
+        (val if red == "sum" else (val * gvec).sum()).backward()
+        dz = torch.from_numpy(g[key + ".dz"])
+        assert float((z.grad.cpu().double() - dz).abs().max()) <= 1e-5 * float(dz.abs().max())
+    assert "reduction='none'" in repr(losses.FocalLoss(reduction="none"))
+    all_ignored = losses.FocalLoss(reduction="none").to(cuda_device)(z0, torch.full_like(y, -100))
+    assert float(all_ignored) == 0.0

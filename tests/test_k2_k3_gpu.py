@@ -409,3 +409,35 @@ def test_k2_tcgen05_forward_bf16(cuda_device, B, D, classes, monkeypatch):
     monkeypatch.delenv("NKBK_DISABLE_TCGEN05")
     for t in range(len(classes)):  # FFMA path keeps W in fp32: differs by the bf16 rounding of W only
         assert rel_err(r["logits"][t], f["logits"][t]) <= 1e-2
+
+
+def test_k2_tcgen05_weight_pack_is_cached_by_version(cuda_device, monkeypatch):
+    """Forward-only bf16 calls (validation / inference) re-pack the bf16 copy of the weights only when the weights'
+    version changes: launches drop from 3 (pack, forward, loss sums) to 2, results stay identical, and an in-place
+    update of the weights (new torch version counter) is picked up."""
+    from nkb_classification_b200 import _lib, ops
+    dev = cuda_device
+    g = torch.Generator().manual_seed(4)
+    B, D, classes = 512, 768, (2, 3, 4, 7, 14)
+    seg = np.concatenate([[0], np.cumsum(classes)]).tolist()
+    emb = torch.randn(B, D, generator=g).to(dev).to(torch.bfloat16)
+    W = (torch.randn(sum(classes), D, generator=g) * 0.05).to(dev)
+    b = torch.zeros(sum(classes), device=dev)
+    bufs = ops.HeadsBuffers(B, D, seg, dev, want_grads=False)
+    pred = torch.empty((B, len(classes)), dtype=torch.int32, device=dev)
+
+    def call():
+        n0 = _lib.launch_count()
+        ops.heads_fwd_loss_bwd(emb, W, b, None, bufs, out_pred=pred)
+        assert ops.heads_last_path() == _lib.PATH_TC_FWD
+        torch.cuda.synchronize()
+        return _lib.launch_count() - n0, bufs.logits.clone(), pred.clone()
+
+    n1, z1, p1 = call()
+    n2, z2, p2 = call()
+    assert n2 == n1 - 1 and torch.equal(z1, z2) and torch.equal(p1, p2)     # second call: no re-pack
+    W.mul_(-1.0)                                                             # in-place update bumps W._version
+    n3, z3, p3 = call()
+    assert n3 == n1 and torch.allclose(z3, -z1, atol=1e-6)                   # re-packed: the new weights are in use
+    n4, z4, _ = call()
+    assert n4 == n1 - 1 and torch.equal(z3, z4)
