@@ -570,7 +570,8 @@ class _IngestSlot:
         self.copied: Optional[torch.cuda.Event] = None
         self.consumed: Optional[torch.cuda.Event] = None
         self.paths: set = set()
-        self.pinned: Dict[str, torch.Tensor] = {}
+        self.meta_h: Optional[torch.Tensor] = None      # pinned: boxes | frame indices | descriptors of the batch
+        self.meta_d: Optional[torch.Tensor] = None
 
 
 class DeviceCropLoader:
@@ -690,8 +691,9 @@ class DeviceCropLoader:
         for i, e in enumerate(entries):
             if e is not None:
                 sizes[i] = (e[1], e[2])
-        order = np.argsort(fidx, kind="stable")                      # samples grouped by frame, for the ROI rectangles
-        starts = np.searchsorted(fidx[order], np.arange(len(plist) + 1))
+        if miss:                                                     # (a fully resident batch skips all of this)
+            order = np.argsort(fidx, kind="stable")                  # samples grouped by frame, for the ROI rectangles
+            starts = np.searchsorted(fidx[order], np.arange(len(plist) + 1))
         to_cache, to_travel = [], []            # (frame index, pixels)
         for i, fr in zip(miss, decoded):
             H, W = fr.shape[:2]
@@ -728,8 +730,9 @@ class DeviceCropLoader:
             nb = ~has_box
             boxes[nb, 0], boxes[nb, 1] = 0, 0
             boxes[nb, 2], boxes[nb, 3] = sizes[fidx[nb], 1], sizes[fidx[nb], 0]
-        boxes[:, [0, 2]] -= origin[fidx, 0:1]
-        boxes[:, [1, 3]] -= origin[fidx, 1:2]
+        if to_travel:                            # regions of interest: boxes move with their region's origin
+            boxes[:, [0, 2]] -= origin[fidx, 0:1]
+            boxes[:, [1, 3]] -= origin[fidx, 1:2]
         boxes = boxes.astype(np.int32)
         validate_boxes(boxes, fidx, sizes)
         aug = self.plan.draw(n, self.aug_rng)     # in batch order: one producer, so the stream is reproducible
@@ -758,10 +761,23 @@ class DeviceCropLoader:
                 # K1 addresses sources as base + int64 offset: a region in the slot's buffer is reached from the arena
                 off = (slot.dev.data_ptr() - base.data_ptr()) + (o - travel_lo)
                 desc[i] = (off, h, w, pitch)
-            meta = dict(boxes=torch.from_numpy(boxes).to(dev, non_blocking=True),
-                        fidx=torch.from_numpy(fidx).to(dev, non_blocking=True),
-                        desc=torch.from_numpy(desc).to(dev, non_blocking=True))
-            self.stats["h2d_bytes"] += boxes.nbytes + fidx.nbytes + desc.nbytes
+            # boxes | frame indices | descriptors travel as ONE copy out of the slot's pinned staging into the slot's own
+            # device buffer (recycled only after K1 of the batch has run: no allocation, no record_stream per batch)
+            nb, nf, nd = boxes.nbytes, fidx.nbytes, desc.nbytes
+            o_f, o_d = nb, (nb + nf + 7) // 8 * 8
+            mbytes = o_d + nd
+            if slot.meta_h is None or slot.meta_h.numel() < mbytes:
+                slot.meta_h = torch.empty(int(mbytes * 1.5) + 256, dtype=torch.uint8).pin_memory()
+                slot.meta_d = torch.empty(slot.meta_h.numel(), dtype=torch.uint8, device=dev)
+            mh = slot.meta_h.numpy()
+            mh[:nb] = boxes.view(np.uint8).reshape(-1)
+            mh[o_f: o_f + nf] = fidx.view(np.uint8).reshape(-1)
+            mh[o_d: o_d + nd] = desc.view(np.uint8).reshape(-1)
+            slot.meta_d[:mbytes].copy_(slot.meta_h[:mbytes], non_blocking=True)
+            md = slot.meta_d
+            meta = dict(boxes=md[:nb].view(torch.int32).view(-1, 4), fidx=md[o_f: o_f + nf].view(torch.int32),
+                        desc=md[o_d: o_d + nd].view(torch.int64).view(-1, 4))
+            self.stats["h2d_bytes"] += nb + nf + nd
             if aug is not None:
                 ops.upload_augment(aug, dev)      # train pipelines: parameters ride the copy stream too
             slot.copied.record(self._copy_stream)
@@ -790,7 +806,7 @@ class DeviceCropLoader:
         slot = self._slots[meta["slot"]]
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(slot.copied)
-        shared = [meta["boxes"], meta["fidx"], meta["desc"]]
+        shared = []          # (the slot's meta buffer lives as long as the loader: nothing to record for it)
         if slot.dev is not None:
             shared.append(slot.dev)
         if meta["aug"] is not None:
