@@ -828,33 +828,31 @@ __global__ void __launch_bounds__(KF_THREADS, 1) k2_fused_step(const KFParams p)
     }
     __syncthreads();
     if (p.timing != nullptr && tid == 0) p.timing[blockIdx.x * KF_TIMING_SLOTS + 12] = (unsigned long long)clock64();
-    if (tid < world && tid != rank)
-        for (int sl = blockIdx.x; sl < nsl; sl += G_ctas) peer_publish(L, tid, par, sl, step);
+    if (tid < world && tid != rank) peer_publish_many(L, tid, par, blockIdx.x, G_ctas, nsl, step);
     if (p.timing != nullptr && tid == 0) p.timing[blockIdx.x * KF_TIMING_SLOTS + 13] = (unsigned long long)clock64();
-
-    // wait + rank-ordered sum + finalize, slice by slice (all pushes of this CTA are out: no wait can block a push)
-    bool have_gtail = false;
-    for (int sl = blockIdx.x; sl < nsl; sl += G_ctas) {
-        if (tid < world && tid != rank) peer_wait(L, tid, par, sl, step);
-        __syncthreads();
-        if (p.timing != nullptr && tid == 0 && sl == (int)blockIdx.x) p.timing[blockIdx.x * KF_TIMING_SLOTS + 14] = (unsigned long long)clock64();
-        if (!have_gtail) {   // global loss sums / denominators in rank order: identical in every CTA of every rank
-            const long long tail_off = L.cap_vecs + (long long)sl * PEER_TAIL_VECS;
-            if (tid < 2 * T) {
-                float sum = 0.f;
-                for (int r = 0; r < world; ++r) {
-                    float x;
-                    if (r == rank) x = tail_l[tid];
-                    else x = __ldcg(reinterpret_cast<const float*>(L.data[rank] + (par * world + r) * L.slot_vecs + tail_off) + tid);
-                    sum = (r == 0) ? x : sum + x;
-                }
-                tail_g[tid] = sum;
+    // wait for every peer's copy of all my slices (all pushes of this CTA are out: no wait can block a push), then the
+    // rank-ordered sum + finalize over the same flat list
+    if (tid < world && tid != rank) peer_wait_many(L, tid, par, blockIdx.x, G_ctas, nsl, step);
+    __syncthreads();
+    if (p.timing != nullptr && tid == 0) p.timing[blockIdx.x * KF_TIMING_SLOTS + 14] = (unsigned long long)clock64();
+    if (n_my > 0) {   // global loss sums / denominators in rank order: identical in every CTA of every rank
+        const long long tail_off = L.cap_vecs + (long long)blockIdx.x * PEER_TAIL_VECS;
+        if (tid < 2 * T) {
+            float sum = 0.f;
+            for (int r = 0; r < world; ++r) {
+                float x;
+                if (r == rank) x = tail_l[tid];
+                else x = __ldcg(reinterpret_cast<const float*>(L.data[rank] + (par * world + r) * L.slot_vecs + tail_off) + tid);
+                sum = (r == 0) ? x : sum + x;
             }
-            __syncthreads();
-            have_gtail = true;
+            tail_g[tid] = sum;
         }
-        const int v0 = sl * per, v1 = min(v0 + per, VT);
-        for (int v = v0 + tid; v < v1; v += KF_THREADS) {
+        __syncthreads();
+        for (int i = tid; i < n_my_vec; i += KF_THREADS) {
+            int v;
+            bool on;
+            flat_vec(i, v, on);
+            if (!on) continue;
             if (v < vf) {
                 float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 for (int r = 0; r < world; ++r) {
@@ -957,7 +955,15 @@ static bool kf_plan(int B, int D, int NC, int T, int es, long long n_cm, int n_s
     P.hist_smem = (n_cm > 0 && n_cm <= KF_MAX_SMEM_HIST) ? 1 : 0;
     const int hist_bins = P.hist_smem ? (int)n_cm : 0;
     int rpc = (B + n_sm - 1) / n_sm;
-    if (rpc < KF_TILE_ROWS) rpc = KF_TILE_ROWS;   // fewer, fuller CTAs for small batches: fewer partials to sum
+    // Small batches: fewer, fuller CTAs (three tiles each).  Fewer partials to sum and fewer flags to exchange; above all
+    // the kernel then leaves most SMs to whatever runs next to it -- K1 of the next batch in a pipelined loop: with
+    // 512 rows, 8 -> 24 rows per CTA costs 3 us when the kernel runs alone and saves 7.5 us when K1 overlaps it.
+    int min_rows = 3 * KF_TILE_ROWS;
+    if (const char* mr = getenv("NKBK_FUSED_MIN_ROWS")) {   // experiment knob (8 | 16 | 24 | 32)
+        const int v = atoi(mr);
+        if (v >= 1 && v <= 1024) min_rows = v;
+    }
+    if (rpc < min_rows) rpc = min_rows;
     P.rows_per_cta = rpc;
     P.grid = (B + rpc - 1) / rpc;
     P.tile_rows = 0;

@@ -39,6 +39,14 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void st_relaxed_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_relaxed_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ unsigned long long global_timer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -71,6 +79,31 @@ __device__ __forceinline__ void peer_wait(const PeerLinks& L, int r, long long p
             break;
         }
     }
+}
+
+// The same for a CTA that owns SEVERAL slices (first, first + stride, ... < n_slices): one system-scope fence covers all
+// of them -- a release per flag would serialise one round trip per slice -- then relaxed flag stores; on the way in,
+// relaxed polling of every flag and one fence at the end.
+__device__ __forceinline__ void peer_publish_many(const PeerLinks& L, int r, long long par, int first, int stride,
+                                                  int n_slices, unsigned int step) {
+    __threadfence_system();
+    unsigned int* f = L.flags[r] + (par * L.world + L.rank) * PEER_MAX_SLICES;
+    for (int sl = first; sl < n_slices; sl += stride) st_relaxed_sys(f + sl, step);
+}
+__device__ __forceinline__ void peer_wait_many(const PeerLinks& L, int r, long long par, int first, int stride,
+                                               int n_slices, unsigned int step) {
+    const unsigned int* f = L.flags[L.rank] + (par * L.world + r) * PEER_MAX_SLICES;
+    const unsigned long long t0 = global_timer_ns();
+    for (int sl = first; sl < n_slices; sl += stride) {
+        unsigned int spins = 0;
+        while (ld_relaxed_sys(f + sl) != step) {
+            if ((++spins & 0x3ffu) == 0u && global_timer_ns() - t0 > PEER_TIMEOUT_NS) {
+                atomicExch(L.ctl + 2, 1u + (unsigned int)r);  // status: peer r never arrived
+                break;
+            }
+        }
+    }
+    __threadfence_system();   // acquire side: the payload reads that follow see what the flags announce
 }
 
 // Host side (k4_peer.cu): fills `L` from the connected state; NKBK_E_NCCL when the transport is not connected,

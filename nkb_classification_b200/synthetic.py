@@ -53,6 +53,11 @@ WORKLOADS = {
     "cfg1_single_224": Workload("cfg1_single_224", 32, 224, 224, 1, 224, "stretch", 512, (10,), "CrossEntropyLoss",
                                 0.0, True),
 }
+# one rank's share of configs[4] when its global batch of 4096 is split over 8 / 4 / 2 GPUs (strong scaling): lets the
+# per-rank step of an N-GPU run be studied on one GPU (no exchange)
+for _n in (2, 4, 8):
+    WORKLOADS[f"cfg5_shard{_n}"] = Workload(f"cfg5_shard{_n}", 64 // _n, 1080, 1920, 64, 224, "stretch", 2048, (10,),
+                                            "CrossEntropyLoss", 0.0)
 DEFAULT_WORKLOAD = "cfg5_1080p_64x64"
 
 
