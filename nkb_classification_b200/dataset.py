@@ -49,6 +49,18 @@ def _row_pitch(w: int) -> int:
     return (w * 3 + 15) // 16 * 16      # 16-byte aligned rows: K1's TMA path applies
 
 
+def _unique_inverse(ids: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """np.unique(ids, return_inverse=True) for small non-negative integer ids, without the sort (O(n))."""
+    ids = np.asarray(ids, dtype=np.int64)
+    if ids.size == 0 or ids.min() < 0 or ids.max() > 8 * ids.size + 1024:
+        return np.unique(ids, return_inverse=True)
+    seen = np.zeros(int(ids.max()) + 1, dtype=bool)
+    seen[ids] = True
+    uniq = np.flatnonzero(seen)
+    lut = np.cumsum(seen) - 1
+    return uniq, lut[ids]
+
+
 def _image_size(path: str) -> Tuple[int, int]:
     from PIL import Image
 
@@ -409,7 +421,7 @@ class AnnotatedYOLODataset(_DescDataset):
             self._larr = np.array([l for _, _, l in self.list_bbox], dtype=np.int64)
             self._arr_len = len(self.list_bbox)
         idx = np.asarray(indices, dtype=np.int64)
-        uniq, inv = np.unique(self._pid[idx], return_inverse=True)
+        uniq, inv = _unique_inverse(self._pid[idx])
         return inv.astype(np.int64), [self._plist[u] for u in uniq], self._barr[idx], torch.from_numpy(self._larr[idx])
 
     def decoded_bytes(self) -> int:
@@ -462,7 +474,7 @@ class InMemoryFrames(_DescDataset):
 
     def describe(self, indices):
         idx = np.asarray(indices, dtype=np.int64)
-        uniq, inv = np.unique(self.frame_idx[idx], return_inverse=True)
+        uniq, inv = _unique_inverse(self.frame_idx[idx])
         boxes = self.boxes[idx] if self.boxes is not None else np.full((len(idx), 4), -1, dtype=np.int64)
         if isinstance(self.labels, dict):
             target = {k: torch.from_numpy(np.asarray(v, dtype=np.int64)[idx]) for k, v in self.labels.items()}
@@ -597,7 +609,8 @@ class DeviceCropLoader:
     def __init__(self, dataset: _DescDataset, batch_size: int, shuffle: bool = False, sampler=None,
                  num_workers: int = 0, drop_last: bool = False, device="cuda:0", out_dtype=torch.float32,
                  prefetch: Optional[int] = None, frame_cache_bytes: int = 0, roi_upload: bool = True,
-                 group_by_frame: bool = False, sort_within_batch: bool = False):
+                 group_by_frame: bool = False, sort_within_batch: bool = False, resident_epochs: bool = True,
+                 targets_on_device: bool = False):
         if dataset.transform is None:
             raise ValueError("the dataset needs a Transforms(pipeline) to compile for K1")
         self.dataset, self.batch_size, self.shuffle, self.sampler = dataset, int(batch_size), shuffle, sampler
@@ -613,6 +626,10 @@ class DeviceCropLoader:
         # back to back and their overlapping source rows hit L2 instead of HBM.  Off by default: it changes the order in
         # which a batch's samples (and the logger's per-sample lists) appear.
         self.sort_within_batch = bool(sort_within_batch)
+        # once every frame the epoch touches sits in the frame cache, the whole epoch is planned at once: boxes, frame
+        # indices, descriptors and labels of ALL its batches go to the device in one copy and a batch is one K1 launch on
+        # slices of them -- no producer thread, no per-batch host work (`_iter_resident`)
+        self.resident_epochs, self.targets_on_device = bool(resident_epochs), bool(targets_on_device)
         self.cache = DeviceFrameCache(self.device, frame_cache_bytes) if frame_cache_bytes and frame_cache_bytes > 0 else None
         self._read = getattr(dataset, "read_frame", None) or _imread_bgr      # in-memory datasets supply their own
         # train pipelines: where the per-sample augmentation parameters come from (None = Python's global `random`,
@@ -622,7 +639,7 @@ class DeviceCropLoader:
 
     def reset_stats(self):
         self.stats = {"batches": 0, "crops": 0, "decodes": 0, "h2d_bytes": 0, "cache_hits": 0, "cache_inserts": 0,
-                      "roi_frames": 0, "whole_frames": 0}
+                      "roi_frames": 0, "whole_frames": 0, "resident_epochs": 0}
 
     def __len__(self):
         n = len(self.sampler) if self.sampler is not None else len(self.dataset)
@@ -646,8 +663,9 @@ class DeviceCropLoader:
             order = [i for p in sorted(groups, key=first.get) for i in groups[p]]
         return order
 
-    def _index_batches(self) -> Iterator[List[int]]:
-        order = self._order()
+    def _index_batches(self, order: Optional[List[int]] = None) -> Iterator[List[int]]:
+        if order is None:
+            order = self._order()
         for i in range(0, len(order), self.batch_size):
             b = order[i: i + self.batch_size]
             if len(b) < self.batch_size and self.drop_last:
@@ -823,9 +841,86 @@ class DeviceCropLoader:
     def load_batch(self, indices: List[int]):
         return self._consume(self._stage(indices, 0))
 
+    # ---- resident epochs: the whole epoch planned at once ----
+    def _plan_resident(self, order: List[int]) -> Optional[dict]:
+        """Everything K1 needs for EVERY batch of the epoch, on the device after one copy -- or None when a frame of the
+        epoch is not in the cache (first epoch, dataset larger than the arena) or the pipeline draws per-sample
+        augmentation parameters (those stay on the per-batch path)."""
+        cache = self.cache
+        if (not self.resident_epochs or cache is None or self.plan.augment is not None or not order
+                or self.device.type != "cuda" or type(self.dataset).describe is _DescDataset.describe):
+            return None
+        if self.drop_last:
+            order = order[: len(order) // self.batch_size * self.batch_size]
+            if not order:
+                return None
+        ids, plist, raw_boxes, target = self.dataset.describe(order)
+        entries = [cache.get(p) for p in plist]
+        if any(e is None for e in entries) or not isinstance(target, (dict, torch.Tensor)):
+            return None
+        n, bs = len(ids), self.batch_size
+        perm = None
+        if self.sort_within_batch and n > 1:
+            perm = np.lexsort((ids, np.arange(n) // bs))         # stable: by frame inside each batch, draw order kept
+            ids, raw_boxes = ids[perm], raw_boxes[perm]
+            pt = torch.from_numpy(perm)
+            target = {k_: v[pt] for k_, v in target.items()} if isinstance(target, dict) else target[pt]
+        desc = np.array([(e[0], e[1], e[2], e[3]) for e in entries], dtype=np.int64).reshape(-1, 4)
+        fidx = ids.astype(np.int32)
+        boxes = raw_boxes.astype(np.int64, copy=True)
+        nb_ = boxes[:, 0] < 0                                    # whole-image samples: the box is the frame
+        if nb_.any():
+            boxes[nb_, 0], boxes[nb_, 1] = 0, 0
+            boxes[nb_, 2], boxes[nb_, 3] = desc[fidx[nb_], 2], desc[fidx[nb_], 1]
+        boxes = boxes.astype(np.int32)
+        validate_boxes(boxes, fidx, desc[:, 1:3])
+        names = sorted(target) if isinstance(target, dict) else None
+        lab = (torch.stack([target[k_].reshape(-1) for k_ in names], 0) if names is not None
+               else target.reshape(1, -1)).to(torch.int64).contiguous()          # [T, n]: a task's batch slice is contiguous
+        # one pinned buffer, one H2D: [boxes | frame indices | descriptors | labels]
+        parts = [boxes.view(np.uint8).reshape(-1), fidx.view(np.uint8).reshape(-1), desc.view(np.uint8).reshape(-1),
+                 lab.numpy().view(np.uint8).reshape(-1)]
+        offs, total = [], 0
+        for a in parts:
+            offs.append(total)
+            total += (a.nbytes + 15) // 16 * 16
+        host = torch.empty(total, dtype=torch.uint8).pin_memory()
+        hv = host.numpy()
+        for o, a in zip(offs, parts):
+            hv[o: o + a.nbytes] = a
+        dev = host.to(self.device, non_blocking=True)
+        self.stats["h2d_bytes"] += total
+
+        def view(t, i, dt, shape):
+            return t[offs[i]: offs[i] + parts[i].nbytes].view(dt).view(*shape)
+
+        lab_src = dev if self.targets_on_device else host      # host targets: pinned views, as default_collate + pin
+        lab_t = view(lab_src, 3, torch.int64, (-1, n))
+        self.stats["cache_hits"] += len(plist)
+        return dict(n=n, boxes=view(dev, 0, torch.int32, (n, 4)), fidx=view(dev, 1, torch.int32, (n,)),
+                    desc=view(dev, 2, torch.int64, (-1, 4)), labels=lab_t, names=names, keep=(host, dev))
+
+    def _iter_resident(self, plan: dict):
+        bs, n, names = self.batch_size, plan["n"], plan["names"]
+        self.stats["resident_epochs"] += 1
+        for a in range(0, n, bs):
+            b = min(n, a + bs)
+            img = ops.preprocess_crops(self.cache.buf, plan["boxes"][a:b], plan["fidx"][a:b], self.plan,
+                                       out_dtype=self.out_dtype, frame_desc=plan["desc"])
+            lab = plan["labels"][:, a:b]
+            target = lab[0] if names is None else {k_: lab[t] for t, k_ in enumerate(names)}
+            self.stats["batches"] += 1
+            self.stats["crops"] += b - a
+            yield img, target
+
     def __iter__(self):
+        order = self._order()
+        plan = self._plan_resident(order)
+        if plan is not None:
+            yield from self._iter_resident(plan)
+            return
         if self.prefetch <= 0:
-            for b in self._index_batches():
+            for b in self._index_batches(order):
                 yield self.load_batch(b)
             return
         import queue
@@ -846,7 +941,7 @@ class DeviceCropLoader:
         def producer():
             try:
                 torch.cuda.set_device(self.device)
-                for i, b in enumerate(self._index_batches()):
+                for i, b in enumerate(self._index_batches(order)):
                     if stop.is_set() or not put(self._stage(b, i % nslot)):
                         return
                 put(None)
@@ -872,7 +967,8 @@ def _device_of(data: dict):
     return data.get("device", "cuda:0")
 
 
-_LOADER_KEYS = ("device", "prefetch", "frame_cache_bytes", "roi_upload", "group_by_frame", "sort_within_batch")
+_LOADER_KEYS = ("device", "prefetch", "frame_cache_bytes", "roi_upload", "group_by_frame", "sort_within_batch",
+                "resident_epochs", "targets_on_device")
 
 
 def _frame_cache_bytes(data: dict, device, dataset) -> int:
@@ -914,7 +1010,9 @@ def get_dataset(data, pipeline):
                             num_workers=data.get("num_workers", 0), drop_last=data.get("drop_last", False),
                             device=dev, prefetch=data.get("prefetch"), frame_cache_bytes=_frame_cache_bytes(data, dev, dataset),
                             roi_upload=data.get("roi_upload", True), group_by_frame=data.get("group_by_frame", False),
-                            sort_within_batch=data.get("sort_within_batch", False))
+                            sort_within_batch=data.get("sort_within_batch", False),
+                            resident_epochs=data.get("resident_epochs", True),
+                            targets_on_device=data.get("targets_on_device", False))
 
 
 def get_inference_dataset(data, pipeline):

@@ -18,7 +18,24 @@ from __future__ import annotations
 from collections import defaultdict
 from typing import List, Optional
 
+import numpy as np
 import torch
+
+
+def _to_host(*tensors):
+    """Device tensors -> numpy arrays through pinned memory: the copies are queued back to back and waited for once."""
+    outs, on_dev = [], False
+    for t in tensors:
+        if t.is_cuda:
+            pin = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            pin.copy_(t, non_blocking=True)
+            outs.append(pin)
+            on_dev = True
+        else:
+            outs.append(t)
+    if on_dev:
+        torch.cuda.current_stream().synchronize()
+    return [o.numpy() for o in outs]
 
 
 class BaseLogger:
@@ -34,6 +51,7 @@ class BaseLogger:
 
     def init_iter_logs(self):
         self.epoch_images_example = None
+        self._img_event = None
         self._gt, self._conf, self._pred, self._loss = [], [], [], []
         self._seg, self._names = None, None
 
@@ -76,10 +94,22 @@ class BaseLogger:
         ``cfg.example_images = None`` restores the reference's whole-batch copy."""
         if self.epoch_images_example is None:
             k = getattr(self.cfg, "example_images", 64)
-            self.epoch_images_example = (images if k is None else images[: int(k)]).to("cpu")
+            src = images if k is None else images[: int(k)]
+            if src.is_cuda:
+                # asynchronous copy into fresh pinned memory (a pageable `.to("cpu")` of 38 MB stalls the loop for ~17 ms
+                # at the top of every epoch); get_epoch_results waits for it
+                pin = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+                pin.copy_(src, non_blocking=True)
+                self._img_event = torch.cuda.Event()
+                self._img_event.record()
+                self.epoch_images_example = pin
+            else:
+                self.epoch_images_example = src.to("cpu")
 
     def get_epoch_results(self):
         """One D2H per quantity, then the reference's structure (logging.py:287-294)."""
+        if self._img_event is not None:
+            self._img_event.synchronize()
         if not self._gt:
             empty = [] if self.task == "single" else defaultdict(list)
             return {"running_loss": empty, "confidences": empty, "predictions": empty, "ground_truth": empty,
@@ -90,25 +120,27 @@ class BaseLogger:
             # K5: exact ROC-AUC pair counts from the device-resident epoch, one [NC, 3] int64 D2H
             from . import ops
             auc_counts = ops.roc_auc_counts(conf_d.contiguous(), self._seg, gt_d.to(torch.int64).contiguous()).cpu().numpy()
-        gt = gt_d.cpu().numpy()
-        conf = conf_d.cpu().numpy()
-        pred = torch.cat(self._pred).cpu().numpy()
-        loss = torch.stack(self._loss).cpu().numpy()
+        gt, conf, pred, loss = _to_host(gt_d, conf_d, torch.cat(self._pred), torch.stack(self._loss))
         seg, names = self._seg, self._names
         res = {"images": self.epoch_images_example}
+        # the reference hands out Python lists (logging.py:268-281); building them costs ~0.4 us per crop -- more than
+        # the whole training step of a crop on this path -- so `cfg.epoch_results_numpy = True` keeps the numpy arrays
+        # (every consumer in the reference wraps the lists in np.array / passes them to sklearn anyway)
+        as_np = bool(getattr(self.cfg, "epoch_results_numpy", False))
+        ls = (lambda a: np.ascontiguousarray(a)) if as_np else (lambda a: a.tolist())
         if names is None:
-            res["running_loss"] = loss[:, 0].tolist()
-            res["confidences"] = conf.tolist()
-            res["predictions"] = pred[:, 0].tolist()
-            res["ground_truth"] = gt[:, 0].tolist()
+            res["running_loss"] = ls(loss[:, 0])
+            res["confidences"] = ls(conf)
+            res["predictions"] = ls(pred[:, 0])
+            res["ground_truth"] = ls(gt[:, 0])
         else:
             rl, cf, pr, g = defaultdict(list), defaultdict(list), defaultdict(list), defaultdict(list)
             for t, n in enumerate(names):
-                rl[n] = loss[:, t].tolist()
-                cf[n] = conf[:, seg[t]:seg[t + 1]].tolist()
-                pr[n] = pred[:, t].tolist()
-                g[n] = gt[:, t].tolist()
-            rl["loss"] = loss[:, len(names)].tolist()
+                rl[n] = ls(loss[:, t])
+                cf[n] = ls(conf[:, seg[t]:seg[t + 1]])
+                pr[n] = ls(pred[:, t])
+                g[n] = ls(gt[:, t])
+            rl["loss"] = ls(loss[:, len(names)])
             res.update(running_loss=rl, confidences=cf, predictions=pr, ground_truth=g)
         if auc_counts is not None:
             seg_ = self._seg

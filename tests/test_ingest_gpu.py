@@ -70,8 +70,8 @@ def test_shuffled_loader_with_frame_cache(cuda_device, prefetch):
     run_epoch(loader, 2, ref_img, ref_tgt)                # second epoch: everything is resident
     st2 = loader.stats
     assert st2["decodes"] == 0 and ds.reads == n_frames and st2["cache_inserts"] == 0
-    meta_bytes = n * (16 + 4) + sum(32 * min(n_frames, 32) for _ in range(st2["batches"]))
-    assert st2["h2d_bytes"] <= meta_bytes                 # boxes + frame indices + descriptors only
+    meta_bytes = n * (16 + 4 + 8) + 32 * n_frames + 64    # boxes + frame indices + labels + descriptors, ONE copy
+    assert st2["h2d_bytes"] <= meta_bytes and st2["resident_epochs"] == 1
 
 
 def test_shuffled_loader_roi_upload_without_cache(cuda_device):
@@ -129,3 +129,46 @@ def test_whole_image_dataset_through_the_cache(cuda_device):
     run_epoch(loader, 1, ref_img, ref_tgt)
     run_epoch(loader, 2, ref_img, ref_tgt)
     assert loader.stats["decodes"] == 9
+
+
+def test_resident_epoch_plan_matches_streaming_path(cuda_device):
+    """Epoch >= 2 of a dataset that fits the frame cache is planned at once (one metadata copy, a batch = one K1 launch
+    on slices): same tensors as the per-batch path, for tensor and dict targets, host or device targets, with the
+    in-batch frame sort, a ragged last batch and drop_last."""
+    from nkb_classification_b200 import dataset as D
+    ds = make_dataset()
+    ref_img, ref_tgt = reference_outputs(ds, cuda_device)
+    for kw in (dict(), dict(targets_on_device=True), dict(drop_last=True), dict(sort_within_batch=True)):
+        loader = D.DeviceCropLoader(ds, batch_size=32, shuffle=True, device=cuda_device, prefetch=2,
+                                    frame_cache_bytes=64 << 20, **kw)
+        stream = D.DeviceCropLoader(ds, batch_size=32, shuffle=True, device=cuda_device, frame_cache_bytes=64 << 20,
+                                    resident_epochs=False, **kw)
+        for _ in loader:                                   # epoch 1 fills the cache
+            pass
+        for _ in stream:
+            pass
+        torch.manual_seed(5)
+        a = [(img.clone(), t) for img, t in loader]
+        torch.manual_seed(5)
+        b = [(img.clone(), t) for img, t in stream]
+        assert loader.stats["resident_epochs"] == 1 and stream.stats["resident_epochs"] == 0
+        assert len(a) == len(b) == (3 if kw.get("drop_last") else 4)
+        for (ia, ta), (ib, tb) in zip(a, b):
+            assert torch.equal(ia, ib) and torch.equal(ta.cpu(), tb.cpu())
+            assert ta.is_cuda == bool(kw.get("targets_on_device")) and ta.dtype == torch.int64
+    # dict targets (multi task)
+    lab = {"a": np.arange(len(ds)) % 3, "b": np.arange(len(ds)) % 2}
+    dm = D.InMemoryFrames(ds.frames, ds.frame_idx, lab, boxes=ds.boxes, transform=ds.transform)
+    loader = D.DeviceCropLoader(dm, batch_size=50, shuffle=True, device=cuda_device, frame_cache_bytes=64 << 20)
+    for _ in loader:
+        pass
+    torch.manual_seed(9)
+    order = loader._order()
+    torch.manual_seed(9)
+    pos = 0
+    for img, t in loader:
+        idx = order[pos: pos + img.shape[0]]
+        assert torch.equal(img, ref_img[idx]) and set(t) == {"a", "b"}
+        assert t["a"].tolist() == [lab["a"][i] for i in idx] and t["b"].tolist() == [lab["b"][i] for i in idx]
+        pos += img.shape[0]
+    assert loader.stats["resident_epochs"] == 1 and pos == len(dm)
