@@ -48,6 +48,17 @@ const char* nkbk_last_error(void);
 /* Number of kernels this library has launched in the calling process. */
 int64_t nkbk_launch_count(void);
 
+/* Launch option of the calling thread (default 0).  With 1, every following K1 launch of this thread
+ * (nkbk_preprocess_crops / nkbk_preprocess_crops_aug) is enqueued as a PROGRAMMATIC dependent of the kernel in front
+ * of it in the stream (cudaLaunchAttributeProgrammaticStreamSerialization): when that kernel is this library's fused
+ * heads step -- which releases its dependents as soon as its CTAs are resident -- K1 of batch i+1 starts on the SMs the
+ * heads step of batch i leaves free (it occupies ceil(B / rows_per_cta) SMs) instead of after it.  This is the
+ * pipelined form of the reference's loop (engine.py:39-62: the DataLoader prepares batch i+1 while the model steps on
+ * batch i) in ONE stream.  Only for callers that own their buffers: K1 must not write memory the kernel in front of it
+ * still reads (the caller gives K1 its own output buffer), and K1 reads nothing that kernel writes.  Any other kernel
+ * in front of K1 releases its dependents only when it ends, i.e. ordinary stream order.  Returns the previous value. */
+int nkbk_k1_overlap_previous(int enable);
+
 /* ------------------------------------------------------------------------
  * K1  fused crop + cv2-INTER_LINEAR-exact uint8 resize + Normalize + HWC->NCHW
  *

@@ -14,7 +14,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libnkbk.so"
-SOURCES = ["nkbk_api.cu", "k1_general.cu", "k1_fast.cu", "k2_heads.cu", "k2_fused.cu", "k2_tc.cu", "k3_metrics.cu", "k4_comm.cu", "k4_peer.cu", "k5_auc.cu"]
+SOURCES = ["nkbk_api.cu", "k1_general.cu", "k1_fast.cu", "k1_fast_aug.cu", "k2_heads.cu", "k2_fused.cu", "k2_tc.cu", "k3_metrics.cu", "k4_comm.cu", "k4_peer.cu", "k5_auc.cu"]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

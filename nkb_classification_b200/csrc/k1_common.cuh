@@ -71,6 +71,19 @@ __host__ __device__ __forceinline__ int k1_div_rhe(int n, int d) {  // round-hal
 __host__ __device__ __forceinline__ int k1_hsv_sdiv(int v) { return v ? k1_div_rhe(255 << 12, v) : 0; }
 __host__ __device__ __forceinline__ int k1_hsv_hdiv(int d) { return d ? k1_div_rhe((180 << 12) / 6, d) : 0; }
 
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ float k1_selp(float a, float b, uint32_t cond) {   // cond != 0 ? a : b, never a branch
+    float r;
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\tselp.f32 %0, %1, %2, p;\n\t}" : "=f"(r) : "f"(a), "f"(b), "r"(cond));
+    return r;
+}
+__device__ __forceinline__ int k1_selp_i(int a, int b, uint32_t cond) {
+    int r;
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\tselp.s32 %0, %1, %2, p;\n\t}" : "=r"(r) : "r"(a), "r"(b), "r"(cond));
+    return r;
+}
+#endif
+
 // `tab`: [512] = sdiv_table | hdiv_table180 (the kernel keeps them in shared memory); on the host NULL = compute them.
 __host__ __device__ __forceinline__ void k1_rgb2hsv(int r, int g, int b, int& h, int& s, int& v, const int* tab) {
     v = r > g ? r : g; v = v > b ? v : b;
@@ -83,7 +96,12 @@ __host__ __device__ __forceinline__ void k1_rgb2hsv(int r, int g, int b, int& h,
     const int hd = tab ? tab[256 + diff] : k1_hsv_hdiv(diff);
 #endif
     s = (diff * sd + (1 << 11)) >> 12;
+#ifdef __CUDA_ARCH__
+    // (selects, not branches: neighbouring pixels have different maxima)
+    int hh = k1_selp_i(g - b, k1_selp_i(b - r + 2 * diff, r - g + 4 * diff, (uint32_t)(v == g)), (uint32_t)(v == r));
+#else
     int hh = (v == r) ? (g - b) : ((v == g) ? (b - r + 2 * diff) : (r - g + 4 * diff));
+#endif
     hh = (hh * hd + (1 << 11)) >> 12;   // arithmetic shift, as in OpenCV
     h = hh < 0 ? hh + 180 : hh;
 }
@@ -93,7 +111,10 @@ __host__ __device__ __forceinline__ void k1_hsv2rgb(int h, int s, int v, bool tr
     const float hscale = 0x1.111112p-5f; // 6.f / 180.f
 #ifdef __CUDA_ARCH__
     const float sf = __fmul_rn((float)s, k255), vf = __fmul_rn((float)v, k255), hf = __fmul_rn((float)h, hscale);
-    const float pre = truncf(hf), fr = __fsub_rn(hf, pre);
+    // trunc(hf) == h / 30 for every h in 0..255 (checked exhaustively), so the sector comes from the integer and its
+    // float form from the 2^23 trick instead of FRND + F2I
+    const uint32_t sec6 = (uint32_t)(h * 2185) >> 16;
+    const float pre = __fsub_rn(__int_as_float(0x4B000000 | (int)sec6), 8388608.f), fr = __fsub_rn(hf, pre);
     const float t1 = __fmul_rn(vf, __fsub_rn(1.f, sf));
     const float t2 = __fmul_rn(vf, __fmaf_rn(-sf, fr, 1.f));
     const float t3 = __fmul_rn(vf, __fmaf_rn(-sf, __fsub_rn(1.f, fr), 1.f));
@@ -106,20 +127,32 @@ __host__ __device__ __forceinline__ void k1_hsv2rgb(int h, int s, int v, bool tr
     volatile float i2 = fmaf(-sf, fr, 1.f), i3 = fmaf(-sf, omf, 1.f);
     volatile float t2 = vf * i2, t3 = vf * i3;
 #endif
+#ifdef __CUDA_ARCH__
+    // sector_data = {1,3,0},{1,0,2},{3,0,1},{0,2,1},{0,1,3},{2,1,0} -> (b, g, r) from tab0..3 (= vf, t1, t2, t3).  Even
+    // sectors use t3 and odd ones t2 as their "moving" value tv, and every channel is then one of {vf, t1, tv} chosen
+    // by the sector alone: two selects per channel on bit tests of (1 << sector).  Written with selp so that the lanes
+    // of a warp (which sit in different sectors) never diverge -- as nested ?: the compiler emits a branch tree that
+    // every warp walks completely.
+    const uint32_t m = 1u << (sec6 >= 6u ? sec6 - 6u : sec6);         // 1 << sector (a table may hand out h >= 180)
+    const float tv = k1_selp(t2, t3, m & 0x2Au);                        // odd sectors: t2
+    const float bb = k1_selp(t1, k1_selp(vf, tv, m & 0x18u), m & 0x03u);   // t1: 0,1   vf: 3,4   tv: 2,5
+    const float gg = k1_selp(vf, k1_selp(t1, tv, m & 0x30u), m & 0x06u);   // vf: 1,2   t1: 4,5   tv: 0,3
+    const float rr = k1_selp(vf, k1_selp(t1, tv, m & 0x0Cu), m & 0x21u);   // vf: 0,5   t1: 2,3   tv: 1,4
+    // x * 255 -> uint8 without F2I: adding 2^23 leaves round(x) (ties to even, as cvRound) or, with round-toward-zero,
+    // floor(x) in the low mantissa bits; x >= -1 here and the final clamp maps the -1 a tiny negative x truncates to
+    // (2^23 - 0.5 -> ...FF) back to 0.
+    const float r255 = __fmul_rn(rr, 255.f), g255 = __fmul_rn(gg, 255.f), b255 = __fmul_rn(bb, 255.f);
+    const float big = 8388608.f;
+    const int ri = (trunc ? __float_as_int(__fadd_rz(r255, big)) : __float_as_int(__fadd_rn(r255, big))) - 0x4B000000;
+    const int gi = (trunc ? __float_as_int(__fadd_rz(g255, big)) : __float_as_int(__fadd_rn(g255, big))) - 0x4B000000;
+    const int bi = (trunc ? __float_as_int(__fadd_rz(b255, big)) : __float_as_int(__fadd_rn(b255, big))) - 0x4B000000;
+#else
     int sector = (int)pre;
     sector = sector >= 6 ? sector - 6 : sector;
-    // sector_data = {1,3,0},{1,0,2},{3,0,1},{0,2,1},{0,1,3},{2,1,0} -> (b, g, r) from tab0..3 (= vf, t1, t2, t3);
-    // written as selects so that the lanes of a warp (which sit in different sectors) do not diverge
     const float t0 = vf, u1 = t1, u2 = t2, u3 = t3;
     const float bb = sector <= 1 ? u1 : (sector == 2 ? u3 : (sector == 5 ? u2 : t0));
     const float gg = sector == 0 ? u3 : (sector <= 2 ? t0 : (sector == 3 ? u2 : u1));
     const float rr = (sector == 0 || sector == 5) ? t0 : (sector == 1 ? u2 : (sector == 4 ? u3 : u1));
-#ifdef __CUDA_ARCH__
-    const float r255 = __fmul_rn(rr, 255.f), g255 = __fmul_rn(gg, 255.f), b255 = __fmul_rn(bb, 255.f);
-    const int ri = trunc ? __float2int_rz(r255) : __float2int_rn(r255);
-    const int gi = trunc ? __float2int_rz(g255) : __float2int_rn(g255);
-    const int bi = trunc ? __float2int_rz(b255) : __float2int_rn(b255);
-#else
     volatile float r255 = rr * 255.f, g255 = gg * 255.f, b255 = bb * 255.f;
     const int ri = trunc ? (int)r255 : (int)rintf(r255), gi = trunc ? (int)g255 : (int)rintf(g255),
               bi = trunc ? (int)b255 : (int)rintf(b255);

@@ -18,284 +18,56 @@
 //   * crops the ring cannot serve (frame rows not 16-byte aligned, boxes wider than
 //     ~1500 px, invalid boxes) fall back, per CTA, to the direct-load band routine
 //     of k1_general_impl.cuh -- same bits, one launch for the whole batch.
-#include "k1_general_impl.cuh"
+#include "k1_fast_impl.cuh"
+
+// This translation unit is compiled twice: as is (validation / inference pipelines) and, through k1_fast_aug.cu, with
+// the train-time augmentations fused (K1_FAST_AUG).
+#ifndef K1_FAST_AUG
+#define K1_FAST_AUG false
+#define K1_FAST_LAUNCHER launch_k1_fast
+#endif
 
 namespace nkbk {
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// Source rows are re-read by overlapping boxes of the same frame (and by the neighbouring band of the same box):
-// keep them in L2 (evict_last) while the 3x larger output stream goes through with evict-first stores.
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
-        "l"(src), "r"(bytes), "r"(bar), "l"(policy)
-        : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "NKBK_WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra NKBK_DONE_%=;\n\t"
-        "bra NKBK_WAIT_%=;\n\t"
-        "NKBK_DONE_%=:\n\t"
-        "}" ::"r"(bar),
-        "r"(parity)
-        : "memory");
+// `overlap`: enqueue as a programmatic dependent of the kernel in front (nkbk_k1_overlap_previous): K1 never calls
+// griddepcontrol.wait -- it reads nothing that kernel writes -- so it starts as soon as that kernel has released its
+// dependents (k2_fused_step does so at entry) and SMs are free.
+template <typename Kern>
+static void launch_k1_kernel(Kern kern, const K1Params& p, dim3 grid, cudaStream_t st) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(K1_WARPS * 32);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    if (k1_overlap_previous()) {
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+    }
+    cudaLaunchKernelEx(&cfg, kern, p);
 }
 
-// (((b0 * h0) >> 16) + ((b1 * h1) >> 16) + 2) >> 2 with b pre-shifted by 16.  (Folding the "+2" and the first tap into
-// the IMAD.HI addends through mad.hi.u32 was tried: the 64-bit addend pairs cost more register moves than the adds
-// they save -- 215 vs 177 instructions per output row.)
-__device__ __forceinline__ uint32_t vtap(uint32_t b0, uint32_t h0, uint32_t b1, uint32_t h1) {
-    return (__umulhi(b0, h0) + __umulhi(b1, h1) + 2u) >> 2;
-}
-
-#ifndef K1F_MIN_BLOCKS
-#define K1F_MIN_BLOCKS 4
-#endif
-
-// LB = true: A.LongestMaxSize + centred A.PadIfNeeded (the geometry of every val / train pipeline in the reference's
-// configs): the resized crop covers columns [left, left + dw) and rows [top, top + dh) of the output; lanes / rows
-// outside it emit the pad value and never touch the source.
-template <int JMAX, typename OutT, bool LB>
-__global__ void __launch_bounds__(K1_WARPS * 32, K1F_MIN_BLOCKS) k1_crop_resize_normalize_tma(const K1Params p) {
-    __shared__ __align__(128) uint8_t ring[K1_WARPS][K1F_RING_BYTES];
-    __shared__ __align__(8) uint64_t bars[K1_WARPS][K1F_MAX_SLOTS];
-    __shared__ int fetch_rows[K1_WARPS][64];
-
-    const int crop = blockIdx.x;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int band = blockIdx.y * K1_WARPS + warp;
-    const int y_begin = band * p.rows_per_warp_fast;
-    if (y_begin >= p.out_h) return;
-    const int nrows = min(p.rows_per_warp_fast, p.out_h - y_begin);   // <= 32: one output row per lane
-    const int ox0 = blockIdx.z * (32 * JMAX) + lane;
-
-    const CropGeom g = load_geom(p, crop);
-    uint32_t seg_start, seg_bytes, slot_stride;
-    int nslot;
-    int dw = p.out_w, dh = p.out_h, top = 0, left = 0;
-    bool fast = fast_path_qualifies(p, g, seg_start, seg_bytes, slot_stride, nslot);
-    if (LB && fast) fast = letterbox_geometry(g.bh, g.bw, p.max_size, p.out_h, p.out_w, dh, dw, top, left);
-    if (!fast) {
-        // unaligned frame rows, a box wider than the ring, an invalid box or a letterbox that does not fit: same
-        // arithmetic, direct loads
-        k1_process_band<JMAX, OutT, true, false>(p, crop, g, y_begin, nrows, ox0,
-                                                 blockIdx.y == 0 && blockIdx.z == 0 && warp == 0);
-        return;
-    }
-
-    // ---- per-warp barriers ----
-    const uint32_t bar0 = smem_u32(&bars[warp][0]);
-    const uint32_t ring0 = smem_u32(&ring[warp][0]);
-    if (lane == 0) {
-        for (int s = 0; s < nslot; ++s) mbar_init(bar0 + 8u * s, 1u);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-
-    // ---- horizontal tables: smem byte offset of the window, funnel shift, packed coefficients ----
-    uint32_t soa[JMAX], sk8[JMAX], cf[JMAX];
-    uint32_t vmask = (1u << JMAX) - 1u;   // LB: columns of this lane that receive resized pixels (the rest is border)
-    {
-        const double sxs = axis_scale(dw, g.bw);
-        if (LB) vmask = 0;
-#pragma unroll
-        for (int j = 0; j < JMAX; ++j) {
-            int s = 0, c0 = 0, c1 = 0;
-            const int dx = ox0 + 32 * j - left;
-            const bool valid = !LB || (dx >= 0 && dx < dw);
-            if (valid) axis_coef(dx, sxs, g.bw, true, s, c0, c1);
-            int px = g.bx0 + s;
-            uint32_t c = uint32_t(c0) | (uint32_t(c1) << 16);
-            if (px + 1 >= g.fw) {  // window would leave the frame row: shift it left, weight moves to tap 1
-                px -= 1;
-                c = uint32_t(c0) << 16;
-            }
-            if (LB) {
-                vmask |= uint32_t(valid) << j;
-                if (!valid) c = 0u;   // border column: reads the box's first window, weights zero (value replaced below)
-            }
-            const uint32_t so = uint32_t(px) * 3u - seg_start;
-            soa[j] = so & ~3u;
-            sk8[j] = (so & 3u) * 8u;
-            cf[j] = c;
-        }
-    }
-
-    // ---- vertical tables: lane l holds output row y_begin + l ----
-    int my_r0 = -1, my_r1 = -1;
-    uint32_t my_b0 = 0, my_b1 = 0;
-    if (lane < nrows) {
-        const int dy = y_begin + lane - top;
-        if (!LB || (dy >= 0 && dy < dh)) {   // LB: border rows keep r0 = -1 and never enter the fetch list
-            int s, c0, c1;
-            axis_coef(dy, axis_scale(dh, g.bh), g.bh, false, s, c0, c1);
-            my_r0 = min(max(s, 0), g.bh - 1);
-            my_r1 = min(max(s + 1, 0), g.bh - 1);
-            my_b0 = uint32_t(c0) << 16;  // pre-shifted: umulhi(b << 16, h) == (b * h) >> 16
-            my_b1 = uint32_t(c1) << 16;
-        }
-    }
-
-    // ---- fetch list: the strictly increasing sequence of source rows this band consumes ----
-    int nfetch;
-    {
-        int prev_r1 = __shfl_up_sync(0xffffffffu, my_r1, 1);
-        if (lane == 0) prev_r1 = -1;
-        const bool new0 = lane < nrows && my_r0 > prev_r1;
-        const bool new1 = lane < nrows && my_r1 > my_r0 && my_r1 > prev_r1;
-        const uint32_t m0 = __ballot_sync(0xffffffffu, new0), m1 = __ballot_sync(0xffffffffu, new1);
-        const uint32_t lt = (1u << lane) - 1u;
-        const int pos0 = __popc(m0 & lt) + __popc(m1 & lt);
-        if (new0) fetch_rows[warp][pos0] = my_r0;
-        if (new1) fetch_rows[warp][pos0 + (new0 ? 1 : 0)] = my_r1;
-        nfetch = __popc(m0) + __popc(m1);
-    }
-    __syncwarp();
-
-    const uint8_t* const src_seg = p.frames + g.f_off + (int64_t)g.by0 * g.pitch + seg_start;
-    const uint32_t pitch32 = (uint32_t)g.pitch;  // qualifying crops have bh * pitch < 2^31 (fast_path_qualifies)
-    const uint64_t l2pol = l2_policy_evict_last();
-    // lane 0: start the bulk copy of fetch number k into the slot at (slot_addr, bar_addr)
-    auto issue = [&](int k, uint32_t slot_addr, uint32_t bar_addr) {
-        const uint32_t row = (uint32_t)fetch_rows[warp][k];
-        mbar_expect_tx(bar_addr, seg_bytes);
-        bulk_g2s(slot_addr, src_seg + row * pitch32, seg_bytes, bar_addr, l2pol);
-    };
-    if (lane == 0) {
-        const int pre = min(nslot, nfetch);
-        for (int k = 0; k < pre; ++k) issue(k, ring0 + slot_stride * k, bar0 + 8u * k);
-    }
-
-    const uint32_t sel0 = p.sel[0], sel1 = p.sel[1], sel2 = p.sel[2];
-    const float m0f = p.m[0], m1f = p.m[1], m2f = p.m[2];
-    const float d0f = p.d[0], d1f = p.d[1], d2f = p.d[2];
-    const int64_t plane = (int64_t)p.out_h * p.out_w;
-    OutT* o = reinterpret_cast<OutT*>(p.out) + (int64_t)crop * 3 * plane + (int64_t)y_begin * p.out_w + ox0;
-    const int out_w = p.out_w;
-
-    uint32_t HA[JMAX][3], HB[JMAX][3];
-    int iA = -1, iB = -1;
-    int consumed = 0;
-    uint32_t cslot = 0, cparity = 0, cur_slot = ring0, cur_bar = bar0;
-    const uint32_t ring_end = ring0 + slot_stride * (uint32_t)nslot;
-
-    // wait for the next staged row, run the horizontal pass into H, refill the slot
-    auto consume_into = [&](uint32_t (&H)[JMAX][3]) {
-        mbar_wait(cur_bar, cparity);
-#pragma unroll
-        for (int j = 0; j < JMAX; ++j) {
-            const uint32_t a = cur_slot + soa[j];
-            uint32_t w0, w1, w2;
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(a));
-            asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(w1) : "r"(a));
-            asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(w2) : "r"(a));
-            const uint32_t lo = __funnelshift_r(w0, w1, sk8[j]);  // bytes o .. o+3
-            const uint32_t hi = __funnelshift_r(w1, w2, sk8[j]);  // bytes o+4 .. o+7
-            H[j][0] = __dp2a_lo(cf[j], __byte_perm(lo, hi, sel0), 0u) >> 4;
-            H[j][1] = __dp2a_lo(cf[j], __byte_perm(lo, hi, sel1), 0u) >> 4;
-            H[j][2] = __dp2a_lo(cf[j], __byte_perm(lo, hi, sel2), 0u) >> 4;
-        }
-        __syncwarp();  // every lane has read the slot before it is overwritten
-        if (lane == 0 && consumed + nslot < nfetch) issue(consumed + nslot, cur_slot, cur_bar);
-        ++consumed;
-        cur_slot += slot_stride;
-        cur_bar += 8u;
-        if (cur_slot == ring_end) { cur_slot = ring0; cur_bar = bar0; cparity ^= 1u; }
-    };
-    (void)cslot;
-
-    for (int yy = 0; yy < nrows; ++yy) {
-        const int r0 = __shfl_sync(0xffffffffu, my_r0, yy);
-        const int r1 = __shfl_sync(0xffffffffu, my_r1, yy);
-        const uint32_t b0 = __shfl_sync(0xffffffffu, my_b0, yy);
-        const uint32_t b1 = __shfl_sync(0xffffffffu, my_b1, yy);
-        if (LB && r0 < 0) {   // letterbox border row: the normalised pad value, no source row involved
-#pragma unroll
-            for (int j = 0; j < JMAX; ++j) {
-                store_out<OutT>(o + 32 * j, p.padf[0]);
-                store_out<OutT>(o + plane + 32 * j, p.padf[1]);
-                store_out<OutT>(o + 2 * plane + 32 * j, p.padf[2]);
-            }
-            o += out_w;
-            continue;
-        }
-        auto vertical = [&](const uint32_t (&Ht)[JMAX][3], const uint32_t (&Hb)[JMAX][3]) {
-            // Normalize two columns per instruction: (v - m) * d as FADD2 + FMUL2 (packed fp32, IEEE round-to-nearest
-            // per half: the same two separately rounded operations, half the issue slots)
-            const float mf[3] = {m0f, m1f, m2f}, df[3] = {d0f, d1f, d2f};
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                OutT* oc = o + c * plane;
-#pragma unroll
-                for (int j = 0; j < JMAX; j += 2) {
-                    uint32_t va = vtap(b0, Ht[j][c], b1, Hb[j][c]);
-                    if (LB && !(vmask >> j & 1)) va = p.padu[c];
-                    if (j + 1 < JMAX) {
-                        uint32_t vb = vtap(b0, Ht[j + 1][c], b1, Hb[j + 1][c]);
-                        if (LB && !(vmask >> (j + 1) & 1)) vb = p.padu[c];
-                        float ra, rb;
-                        normalize2((float)va, (float)vb, mf[c], df[c], ra, rb);
-                        store_out<OutT>(oc + 32 * j, ra);
-                        store_out<OutT>(oc + 32 * (j + 1), rb);
-                    } else {
-                        store_out<OutT>(oc + 32 * j, __fmul_rn(__fsub_rn((float)va, mf[c]), df[c]));
-                    }
-                }
-            }
-        };
-        // Ht must hold source row r0, Hb row r1 (r1 == r0 only when the tap is clamped at an edge)
-        auto row_step = [&](uint32_t (&Ht)[JMAX][3], uint32_t (&Hb)[JMAX][3], int& it, int& ib) {
-            if (r0 != it) { consume_into(Ht); it = r0; }
-            if (r1 != r0) {
-                if (r1 != ib) { consume_into(Hb); ib = r1; }
-                vertical(Ht, Hb);
-            } else {
-                vertical(Ht, Ht);
-            }
-        };
-        // roles flip (no register copies) when the lower tap of the previous row is this row's upper tap
-        const bool a_is_top = (r0 == iA) || (r0 != iB);
-        if (a_is_top) row_step(HA, HB, iA, iB);
-        else row_step(HB, HA, iB, iA);
-        o += out_w;
-    }
-}
-
-template <int JMAX>
+template <int JMAX, bool AUG>
 static void launch_fast_j(const K1Params& p, dim3 grid, cudaStream_t st, bool f32) {
     if (p.mode == NKBK_MODE_LETTERBOX) {
-        if (f32) k1_crop_resize_normalize_tma<JMAX, float, true><<<grid, K1_WARPS * 32, 0, st>>>(p);
-        else k1_crop_resize_normalize_tma<JMAX, __nv_bfloat16, true><<<grid, K1_WARPS * 32, 0, st>>>(p);
+        if (f32) launch_k1_kernel(k1_crop_resize_normalize_tma<JMAX, float, true, AUG>, p, grid, st);
+        else launch_k1_kernel(k1_crop_resize_normalize_tma<JMAX, __nv_bfloat16, true, AUG>, p, grid, st);
     } else {
-        if (f32) k1_crop_resize_normalize_tma<JMAX, float, false><<<grid, K1_WARPS * 32, 0, st>>>(p);
-        else k1_crop_resize_normalize_tma<JMAX, __nv_bfloat16, false><<<grid, K1_WARPS * 32, 0, st>>>(p);
+        if (f32) launch_k1_kernel(k1_crop_resize_normalize_tma<JMAX, float, false, AUG>, p, grid, st);
+        else launch_k1_kernel(k1_crop_resize_normalize_tma<JMAX, __nv_bfloat16, false, AUG>, p, grid, st);
     }
 }
 
 // Returns false when no fast instantiation exists for this column-tile width.
-bool launch_k1_fast(const K1Params& p, int jmax, dim3 grid, cudaStream_t st, bool f32) {
+bool K1_FAST_LAUNCHER(const K1Params& p, int jmax, dim3 grid, cudaStream_t st, bool f32) {
     switch (jmax) {
-        case 4: launch_fast_j<4>(p, grid, st, f32); return true;
-        case 5: launch_fast_j<5>(p, grid, st, f32); return true;
-        case 6: launch_fast_j<6>(p, grid, st, f32); return true;
-        case 7: launch_fast_j<7>(p, grid, st, f32); return true;
-        case 8: launch_fast_j<8>(p, grid, st, f32); return true;
+        case 4: launch_fast_j<4, K1_FAST_AUG>(p, grid, st, f32); return true;
+        case 5: launch_fast_j<5, K1_FAST_AUG>(p, grid, st, f32); return true;
+        case 6: launch_fast_j<6, K1_FAST_AUG>(p, grid, st, f32); return true;
+        case 7: launch_fast_j<7, K1_FAST_AUG>(p, grid, st, f32); return true;
+        case 8: launch_fast_j<8, K1_FAST_AUG>(p, grid, st, f32); return true;
         default: return false;
     }
 }

@@ -30,10 +30,12 @@
 //   (b*(H>>4))>>16 per tap, +2, >> 2, int->float, then (v - mean255) * denom
 //   as two separately rounded fp32 operations.
 #include "k1_general_impl.cuh"
+#include <stdlib.h>
 
 namespace nkbk {
 
-bool launch_k1_fast(const K1Params& p, int jmax, dim3 grid, cudaStream_t st, bool f32);  // k1_fast.cu
+bool launch_k1_fast(const K1Params& p, int jmax, dim3 grid, cudaStream_t st, bool f32);      // k1_fast.cu
+bool launch_k1_fast_aug(const K1Params& p, int jmax, dim3 grid, cudaStream_t st, bool f32);  // k1_fast_aug.cu
 
 // One crop per blockIdx.x, one band of rows per warp.
 template <int JMAX, typename OutT, bool GENERAL, bool WRITE_U8, bool AUG = false>
@@ -184,10 +186,11 @@ static int k1_preprocess_impl(const void* frames_base, const int64_t* frame_desc
     p.rows_per_warp_fast = p.rows_per_warp;
 
     // ---- fast path: A.Resize or LongestMaxSize + PadIfNeeded, output width a whole number of 32*J column tiles,
-    // no uint8 side output, no train-time augmentations ----
+    // no uint8 side output; the train-time augmentations have their own instantiation (k1_fast_aug.cu) ----
     // Crops whose frame rows are not 16-byte aligned or whose boxes are too wide for the shared-memory ring are
-    // left untouched by the TMA kernel and produced by the general kernel in a small-grid fix-up pass.
-    if (out_u8 == nullptr && out_w % 32 == 0 && aug == nullptr) {
+    // produced, per CTA, by the direct-load band routine inside the same launch.
+    static const bool aug_direct = getenv("NKBK_K1_AUG_DIRECT") != nullptr;   // experiment knob: augmentations on the direct-load kernel
+    if (out_u8 == nullptr && out_w % 32 == 0 && (aug == nullptr || !aug_direct)) {
         const int cols = out_w / 32;
         int fj = 0;
         for (int j = 8; j >= 4; --j)
@@ -200,7 +203,7 @@ static int k1_preprocess_impl(const void* frames_base, const int64_t* frame_desc
         p.rows_per_warp_fast = (out_h + fby * K1_WARPS - 1) / (fby * K1_WARPS);
         if (fj != 0 && cols / fj <= 65535 && fby <= 65535) {
             dim3 fgrid((unsigned)n, (unsigned)fby, (unsigned)(cols / fj));
-            if (launch_k1_fast(p, fj, fgrid, st, f32)) {
+            if (aug != nullptr ? launch_k1_fast_aug(p, fj, fgrid, st, f32) : launch_k1_fast(p, fj, fgrid, st, f32)) {
                 NKBK_CHECK_LAUNCH("k1_crop_resize_normalize_tma");
                 return NKBK_OK;   // crops the TMA path cannot take are produced in-kernel by the direct-load routine
             }

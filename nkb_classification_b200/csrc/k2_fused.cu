@@ -209,6 +209,9 @@ __global__ void __launch_bounds__(KF_THREADS, 1) k2_fused_step(const KFParams p)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ unsigned int step_s;
     __shared__ bool last_s;
+    // This CTA is resident: a kernel enqueued behind this one as a programmatic dependent (K1 of the next batch under
+    // nkbk_k1_overlap_previous) may start on the SMs this grid does not occupy.  No effect on ordinary launches.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const K2FwdParams& f = p.f;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int T = f.seg.T, NC = f.NC, D = f.D, NCD = p.NCD, TR = p.tile_rows;

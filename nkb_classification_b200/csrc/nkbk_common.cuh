@@ -12,6 +12,7 @@ namespace nkbk {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+bool k1_overlap_previous();   // nkbk_k1_overlap_previous(): K1 launches as programmatic dependents
 
 #define NKBK_CHECK_ARG(cond, ...)            \
     do {                                     \

@@ -10,7 +10,7 @@ from typing import Dict, Optional, Sequence
 import numpy as np
 import torch
 
-from . import ops
+from . import _lib, ops
 from ._lib import LOSS_CE, LOSS_FOCAL
 from .parallel import Communicator
 from .transforms import PreprocessPlan
@@ -42,10 +42,20 @@ class HotPath:
         self._images: Dict[int, torch.Tensor] = {}
         self._pred: Dict[int, torch.Tensor] = {}
         self._desc = None
+        self._heads_done: Optional[torch.cuda.Event] = None   # set by mark_heads_done() in overlapped loops
+
+    def mark_heads_done(self):
+        """Call right after heads_step in a loop that launches K1 with ``overlap_previous=True``."""
+        if self._heads_done is None:
+            self._heads_done = torch.cuda.Event()
+        self._heads_done.record(torch.cuda.current_stream(self.device))
 
     # ---- K1 ----
     def preprocess(self, frames: torch.Tensor, boxes: torch.Tensor, frame_idx: torch.Tensor,
-                   frame_desc: Optional[torch.Tensor] = None, aug=None) -> torch.Tensor:
+                   frame_desc: Optional[torch.Tensor] = None, aug=None, overlap_previous: bool = False) -> torch.Tensor:
+        """``overlap_previous``: this K1 (batch i+1) may start while the fused heads step enqueued just before it on the
+        same stream (batch i) is still running, on the SMs that step leaves free (nkbk_k1_overlap_previous: a
+        programmatic dependent launch).  Safe here because this object owns K1's output buffer and the heads buffers."""
         n = int(frame_idx.numel())
         out = self._images.get(n)
         if out is None:
@@ -58,8 +68,15 @@ class HotPath:
             frame_desc = self._desc[1]
         if aug is None and self.plan.augment is not None:
             aug = self.plan.draw(n)            # train-time pipeline: draw this batch's per-sample parameters
-        return ops.preprocess_crops(frames, boxes, frame_idx, self.plan, self.out_dtype, out=out, frame_desc=frame_desc,
-                                    aug=aug)
+        if not overlap_previous:
+            return ops.preprocess_crops(frames, boxes, frame_idx, self.plan, self.out_dtype, out=out,
+                                        frame_desc=frame_desc, aug=aug)
+        prev = _lib.lib().nkbk_k1_overlap_previous(1)
+        try:
+            return ops.preprocess_crops(frames, boxes, frame_idx, self.plan, self.out_dtype, out=out,
+                                        frame_desc=frame_desc, aug=aug)
+        finally:
+            _lib.lib().nkbk_k1_overlap_previous(prev)
 
     # ---- K2 + K3 + K4 ----
     def _buffers(self, B: int, train: bool, want_probs: bool) -> ops.HeadsBuffers:
@@ -86,6 +103,9 @@ class HotPath:
             if pred is None:
                 pred = torch.empty((B, self.T), dtype=torch.int32, device=self.device)
                 self._pred = {B: pred}
+        if self._heads_done is not None:
+            # an overlapped K1 sits between two heads steps: make the order of the heads steps themselves explicit
+            torch.cuda.current_stream(self.device).wait_event(self._heads_done)
         if train and (self.comm.world == 1 or self.transport == "peer"):
             # the whole step -- forward, loss, K3, dW / db, exchange (K4' as the kernel's epilogue), finalize -- as ONE
             # launch (nkbk_heads_train_step); the NCCL transport keeps the separate launches below
