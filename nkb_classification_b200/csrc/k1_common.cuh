@@ -157,9 +157,17 @@ __host__ __device__ __forceinline__ void k1_hsv2rgb(int h, int s, int v, bool tr
     const int ri = trunc ? (int)r255 : (int)rintf(r255), gi = trunc ? (int)g255 : (int)rintf(g255),
               bi = trunc ? (int)b255 : (int)rintf(b255);
 #endif
+#ifdef __CUDA_ARCH__
+    // every tab value is <= vf <= fl(255 * k255) = 1 + 2^-23, so x * 255 < 255.5 rounds to at most 255: only the lower
+    // clamp (the -1 above) is needed
+    r = (uint32_t)max(ri, 0);
+    g = (uint32_t)max(gi, 0);
+    b = (uint32_t)max(bi, 0);
+#else
     r = (uint32_t)(ri < 0 ? 0 : (ri > 255 ? 255 : ri));
     g = (uint32_t)(gi < 0 ? 0 : (gi > 255 ? 255 : gi));
     b = (uint32_t)(bi < 0 ? 0 : (bi > 255 ? 255 : bi));
+#endif
 }
 // lut: [3][256] = hue, sat, val tables of this sample
 template <typename LoadByte>

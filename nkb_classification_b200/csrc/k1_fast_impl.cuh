@@ -51,7 +51,7 @@ __device__ __forceinline__ uint32_t vtap(uint32_t b0, uint32_t h0, uint32_t b1, 
 #define K1F_MIN_BLOCKS 4
 #endif
 #ifndef K1F_MIN_BLOCKS_AUG
-#define K1F_MIN_BLOCKS_AUG 4
+#define K1F_MIN_BLOCKS_AUG 3   // 168 registers, no spills (4 blocks -> 128 registers spill in the colour ops: 1.66 ms vs the direct kernel's 1.38)
 #endif
 
 // LB = true: A.LongestMaxSize + centred A.PadIfNeeded (the geometry of every val / train pipeline in the reference's
@@ -69,6 +69,7 @@ k1_crop_resize_normalize_tma(const K1Params p) {
     // HueSaturationValue: OpenCV's two division tables (built once per CTA) + per warp the current crop's 3 x 256 tables
     __shared__ int hsv_div_tab[AUG ? 512 : 1];
     __shared__ __align__(16) uint8_t hsv_lut_s[AUG ? K1_WARPS * 768 : 16];
+    __shared__ __align__(16) uint8_t bc_lut_s[AUG ? K1_WARPS * 256 : 16];   // per warp: the crop's brightness / contrast table
     if (AUG && p.aug_hsv_lut != nullptr) {
         for (int i = threadIdx.x; i < 256; i += K1_WARPS * 32) {
             hsv_div_tab[i] = k1_hsv_sdiv(i);
@@ -198,17 +199,25 @@ k1_crop_resize_normalize_tma(const K1Params p) {
     if (AUG) {
         aflags = __ldg(p.aug_flags + crop);
         nholes = min(aflags >> 8, p.aug_max_holes);
-        if (aflags & K1_AUG_BC) { a_alpha = __ldg(p.aug_alpha + crop); a_beta = __ldg(p.aug_beta + crop); }
         holes = p.aug_holes + (int64_t)crop * p.aug_max_holes * 4;
+        if (aflags & K1_AUG_BC) {
+            // albumentations applies brightness / contrast as a 256-entry table through cv2.LUT; so does this warp: eight
+            // entries per lane, then one byte load per channel instead of six instructions
+            a_alpha = __ldg(p.aug_alpha + crop); a_beta = __ldg(p.aug_beta + crop);
+            uint8_t* t = bc_lut_s + warp * 256;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t[lane + 32 * i] = (uint8_t)k1_brightness_contrast((uint32_t)(lane + 32 * i), a_alpha, a_beta);
+        }
         if (aflags & K1_AUG_HSV) {   // this crop's hue / sat / val tables -> the warp's 768 bytes of shared memory
             const uint32_t* src = reinterpret_cast<const uint32_t*>(p.aug_hsv_lut + (int64_t)crop * 768);
             uint32_t* dst = reinterpret_cast<uint32_t*>(hsv_lut_s + warp * 768);
 #pragma unroll
             for (int i = 0; i < 6; ++i) dst[lane + 32 * i] = __ldg(src + lane + 32 * i);
-            __syncwarp();
             hsv_lut = hsv_lut_s + warp * 768;
         }
+        __syncwarp();
     }
+    const uint8_t* const bc_lut = bc_lut_s + (AUG ? warp * 256 : 0);
     const bool hflip = AUG && (aflags & K1_AUG_HFLIP), vflip = AUG && (aflags & K1_AUG_VFLIP);
     const int xstep = hflip ? -32 : 32;                       // destination column step between this lane's j's
     const int xd0 = hflip ? p.out_w - 1 - ox0 : ox0;          // destination column of j = 0
@@ -238,7 +247,7 @@ k1_crop_resize_normalize_tma(const K1Params p) {
 #pragma unroll
             for (int j = 0; j < JMAX; ++j)
 #pragma unroll
-                for (int c = 0; c < 3; ++c) P[j][c] = k1_brightness_contrast(P[j][c], a_alpha, a_beta);
+                for (int c = 0; c < 3; ++c) P[j][c] = bc_lut[P[j][c]];
         }
         if (hsv_lut != nullptr) {
 #pragma unroll
@@ -330,18 +339,17 @@ k1_crop_resize_normalize_tma(const K1Params p) {
             o += out_w;
             continue;
         }
+        uint32_t PA[AUG ? JMAX : 1][3];   // AUG: this row's resized (and padded) pixels
         auto vertical = [&](const uint32_t (&Ht)[JMAX][3], const uint32_t (&Hb)[JMAX][3]) {
-            if constexpr (AUG) {
-                uint32_t P[JMAX][3];
+            if constexpr (AUG) {   // only the pixels here: the colour ops and the stores follow ONCE below (this lambda is
+                                   // inlined four times; four copies of the colour ops thrash the instruction cache)
 #pragma unroll
                 for (int j = 0; j < JMAX; ++j)
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
-                        P[j][c] = vtap(b0, Ht[j][c], b1, Hb[j][c]);
-                        if (LB && !(vmask >> j & 1)) P[j][c] = p.padu[c];
+                        PA[j][c] = vtap(b0, Ht[j][c], b1, Hb[j][c]);
+                        if (LB && !(vmask >> j & 1)) PA[j][c] = p.padu[c];
                     }
-                augment_row(P, hmask);
-                store_row(od, P);
                 return;
             }
             // Normalize two columns per instruction: (v - m) * d as FADD2 + FMUL2 (packed fp32, IEEE round-to-nearest
@@ -381,6 +389,10 @@ k1_crop_resize_normalize_tma(const K1Params p) {
         const bool a_is_top = (r0 == iA) || (r0 != iB);
         if (a_is_top) row_step(HA, HB, iA, iB);
         else row_step(HB, HA, iB, iA);
+        if constexpr (AUG) {
+            augment_row(PA, hmask);
+            store_row(od, PA);
+        }
         o += out_w;
     }
 }
