@@ -196,9 +196,18 @@ static int k1_preprocess_impl(const void* frames_base, const int64_t* frame_desc
         for (int j = 8; j >= 4; --j)
             if (cols % j == 0) { fj = j; break; }
         // the TMA kernel amortises its per-band prologue over up to 32 rows per warp (128 per CTA)
-        // ... but small batches need the parallelism more: halve the band until ~2 waves of warps exist
+        // ... but small batches need the parallelism more.  Measured (rows per warp 32 / 24 / 16 / 12 / 8 / 6, K1 in us):
+        // 512 crops 83.0 / 79.9 / 78.4 / 80.0 / 80.6 / 86.5; 1024 crops 144.9 / 142.0 / 141.9 / 146.7 / 150.3 / 163.9;
+        // 256 images of 256^2 47.1 / 47.5 / 41.7 / 45.9 / 45.8 / 48.4 -- 16 rows until there are ~4 bands per resident
+        // warp, 8 rows only for batches that cannot even fill half the warp slots with 16-row bands.
+        const int64_t tiles = (int64_t)n * (cols / (fj ? fj : 1));
         int rmax = 32;
-        while (rmax > 8 && (int64_t)n * ((out_h + rmax - 1) / rmax) * (cols / (fj ? fj : 1)) < 148 * 16 * 2) rmax /= 2;
+        if (tiles * ((out_h + 31) / 32) < 148 * 16 * 4) rmax = 16;
+        if (tiles * ((out_h + 15) / 16) < 148 * 16 / 2) rmax = 8;
+        if (const char* e = getenv("NKBK_K1_RMAX")) {   // experiment knob: rows per warp of the TMA kernel (4 .. 32)
+            const int v = atoi(e);
+            if (v >= 4 && v <= 32) rmax = v;
+        }
         const int fby = (out_h + rmax * K1_WARPS - 1) / (rmax * K1_WARPS);
         p.rows_per_warp_fast = (out_h + fby * K1_WARPS - 1) / (fby * K1_WARPS);
         if (fj != 0 && cols / fj <= 65535 && fby <= 65535) {

@@ -28,6 +28,18 @@ constexpr int K2_DW_ROWS = 32 * NKBK_DW_WARPS;    // rows per dW chunk (32 per w
 constexpr int K2_DW_COLS = 128;    // columns per dW CTA (4 per lane)
 constexpr int K2_DW_NCB = 16;      // classes per dW pass
 
+// K3 in the forward-only kernels: one confusion count per (row, task), warp-aggregated -- the lanes of the calling warp
+// that hit the same bin are found with match.any and their leader adds the whole group with ONE 64-bit reduction, so a
+// trained model (every row on the diagonal) issues one atomic per warp and bin, not one per row.  Call with the lanes
+// that have a count converged (`bin` < 0 = this lane has none); exact integers, order independent.
+__device__ __forceinline__ void k3_count_aggregated(unsigned long long* cm, long long bin) {
+    const unsigned int act = __activemask();
+    const unsigned int have = __ballot_sync(act, bin >= 0);
+    if (bin < 0) return;
+    const unsigned int peers = __match_any_sync(have, bin);
+    if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(cm + bin, (unsigned long long)__popc(peers));
+}
+
 struct K2Seg {
     int T;
     int off[K2_MAX_TASKS + 1];

@@ -358,14 +358,16 @@ __global__ void __launch_bounds__(K2_V3_WARPS * 32) k2_heads_forward_v3(const K2
             if (p.out_pred) p.out_pred[(int64_t)row * T + t] = bi;
             if (p.cm_step != nullptr && p.labels != nullptr) {
                 const int64_t y = p.labels[(int64_t)row * T + t];
+                long long bin = -1;
                 if (y >= 0 && y < C) {
                     int64_t off = 0;
                     for (int s = 0; s < t; ++s) {
                         const int64_t Cs = p.seg.off[s + 1] - p.seg.off[s];
                         off += Cs * Cs;
                     }
-                    atomicAdd(p.cm_step + off + y * C + bi, 1ull);
+                    bin = off + y * C + bi;
                 }
+                k3_count_aggregated(p.cm_step, bin);
             }
         }
     }

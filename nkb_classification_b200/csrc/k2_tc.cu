@@ -319,14 +319,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k2_tc_heads_forward(const __gri
                     if (p.out_pred) p.out_pred[(int64_t)row * T + t] = bi;
                     if (p.cm_step != nullptr && p.labels != nullptr) {
                         const int64_t y = p.labels[(int64_t)row * T + t];
+                        long long bin = -1;
                         if (y >= 0 && y < C) {
                             int64_t off = 0;
                             for (int u = 0; u < t; ++u) {
                                 const int64_t Cu = p.seg.off[u + 1] - p.seg.off[u];
                                 off += Cu * Cu;
                             }
-                            atomicAdd(p.cm_step + off + y * C + bi, 1ull);
+                            bin = off + y * C + bi;
                         }
+                        k3_count_aggregated(p.cm_step, bin);   // 32 rows per warp: a trained model -> ~1 atomic per warp
                     }
                 }
             }

@@ -67,15 +67,18 @@ def inference(model: torch.nn.Module, loader, classes: Union[list, dict], save_p
         paths_all += list(img_paths)
     if preds_dev:
         pred = torch.cat(preds_dev).cpu().numpy()
-        cols = []
+        def names_of(mapping, idx):      # class names by fancy indexing instead of a Python loop per prediction
+            lut = np.array([str(mapping[i]) for i in range(len(mapping))], dtype=object)
+            return lut[idx.astype(np.int64)]
+
+        cols = {}
         if task == "single":
-            cols.append([idx_to_class[int(i)] for i in pred[:, 0]])
+            cols[columns[0]] = names_of(idx_to_class, pred[:, 0])
         else:
             for target_name in target_names:
-                t = names.index(target_name)
-                cols.append([idx_to_class[target_name][int(i)] for i in pred[:, t]])
-        cols.append(paths_all)
-        table = pd.DataFrame(np.vstack(cols).T, columns=columns)
+                cols[target_name] = names_of(idx_to_class[target_name], pred[:, names.index(target_name)])
+        cols["path"] = np.array(paths_all, dtype=object)
+        table = pd.DataFrame(cols, columns=columns)
     else:
         table = pd.DataFrame(columns=columns)
     table.to_csv(Path(save_path, "inference_annotations.csv"), index=False)

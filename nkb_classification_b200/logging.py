@@ -38,6 +38,22 @@ def _to_host(*tensors):
     return [o.numpy() for o in outs]
 
 
+def gather_rows(t: torch.Tensor) -> torch.Tensor:
+    """Rows of every rank, in rank order (ranks may hold different numbers of rows: uneven frame shards).  Collective over
+    torch.distributed's default group; the row counts travel first, so this synchronises -- epoch end only."""
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    ns = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(ns, n)
+    ns = [int(x.item()) for x in ns]
+    pad = torch.zeros((max(ns),) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[: t.shape[0]] = t
+    outs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(outs, pad)
+    return torch.cat([o[:k] for o, k in zip(outs, ns)])
+
+
 class BaseLogger:
     def __init__(self, cfg, classes):
         assert cfg.task in ("single", "multi")
@@ -54,6 +70,15 @@ class BaseLogger:
         self._img_event = None
         self._gt, self._conf, self._pred, self._loss = [], [], [], []
         self._seg, self._names = None, None
+
+    def _sharded(self) -> bool:
+        """True when the epoch was computed by several ranks (the engine's fused heads carry a communicator with
+        world > 1), torch.distributed can carry the gather and ``cfg.gather_epoch_results`` (default True) allows it."""
+        comm = None if self.fused is None else self.fused.state.get("comm")
+        if comm is None or getattr(comm, "world", 1) <= 1 or not getattr(self.cfg, "gather_epoch_results", True):
+            return False
+        import torch.distributed as dist
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
     # ---- fused path: everything stays on the device ----
     def log_fused(self, out, labels: torch.Tensor):
@@ -114,13 +139,18 @@ class BaseLogger:
             empty = [] if self.task == "single" else defaultdict(list)
             return {"running_loss": empty, "confidences": empty, "predictions": empty, "ground_truth": empty,
                     "images": self.epoch_images_example}
-        gt_d, conf_d = torch.cat(self._gt), torch.cat(self._conf)
+        gt_d, conf_d, pred_d = torch.cat(self._gt), torch.cat(self._conf), torch.cat(self._pred)
+        if self._sharded():
+            # a sharded run (cfg.communicator, world > 1): the fused step's confusion counts and losses are already global,
+            # so make the per-sample quantities global too -- every rank gathers every rank's rows (rank order), and the
+            # ROC-AUC pair counts below are then taken over the global epoch like the confusion matrix beside them
+            gt_d, conf_d, pred_d = gather_rows(gt_d), gather_rows(conf_d), gather_rows(pred_d)
         auc_counts = None
         if conf_d.is_cuda and self.device_roc_auc:
             # K5: exact ROC-AUC pair counts from the device-resident epoch, one [NC, 3] int64 D2H
             from . import ops
             auc_counts = ops.roc_auc_counts(conf_d.contiguous(), self._seg, gt_d.to(torch.int64).contiguous()).cpu().numpy()
-        gt, conf, pred, loss = _to_host(gt_d, conf_d, torch.cat(self._pred), torch.stack(self._loss))
+        gt, conf, pred, loss = _to_host(gt_d, conf_d, pred_d, torch.stack(self._loss))
         seg, names = self._seg, self._names
         res = {"images": self.epoch_images_example}
         # the reference hands out Python lists (logging.py:268-281); building them costs ~0.4 us per crop -- more than

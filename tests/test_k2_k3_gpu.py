@@ -441,3 +441,55 @@ def test_k2_tcgen05_weight_pack_is_cached_by_version(cuda_device, monkeypatch):
     assert n3 == n1 and torch.allclose(z3, -z1, atol=1e-6)                   # re-packed: the new weights are in use
     n4, z4, _ = call()
     assert n4 == n1 - 1 and torch.equal(z3, z4)
+
+
+@pytest.mark.parametrize("emb_dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("classes", [[10], [4, 3, 6, 9, 8]])
+def test_forward_only_k3_contention(cuda_device, emb_dtype, classes):
+    """Validation / inference steps (forward-only kernels: exact-fp32 FFMA forward, tcgen05 forward for bf16): the
+    confusion counts are warp-aggregated (match.any + one 64-bit atomic per warp and bin).  B = 65 536 rows that all hit
+    ONE bin per task must give exact counts and cost about what uniformly spread labels cost."""
+    from nkb_classification_b200 import ops
+    B, D = 65536, 256
+    dev = cuda_device
+    seg = np.concatenate([[0], np.cumsum(classes)]).tolist()
+    T, NC = len(classes), sum(classes)
+    g = torch.Generator().manual_seed(3)
+    W = torch.zeros(NC, D)
+    for t in range(T):
+        W[seg[t] + 1, :] = 1.0                       # class 1 of every task wins for positive embeddings
+    emb_same = (torch.rand(B, D, generator=g) + 0.5).to(emb_dtype)
+    emb_uni = torch.randn(B, D, generator=g).to(emb_dtype)
+    lab_same = torch.ones(B, T, dtype=torch.int64)
+    lab_uni = torch.stack([torch.randint(0, c, (B,), generator=g) for c in classes], 1).contiguous()
+    bufs = ops.HeadsBuffers(B, D, seg, dev, want_grads=False)
+    ncm = ops.confusion_len(seg)
+    Wd, bd = W.to(dev), torch.zeros(NC, device=dev)
+    pred = torch.empty((B, T), dtype=torch.int32, device=dev)
+
+    def timed(emb, labels):
+        e, l = emb.to(dev), labels.to(dev)
+        cs = torch.zeros(ncm, dtype=torch.int64, device=dev)
+        for _ in range(3):
+            ops.heads_fwd_loss_bwd(e, Wd, bd, l, bufs, oh.LOSS_CE, 0.0, out_pred=pred, cm_step=cs)
+        cs.zero_()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(10):
+            ops.heads_fwd_loss_bwd(e, Wd, bd, l, bufs, oh.LOSS_CE, 0.0, out_pred=pred, cm_step=cs)
+        t1.record()
+        torch.cuda.synchronize()
+        return t0.elapsed_time(t1) / 10, cs.cpu().numpy(), pred.cpu().numpy().copy()
+
+    t_same, cm_same, pred_same = timed(emb_same, lab_same)
+    t_uni, cm_uni, pred_uni = timed(emb_uni, lab_uni)
+    assert (pred_same == 1).all()
+    off = 0
+    for t, C in enumerate(classes):
+        exp = np.zeros((C, C), dtype=np.int64)
+        exp[1, 1] = 10 * B
+        assert np.array_equal(cm_same[off: off + C * C].reshape(C, C), exp)
+        ref = om.confusion_matrix(lab_uni[:, t].numpy(), pred_uni[:, t], C)       # the kernel's own predictions, counted on the host
+        assert np.array_equal(cm_uni[off: off + C * C].reshape(C, C), 10 * ref)
+        off += C * C
+    assert t_same <= 1.25 * t_uni + 0.002, (t_same, t_uni)

@@ -152,3 +152,27 @@ def test_backbone_gradients_are_summed_over_ranks_gloo(tmp_path):
     world, port = 2, _free_port()
     mp.spawn(_backbone_sync_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / f"bb_ok{r}").exists() for r in range(world))
+
+
+def _gather_worker(rank, world, port, out_dir):
+    """logging.gather_rows: every rank ends up with every rank's rows in rank order, uneven shards included (the epoch
+    results of a sharded run are made global with it: ADVICE round 1, scope of the logger's per-sample lists)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nkb_classification_b200.logging import gather_rows
+    full = torch.arange(7 * 3, dtype=torch.float32).reshape(7, 3)
+    lo, hi = (0, 4) if rank == 0 else (4, 7)
+    got = gather_rows(full[lo:hi].contiguous())
+    assert torch.equal(got, full)
+    lab = torch.arange(7, dtype=torch.int64).reshape(7, 1)
+    assert torch.equal(gather_rows(lab[lo:hi].contiguous()), lab)
+    assert torch.equal(gather_rows(full[:0] if rank == 0 else full), full)        # a rank without rows
+    dist.barrier()
+    dist.destroy_process_group()
+    open(os.path.join(out_dir, f"gather_ok{rank}"), "w").write("ok")
+
+
+def test_epoch_results_gather_rows_gloo(tmp_path):
+    world, port = 2, _free_port()
+    mp.spawn(_gather_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"gather_ok{r}").exists() for r in range(world))
