@@ -78,9 +78,14 @@ k1_crop_resize_normalize_tma(const K1Params p) {
         __syncthreads();
     }
 
-    const int crop = blockIdx.x;
+    // crop-major block order: the row blocks of a crop -- and the crops of a frame, which the caller lists together -- are
+    // resident at the same time, so source rows shared by overlapping boxes (the lower half of one box is the upper half
+    // of another) are fetched from HBM once and served from L2 afterwards.  (Row-block-major order walked the frames once
+    // per row block: 520 MB of DRAM reads per launch for 305 MB of distinct source bytes.)
+    const int crop = blockIdx.x / p.fby_fast;
+    const int yblk = blockIdx.x - crop * p.fby_fast;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int band = blockIdx.y * K1_WARPS + warp;
+    const int band = yblk * K1_WARPS + warp;
     const int y_begin = band * p.rows_per_warp_fast;
     if (y_begin >= p.out_h) return;
     const int nrows = min(p.rows_per_warp_fast, p.out_h - y_begin);   // <= 32: one output row per lane
@@ -96,7 +101,7 @@ k1_crop_resize_normalize_tma(const K1Params p) {
         // unaligned frame rows, a box wider than the ring, an invalid box or a letterbox that does not fit: same
         // arithmetic, direct loads
         k1_process_band<JMAX, OutT, true, false, AUG>(p, crop, g, y_begin, nrows, ox0,
-                                                      blockIdx.y == 0 && blockIdx.z == 0 && warp == 0,
+                                                      yblk == 0 && blockIdx.z == 0 && warp == 0,
                                                       AUG ? hsv_div_tab : nullptr, AUG ? hsv_lut_s + warp * 768 : nullptr);
         return;
     }

@@ -184,6 +184,7 @@ static int k1_preprocess_impl(const void* frames_base, const int64_t* frame_desc
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool f32 = out_dtype == NKBK_F32;
     p.rows_per_warp_fast = p.rows_per_warp;
+    p.fby_fast = 1;
 
     // ---- fast path: A.Resize or LongestMaxSize + PadIfNeeded, output width a whole number of 32*J column tiles,
     // no uint8 side output; the train-time augmentations have their own instantiation (k1_fast_aug.cu) ----
@@ -210,8 +211,9 @@ static int k1_preprocess_impl(const void* frames_base, const int64_t* frame_desc
         }
         const int fby = (out_h + rmax * K1_WARPS - 1) / (rmax * K1_WARPS);
         p.rows_per_warp_fast = (out_h + fby * K1_WARPS - 1) / (fby * K1_WARPS);
-        if (fj != 0 && cols / fj <= 65535 && fby <= 65535) {
-            dim3 fgrid((unsigned)n, (unsigned)fby, (unsigned)(cols / fj));
+        p.fby_fast = fby;
+        if (fj != 0 && cols / fj <= 65535 && (int64_t)n * fby < (int64_t(1) << 31)) {
+            dim3 fgrid((unsigned)((int64_t)n * fby), 1u, (unsigned)(cols / fj));
             if (aug != nullptr ? launch_k1_fast_aug(p, fj, fgrid, st, f32) : launch_k1_fast(p, fj, fgrid, st, f32)) {
                 NKBK_CHECK_LAUNCH("k1_crop_resize_normalize_tma");
                 return NKBK_OK;   // crops the TMA path cannot take are produced in-kernel by the direct-load routine
