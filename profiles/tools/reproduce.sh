@@ -33,3 +33,18 @@ done
 # --- parity
 python -m pytest tests -x -q -m gpu
 python profiles/tools/hsv_gpu_probe.py
+
+# --- round 2 (profiles/r2/)
+B="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-variants --no-api --no-graph"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_final.csv $B
+ncu --set full --clock-control none --import-source on -k regex:"k1_crop|k2_fused" -s 12 -c 2 -o gpurun_out/k1_k2fused -f $B
+ncu --set full --clock-control none --import-source on -k regex:"k1_crop" -s 6 -c 1 -o gpurun_out/k1_aug -f $B --train-aug
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct \
+    --clock-control none -k regex:k1_crop -s 4 -c 2 --csv --log-file gpurun_out/k1_crop_major_dram.csv $B
+python profiles/tools/k2_bench.py; NKBK_FUSED_TIMING=1 python profiles/tools/k2_phases.py      # the fused heads step alone
+python profiles/tools/engine_profile.py; python profiles/tools/engine_trace.py                # the API leg on the host / device
+python profiles/tools/h2d_ceiling.py                                                          # (under torchrun for N > 1)
+python bench.py --workload cfg5_shard8 --steps 50 --warmup 5 --no-cpu-baseline --no-e2e --no-variants --no-api
+T="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29712"
+$T bench.py --gpus 8 --steps 50 --warmup 5 --no-e2e                                           # weak + strong + parity_check
+$T profiles/tools/k4_phases.py                                                                # exchange phases, NCCL beside it
