@@ -219,6 +219,11 @@ REPS = 3   # every timed region = `reps` repetitions of exactly K steps, each br
 
 def _plan_for(wl, train_aug):
     from nkb_classification_b200 import transforms as T
+    return T.compile_pipeline(_pipeline_ops(wl, train_aug))
+
+
+def _pipeline_ops(wl, train_aug):
+    from nkb_classification_b200 import transforms as T
     geo = ([T.Resize(wl.out_size, wl.out_size)] if wl.mode == "stretch" else
            [T.LongestMaxSize(wl.out_size), T.PadIfNeeded(wl.out_size, wl.out_size, border_mode=T.BORDER_CONSTANT, value=0)])
     aug_ops = []
@@ -228,7 +233,7 @@ def _plan_for(wl, train_aug):
                    T.HueSaturationValue(hue_shift_limit=0, sat_shift_limit=10, val_shift_limit=50, p=0.5),
                    T.CoarseDropout(max_holes=4, min_holes=1, max_height=0.2, min_height=0.05, max_width=0.2,
                                    min_width=0.05, fill_value=[0, 0.5, 1], p=0.5)]
-    return T.compile_pipeline(geo + aug_ops + [T.Normalize(MEAN, STD), T.ToTensorV2()])
+    return geo + aug_ops + [T.Normalize(MEAN, STD), T.ToTensorV2()]
 
 
 class Leg:
@@ -560,6 +565,34 @@ def api_bench(wl, dev, n_batches):
                           "note": "wall clock around the whole epoch, epoch results (one D2H per quantity, K5 ROC-AUC "
                                   "counts) included; cold = first epoch (frames decoded + uploaded once), warm = frames "
                                   "resident in the device frame cache"}
+    # the same loop with the reference's TRAIN pipeline (configs/singletask_config.py:162-201): per-sample augmentation
+    # parameters drawn on the host per batch (vectorised), hue / sat / val tables built on the device, K1 with the
+    # augmentations fused
+    try:
+        import dataclasses
+        ds_a = D.InMemoryFrames(frames, fidx_all, labels, boxes=boxes_all, classes=classes)
+        loader_a = D.get_dataset(dict(data, dataset=ds_a), _pipeline_ops(dataclasses.replace(wl, mode="stretch"), True))
+        clocked_a = _Clocked(loader_a)
+
+        def train_a():
+            return engine.train_epoch(model, clocked_a, opt, None, scaler, criterion, dev, cfg, logger)
+
+        cfg.epoch_results_numpy = True
+        timed_epoch(train_a)                                   # cold: fills the frame cache
+        t_a, loop_a = float("inf"), float("inf")
+        for _ in range(2):
+            t_a = min(t_a, timed_epoch(train_a))
+            loop_a = min(loop_a, 1e3 * (clocked_a.t[-1] - clocked_a.t[1]) / (n_batches - 1))
+        cfg.epoch_results_numpy = False
+        out["train_epoch_train_pipeline"] = {
+            "loop_ms_per_batch": loop_a, "loop_crops_per_s": n1 / (loop_a * 1e-3), "warm_numpy_results_crops_per_s": n / t_a,
+            "resident_epochs": loader_a.stats.get("resident_epochs", 0),
+            "note": "train_epoch over get_dataset(..., train pipeline: flips + brightness/contrast + HueSaturationValue + "
+                    "CoarseDropout fused into K1); parameters drawn per batch on the host (numpy, all samples at once)"}
+        del loader_a, ds_a, clocked_a
+    except Exception as e:   # pragma: no cover
+        out["train_epoch_train_pipeline"] = {"error": repr(e)}
+
     # inference(): same frames through the inference entry point (predictions -> CSV)
     icfg = SimpleNamespace(task="single", target_column="label", enable_mixed_presicion=False, disable_tqdm=True)
 

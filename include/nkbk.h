@@ -120,6 +120,15 @@ int nkbk_preprocess_crops_aug(const void* frames_base, const int64_t* frame_desc
                               const uint8_t* aug_hsv_lut, int hsv_trunc_cols, void* out, int out_dtype,
                               uint8_t* out_u8, int32_t* bad_count, void* stream);
 
+/* The hue / sat / val tables of A.HueSaturationValue built ON THE DEVICE from the per-sample shifts, so that a batch
+ * uploads 24 bytes per sample instead of 768 (albumentations' `_shift_hsv_uint8`: an int16 ramp plus the float64 shift,
+ * `mod 180` for hue / `clip(0, 255)` for saturation and value, truncated to uint8 -- the same float64 operations here;
+ * a zero shift, or a sample without bit 3 in aug_flags, keeps the identity table).
+ *   hsv_shift   fp64 [n][3] hue, sat, val shift draws (device)
+ *   aug_flags   int32 [n] (device; as for nkbk_preprocess_crops_aug)
+ *   out_lut     uint8 [n][3][256] (device): what nkbk_preprocess_crops_aug takes as aug_hsv_lut */
+int nkbk_build_hsv_luts(const double* hsv_shift, const int32_t* aug_flags, int n, uint8_t* out_lut, void* stream);
+
 /* Host-only helper (no CUDA): the per-axis coefficient table K1 uses, for
  * parity tests on machines without a GPU.  Writes dsize entries each. */
 int nkbk_debug_axis_table(int dsize, int ssize, int horizontal, int32_t* src_index, int32_t* coef0, int32_t* coef1);

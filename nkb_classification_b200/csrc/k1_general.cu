@@ -80,6 +80,27 @@ static void launch_k1(const K1Params& p, dim3 grid, cudaStream_t st, bool genera
         k1_crop_resize_normalize<JMAX, OutT, true, false><<<grid, K1_WARPS * 32, 0, st>>>(p);
 }
 
+// albumentations' hue / sat / val tables from the per-sample shifts (float64, as numpy evaluates `ramp + shift`)
+__global__ void k1_build_hsv_luts(const double* __restrict__ shift, const int32_t* __restrict__ flags, int n,
+                                  uint8_t* __restrict__ lut) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;    // one thread per table entry
+    if (i >= (int64_t)n * 768) return;
+    const int s = (int)(i / 768), e = (int)(i - (int64_t)s * 768), c = e >> 8, v = e & 255;
+    uint8_t out = (uint8_t)v;
+    const double sh = shift[3 * s + c];
+    if ((flags[s] & K1_AUG_HSV) && sh != 0.0) {
+        double t = __dadd_rn((double)v, sh);
+        if (c == 0) {   // numpy's float mod: fmod, then the divisor's sign
+            t = fmod(t, 180.0);
+            if (t != 0.0 && t < 0.0) t = __dadd_rn(t, 180.0);
+        } else {
+            t = t < 0.0 ? 0.0 : (t > 255.0 ? 255.0 : t);
+        }
+        out = (uint8_t)(int)t;   // truncation, as ndarray.astype(uint8) of an in-range value
+    }
+    lut[i] = out;
+}
+
 struct K1AugArgs {
     const int32_t* flags;
     const float* alpha;
@@ -127,6 +148,18 @@ extern "C" int nkbk_preprocess_crops_aug(const void* frames_base, const int64_t*
     K1AugArgs a{aug_flags, aug_alpha, aug_beta, aug_holes, max_holes, hole_fill, aug_hsv_lut, hsv_trunc_cols};
     return k1_preprocess_impl(frames_base, frame_desc, n_frames, boxes, frame_idx, n, mode, out_h, out_w, max_size,
                               pad_value, mean255, denom, channel_swap, out, out_dtype, out_u8, bad_count, &a, stream);
+}
+
+extern "C" int nkbk_build_hsv_luts(const double* hsv_shift, const int32_t* aug_flags, int n, uint8_t* out_lut,
+                                   void* stream) {
+    NKBK_CHECK_ARG(n >= 0, "nkbk_build_hsv_luts: n=%d < 0", n);
+    if (n == 0) return NKBK_OK;
+    NKBK_CHECK_ARG(hsv_shift && aug_flags && out_lut, "nkbk_build_hsv_luts: NULL pointer");
+    const int64_t total = (int64_t)n * 768;
+    k1_build_hsv_luts<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(hsv_shift, aug_flags,
+                                                                                                  n, out_lut);
+    NKBK_CHECK_LAUNCH("k1_build_hsv_luts");
+    return NKBK_OK;
 }
 
 static int k1_preprocess_impl(const void* frames_base, const int64_t* frame_desc, int n_frames, const int32_t* boxes,

@@ -844,10 +844,11 @@ class DeviceCropLoader:
     # ---- resident epochs: the whole epoch planned at once ----
     def _plan_resident(self, order: List[int]) -> Optional[dict]:
         """Everything K1 needs for EVERY batch of the epoch, on the device after one copy -- or None when a frame of the
-        epoch is not in the cache (first epoch, dataset larger than the arena) or the pipeline draws per-sample
-        augmentation parameters (those stay on the per-batch path)."""
+        epoch is not in the cache (first epoch, dataset larger than the arena).  Train pipelines draw their per-sample
+        augmentation parameters batch by batch inside the loop (`PreprocessPlan.draw`, vectorised: ~2.7 ms per 4096
+        samples; the hue / sat / val tables are built on the device)."""
         cache = self.cache
-        if (not self.resident_epochs or cache is None or self.plan.augment is not None or not order
+        if (not self.resident_epochs or cache is None or not order
                 or self.device.type != "cuda" or type(self.dataset).describe is _DescDataset.describe):
             return None
         if self.drop_last:
@@ -905,8 +906,9 @@ class DeviceCropLoader:
         self.stats["resident_epochs"] += 1
         for a in range(0, n, bs):
             b = min(n, a + bs)
+            aug = self.plan.draw(b - a, self.aug_rng)            # None for a validation / inference pipeline
             img = ops.preprocess_crops(self.cache.buf, plan["boxes"][a:b], plan["fidx"][a:b], self.plan,
-                                       out_dtype=self.out_dtype, frame_desc=plan["desc"])
+                                       out_dtype=self.out_dtype, frame_desc=plan["desc"], aug=aug)
             lab = plan["labels"][:, a:b]
             target = lab[0] if names is None else {k_: lab[t] for t, k_ in enumerate(names)}
             self.stats["batches"] += 1

@@ -139,9 +139,15 @@ def upload_augment(aug, device):
         if aug.hsv_lut.shape != (n, 3, 256) or aug.hsv_lut.dtype != np.uint8:
             raise ValueError("hsv_lut must be uint8 [n, 3, 256]")
         hsv = torch.from_numpy(np.ascontiguousarray(aug.hsv_lut)).to(dev, non_blocking=True)
-    elif np.any(np.asarray(aug.flags) & 8):
-        raise ValueError("a sample has the HueSaturationValue flag but the batch carries no hsv_lut")
-    t = (torch.from_numpy(np.ascontiguousarray(aug.flags, dtype=np.int32)).to(dev, non_blocking=True),
+    elif getattr(aug, "hsv_shift", None) is None and np.any(np.asarray(aug.flags) & 8):
+        raise ValueError("a sample has the HueSaturationValue flag but the batch carries neither hsv_lut nor hsv_shift")
+    flags_d = torch.from_numpy(np.ascontiguousarray(aug.flags, dtype=np.int32)).to(dev, non_blocking=True)
+    if hsv is None and getattr(aug, "hsv_shift", None) is not None:
+        # tables built on the device from the shift draws: 24 bytes per sample cross the bus instead of 768
+        sh = torch.from_numpy(np.ascontiguousarray(aug.hsv_shift, dtype=np.float64).reshape(n, 3)).to(dev, non_blocking=True)
+        hsv = torch.empty((n, 3, 256), dtype=torch.uint8, device=dev)
+        check(lib().nkbk_build_hsv_luts(_ptr(sh), _ptr(flags_d), n, _ptr(hsv), _stream(dev)))
+    t = (flags_d,
          torch.from_numpy(np.ascontiguousarray(aug.alpha, dtype=np.float32)).to(dev, non_blocking=True),
          torch.from_numpy(np.ascontiguousarray(aug.beta, dtype=np.float32)).to(dev, non_blocking=True),
          torch.from_numpy(np.ascontiguousarray(aug.holes, dtype=np.int32)).to(dev, non_blocking=True), hsv)

@@ -213,6 +213,91 @@ class AugmentBatch:
         return int(self.holes.shape[1])
 
 
+def _fill_hsv_luts(flags: np.ndarray, hsv_shift: np.ndarray, hsv_lut: np.ndarray) -> None:
+    """hsv_luts() for every flagged sample at once (same arithmetic: int16 ramp + float64 shift); a table is only
+    computed for the samples whose shift on that channel is non-zero (albumentations keeps the identity otherwise)."""
+    on = np.nonzero(flags & AUG_HSV)[0]
+    if not on.size:
+        return
+    ramp = np.arange(0, 256, dtype=np.int16)[None, :]
+    for c in range(3):
+        rows = on[hsv_shift[on, c] != 0]
+        if not rows.size:
+            continue
+        t = ramp + hsv_shift[rows, c:c + 1]                    # float64 [rows, 256]
+        if c == 0:
+            np.mod(t, 180, out=t)
+        else:
+            np.clip(t, 0, 255, out=t)
+        hsv_lut[rows, c] = t.astype(np.uint8)
+
+
+def draw_augmentations_fast(spec: AugmentSpec, n: int, out_h: int, out_w: int, gen: np.random.Generator,
+                            host_luts: bool = False) -> AugmentBatch:
+    """The same distributions as :func:`draw_augmentations`, drawn for all ``n`` samples at once with a numpy generator
+    (op by op instead of sample by sample): ~1 ms per 4096 samples instead of ~90 ms, which is what keeps a training
+    loop with the reference's train pipeline from being bound by the host.  Per op and sample: ``random() < p``, then
+    the op's parameters -- ``uniform(a, b)`` as ``a + (b - a) * random()`` (so reversed limits behave as in Python),
+    ``randint`` inclusive on both ends.  The STREAM differs from the per-sample draw (and from albumentations', which
+    cannot be pinned here anyway); the arithmetic applied to a drawn parameter set does not.  The hue / sat / val tables
+    are left to the device (``hsv_lut`` None: ``ops.upload_augment`` builds them from ``hsv_shift`` with
+    nkbk_build_hsv_luts) unless ``host_luts``."""
+    max_holes = max(1, spec.holes[1]) if "CoarseDropout" in spec.order else 1
+    flags = np.zeros(n, dtype=np.int32)
+    alpha = np.ones(n, dtype=np.float32)
+    beta = np.zeros(n, dtype=np.float32)
+    bright = np.zeros(n, dtype=np.float64)
+    holes = np.zeros((n, max_holes, 4), dtype=np.int32)
+    has_hsv = "HueSaturationValue" in spec.order
+    hsv_shift = np.zeros((n, 3), dtype=np.float64) if has_hsv else None
+    hsv_lut = np.tile(np.arange(256, dtype=np.uint8), (n, 3, 1)) if (has_hsv and host_luts) else None
+
+    def uni(lim):
+        return lim[0] + (lim[1] - lim[0]) * gen.random(n)
+
+    for name in spec.order:
+        if name == "HorizontalFlip":
+            flags |= np.where(gen.random(n) < spec.hflip_p, AUG_HFLIP, 0).astype(np.int32)
+        elif name == "VerticalFlip":
+            flags |= np.where(gen.random(n) < spec.vflip_p, AUG_VFLIP, 0).astype(np.int32)
+        elif name == "RandomBrightnessContrast":
+            on = gen.random(n) < spec.bc_p
+            a, b = 1.0 + uni(spec.contrast_limit), 0.0 + uni(spec.brightness_limit)
+            alpha = np.where(on, a.astype(np.float32), alpha).astype(np.float32)
+            beta = np.where(on, (b * 255).astype(np.float32), beta).astype(np.float32)
+            bright = np.where(on, b, bright)
+            flags |= np.where(on, AUG_BC, 0).astype(np.int32)
+        elif name == "HueSaturationValue":
+            on = gen.random(n) < spec.hsv_p
+            sh = np.stack([uni(spec.hue_limit), uni(spec.sat_limit), uni(spec.val_limit)], 1)
+            hsv_shift[on] = sh[on]
+            flags |= np.where(on & (sh != 0).any(1), AUG_HSV, 0).astype(np.int32)
+        elif name == "CoarseDropout":
+            on = gen.random(n) < spec.cd_p
+
+            def rint_incl(lo, hi):     # randint(lo, hi) inclusive, hi an int or an array: floor(lo + u * (hi - lo + 1))
+                return (lo + np.floor(gen.random(n) * (hi - lo + 1))).astype(np.int32)
+
+            k = rint_incl(spec.holes[0], spec.holes[1])
+            ints = all(isinstance(v, (int, np.integer)) for v in (*spec.hole_h, *spec.hole_w))
+            for h in range(max_holes):
+                if ints:
+                    hh, hw = rint_incl(spec.hole_h[0], spec.hole_h[1]), rint_incl(spec.hole_w[0], spec.hole_w[1])
+                else:
+                    hh = (out_h * uni(spec.hole_h)).astype(np.int32)
+                    hw = (out_w * uni(spec.hole_w)).astype(np.int32)
+                y1, x1 = rint_incl(0, out_h - hh), rint_incl(0, out_w - hw)
+                use = (on & (h < k)).astype(np.int32)            # holes beyond the drawn count stay (0, 0, 0, 0)
+                holes[:, h, 0], holes[:, h, 1] = x1 * use, y1 * use
+                holes[:, h, 2], holes[:, h, 3] = (x1 + hw) * use, (y1 + hh) * use
+            flags |= np.where(on, k << 8, 0).astype(np.int32)
+    if hsv_lut is not None:
+        _fill_hsv_luts(flags, hsv_shift, hsv_lut)
+    lanes = cv2_hsv_simd_lanes() if has_hsv else 0
+    return AugmentBatch(flags, alpha, beta, holes, spec.fill, bright, hsv_shift, hsv_lut,
+                        (out_w // lanes) * lanes if lanes else 0)
+
+
 def draw_augmentations(spec: AugmentSpec, n: int, out_h: int, out_w: int, rng=None) -> AugmentBatch:
     """Draw what ``A.Compose.__call__`` would draw for ``n`` samples: per op, ``random() < p`` and then the op's
     ``get_params`` (albumentations 1.3.x: RandomBrightnessContrast draws contrast then brightness with ``uniform``;
@@ -270,17 +355,7 @@ def draw_augmentations(spec: AugmentSpec, n: int, out_h: int, out_w: int, rng=No
                     f |= k << 8
         flags[i] = f
     if has_hsv:
-        on = np.nonzero(flags & AUG_HSV)[0]
-        if on.size:   # hsv_luts() for every flagged sample at once (same arithmetic: int16 ramp + float64 shift)
-            ramp = np.arange(0, 256, dtype=np.int16)[None, :]
-            sh = hsv_shift[on]
-            hue = np.mod(ramp + sh[:, 0:1], 180).astype(np.uint8)
-            sat = np.clip(ramp + sh[:, 1:2], 0, 255).astype(np.uint8)
-            val = np.clip(ramp + sh[:, 2:3], 0, 255).astype(np.uint8)
-            ident = np.arange(256, dtype=np.uint8)[None, :]
-            hsv_lut[on, 0] = np.where(sh[:, 0:1] != 0, hue, ident)
-            hsv_lut[on, 1] = np.where(sh[:, 1:2] != 0, sat, ident)
-            hsv_lut[on, 2] = np.where(sh[:, 2:3] != 0, val, ident)
+        _fill_hsv_luts(flags, hsv_shift, hsv_lut)
     lanes = cv2_hsv_simd_lanes() if has_hsv else 0
     return AugmentBatch(flags, alpha, beta, holes, spec.fill, bright, hsv_shift, hsv_lut,
                         (out_w // lanes) * lanes if lanes else 0)
@@ -303,8 +378,18 @@ class PreprocessPlan:
         return dataclasses.replace(self, channel_swap=bool(swap))
 
     def draw(self, n: int, rng=None) -> Optional[AugmentBatch]:
-        """Per-sample augmentation parameters for a batch of ``n`` (None for a val / inference pipeline)."""
-        return None if self.augment is None else draw_augmentations(self.augment, n, self.out_h, self.out_w, rng)
+        """Per-sample augmentation parameters for a batch of ``n`` (None for a val / inference pipeline).
+        ``rng``: None -> all samples at once with a numpy generator seeded from Python's global ``random`` (so
+        ``random.seed(...)`` still governs the run, as it governs albumentations); a ``numpy.random.Generator`` -> the
+        same with that generator; a ``random.Random`` -> the per-sample walk in albumentations' call order
+        (:func:`draw_augmentations`, ~90 ms per 4096 samples)."""
+        if self.augment is None:
+            return None
+        if rng is None:
+            rng = np.random.default_rng(_random.getrandbits(64))
+        if isinstance(rng, np.random.Generator):
+            return draw_augmentations_fast(self.augment, n, self.out_h, self.out_w, rng)
+        return draw_augmentations(self.augment, n, self.out_h, self.out_w, rng)
 
 
 def normalize_constants(mean, std, max_pixel_value=255.0):

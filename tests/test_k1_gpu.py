@@ -423,3 +423,59 @@ def test_k1_train_pipeline_augmentations_vs_oracle(cuda_device, kw):
         run_k1(cuda_device, frames, boxes, fidx, plan)
     with pytest.raises(ValueError):
         run_k1(cuda_device, frames, boxes, fidx, base, aug=batch)
+
+
+def test_hsv_luts_built_on_the_device_equal_albumentations_tables(cuda_device):
+    """nkbk_build_hsv_luts: the hue / sat / val tables from the per-sample shifts on the device == transforms.hsv_luts
+    (albumentations' `_shift_hsv_uint8` tables: int16 ramp + float64 shift, mod 180 / clip, truncated), bit for bit;
+    hue shifts of both signs, zero shifts (identity), samples without the HueSaturationValue flag (identity)."""
+    import ctypes
+    from nkb_classification_b200 import _lib, transforms as T
+    rng = np.random.default_rng(5)
+    n = 600
+    sh = np.stack([rng.uniform(-200, 200, n), rng.uniform(-300, 300, n), rng.uniform(-300, 300, n)], 1)
+    sh[::7, 0] = 0.0
+    sh[::5, 1] = 0.0
+    sh[::11] = np.round(sh[::11])            # integer shifts: exact ties of the mod / clip
+    flags = np.where(rng.random(n) < 0.8, 8, 0).astype(np.int32) | rng.integers(0, 8, n).astype(np.int32)
+    sd, fd = torch.from_numpy(sh).to(cuda_device), torch.from_numpy(flags).to(cuda_device)
+    out = torch.empty((n, 3, 256), dtype=torch.uint8, device=cuda_device)
+    _lib.check(_lib.lib().nkbk_build_hsv_luts(ctypes.c_void_p(sd.data_ptr()), ctypes.c_void_p(fd.data_ptr()), n,
+                                             ctypes.c_void_p(out.data_ptr()),
+                                             ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    got = out.cpu().numpy()
+    ident = np.tile(np.arange(256, dtype=np.uint8), (3, 1))
+    for i in range(n):
+        exp = T.hsv_luts(*sh[i]) if flags[i] & 8 else ident
+        assert np.array_equal(got[i], exp), (i, sh[i], flags[i])
+
+
+def test_k1_train_pipeline_with_vectorised_draw_and_device_tables(cuda_device):
+    """`plan.draw(n)` (all samples at once, tables left to the device) feeds K1 the same way the per-sample draw does:
+    bit-exact against the oracle evaluated on the drawn parameters, through the TMA-ring kernel (no uint8 side output)
+    and the direct-load kernel (with it)."""
+    import random
+    from nkb_classification_b200 import transforms as T
+    rng = np.random.default_rng(29)
+    frames = rng.integers(0, 256, (3, 270, 480, 3), dtype=np.uint8)
+    boxes = _random_boxes(rng, 150, 270, 480, wmin=6) + [(0, 0, 480, 270)]
+    fidx = [i % 3 for i in range(len(boxes))]
+    base = make_plan(T, out_h=224, out_w=224)
+    plan = T.compile_pipeline([T.Resize(224, 224), T.HorizontalFlip(p=0.5), T.VerticalFlip(p=0.5),
+                               T.RandomBrightnessContrast(brightness_limit=(-0.2, 0.2), contrast_limit=(0.1, -0.5), p=0.5),
+                               T.HueSaturationValue(hue_shift_limit=15, sat_shift_limit=10, val_shift_limit=50, p=0.5),
+                               T.CoarseDropout(max_holes=4, min_holes=1, max_height=0.2, min_height=0.05, max_width=0.2,
+                                               min_width=0.05, fill_value=[0, 0.5, 1], p=0.5),
+                               T.Normalize(MEAN, STD), T.ToTensorV2()], channel_swap=base.channel_swap)
+    random.seed(4)
+    batch = plan.draw(len(boxes))
+    assert batch.hsv_lut is None and batch.hsv_shift is not None          # tables are the device's job
+    random.seed(4)
+    again = plan.draw(len(boxes))
+    assert np.array_equal(batch.flags, again.flags) and np.array_equal(batch.holes, again.holes)   # random.seed governs
+    eu8, ef32 = opre.preprocess_batch(frames, boxes, fidx, oracle_plan(plan), impl="cv2", augs=_aug_samples(batch))
+    out, u8 = run_k1(cuda_device, frames, boxes, fidx, plan, aug=batch)
+    assert np.array_equal(u8.cpu().numpy(), eu8)
+    assert_same_f32(out, ef32)
+    out_fast, _ = run_k1(cuda_device, frames, boxes, fidx, plan, want_u8=False, aug=batch)
+    assert_same_f32(out_fast, ef32)

@@ -201,3 +201,30 @@ def test_hsv_pixel_function_matches_albumentations_oracle(nkbk_lib):
     assert np.array_equal(emu, opre.shift_hsv_u8(img, 3.3, 4.4, -20.2))
     b = T.compile_pipeline(reference_train_ops(100)).draw(3, __import__("random").Random(0))
     assert b.hsv_trunc_cols == tc
+
+
+def test_vectorised_draw_has_the_distributions_of_the_per_sample_draw():
+    """`plan.draw(n)` (numpy, op by op) against `plan.draw(n, random.Random)` (albumentations' call order): same flag
+    frequencies, parameter ranges and hole geometry; holes beyond the drawn count stay zero; no host tables."""
+    import random
+    p = T.compile_pipeline(T.Compose(reference_train_ops(64)))
+    n = 40000
+    random.seed(11)
+    a = p.draw(n)
+    b = p.draw(n, random.Random(12))
+    assert a.hsv_lut is None and b.hsv_lut is not None
+    for bit in range(4):
+        fa, fb = ((a.flags >> bit) & 1).mean(), ((b.flags >> bit) & 1).mean()
+        assert abs(fa - 0.5) < 0.02 and abs(fb - 0.5) < 0.02
+    ka, kb = a.flags >> 8, b.flags >> 8
+    assert ka.max() == 4 and set(np.unique(ka)) == {0, 1, 2, 3, 4} and abs(ka.mean() - kb.mean()) < 0.05
+    on = (a.flags & 4) != 0
+    assert 0.5 <= a.alpha[on].min() and a.alpha[on].max() <= 1.1 and np.all(a.alpha[~on] == 1) and np.all(a.beta[~on] == 0)
+    assert np.allclose(a.beta[on], (a.brightness[on] * 255).astype(np.float32)) and np.abs(a.brightness).max() <= 0.2
+    hs = (a.flags & 8) != 0
+    assert np.all(a.hsv_shift[hs, 0] == 0) and np.abs(a.hsv_shift[:, 1]).max() <= 10 and np.abs(a.hsv_shift[:, 2]).max() <= 50
+    w, h = a.holes[..., 2] - a.holes[..., 0], a.holes[..., 3] - a.holes[..., 1]
+    assert np.array_equal((w > 0).sum(1), ka) and np.array_equal((h > 0).sum(1), ka)
+    assert w[w > 0].min() >= int(64 * 0.05) and w.max() <= int(64 * 0.2) and a.holes[..., 2].max() <= 64 and a.holes.min() >= 0
+    wb = b.holes[..., 2] - b.holes[..., 0]
+    assert abs(w[w > 0].mean() - wb[wb > 0].mean()) < 0.2
