@@ -645,14 +645,17 @@ class DeviceCropLoader:
         n = len(self.sampler) if self.sampler is not None else len(self.dataset)
         return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
 
-    def _order(self) -> List[int]:
+    def _order(self):
+        """Sample indices of one epoch: a list, or -- on the plain shuffle / in-order paths, where nothing walks it
+        element by element -- an int64 numpy array (a 100 k-element list costs milliseconds to build and to convert)."""
         if self.sampler is not None:
             order = list(iter(self.sampler))
         elif self.shuffle:
-            order = torch.randperm(len(self.dataset)).tolist()
+            order = torch.randperm(len(self.dataset)).numpy()
         else:
-            order = list(range(len(self.dataset)))
+            order = np.arange(len(self.dataset), dtype=np.int64)
         if self.group_by_frame and (self.sampler is not None or self.shuffle):
+            order = [int(i) for i in order]
             # keep the draw (which samples, how often) and make the samples of a frame adjacent: frames in the order of
             # their first draw -- itself random -- and samples inside a frame in draw order
             first, groups = {}, {}
@@ -663,7 +666,7 @@ class DeviceCropLoader:
             order = [i for p in sorted(groups, key=first.get) for i in groups[p]]
         return order
 
-    def _index_batches(self, order: Optional[List[int]] = None) -> Iterator[List[int]]:
+    def _index_batches(self, order=None) -> Iterator[List[int]]:
         if order is None:
             order = self._order()
         for i in range(0, len(order), self.batch_size):
@@ -848,12 +851,12 @@ class DeviceCropLoader:
         augmentation parameters batch by batch inside the loop (`PreprocessPlan.draw`, vectorised: ~2.7 ms per 4096
         samples; the hue / sat / val tables are built on the device)."""
         cache = self.cache
-        if (not self.resident_epochs or cache is None or not order
+        if (not self.resident_epochs or cache is None or len(order) == 0
                 or self.device.type != "cuda" or type(self.dataset).describe is _DescDataset.describe):
             return None
         if self.drop_last:
             order = order[: len(order) // self.batch_size * self.batch_size]
-            if not order:
+            if len(order) == 0:
                 return None
         ids, plist, raw_boxes, target = self.dataset.describe(order)
         entries = [cache.get(p) for p in plist]
@@ -862,7 +865,11 @@ class DeviceCropLoader:
         n, bs = len(ids), self.batch_size
         perm = None
         if self.sort_within_batch and n > 1:
-            perm = np.lexsort((ids, np.arange(n) // bs))         # stable: by frame inside each batch, draw order kept
+            if len(plist) <= 65536 and n % bs == 0:               # 16-bit keys: numpy's stable sort is a radix sort
+                perm = (np.argsort(ids.astype(np.uint16).reshape(-1, bs), axis=1, kind="stable")
+                        + (np.arange(n // bs, dtype=np.int64) * bs)[:, None]).reshape(-1)
+            else:
+                perm = np.lexsort((ids, np.arange(n) // bs))     # stable: by frame inside each batch, draw order kept
             ids, raw_boxes = ids[perm], raw_boxes[perm]
             pt = torch.from_numpy(perm)
             target = {k_: v[pt] for k_, v in target.items()} if isinstance(target, dict) else target[pt]
