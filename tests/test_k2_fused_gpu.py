@@ -235,3 +235,42 @@ def test_fused_k3_contention(cuda_device, classes):
         assert int(cm_uni[off: off + C * C].sum()) == 10 * B
         off += C * C
     assert t_same <= 1.10 * t_uni + 0.002, (t_same, t_uni)
+
+
+def test_k1_as_programmatic_dependent_of_the_heads_step(cuda_device):
+    """nkbk_k1_overlap_previous: K1 of the next batch enqueued behind the fused heads step as a programmatic dependent
+    (it may start while that kernel still runs, on the SMs it leaves free) -- in a loop of several steps both kernels
+    must produce exactly what the ordinary stream order produces, and the thread's launch option is restored."""
+    from nkb_classification_b200 import _lib, hotpath, transforms as T
+    dev = cuda_device
+    plan = T.compile_pipeline([T.Resize(224, 224), T.Normalize(), T.ToTensorV2()])
+    rng = np.random.default_rng(2)
+    frames = torch.from_numpy(rng.integers(0, 256, (4, 360, 640, 3), dtype=np.uint8)).to(dev)
+    n = 512
+    x0, y0 = rng.integers(0, 400, n), rng.integers(0, 200, n)
+    boxes = torch.from_numpy(np.stack([x0, y0, x0 + rng.integers(8, 240, n), y0 + rng.integers(8, 160, n)], 1).astype(np.int32)).to(dev)
+    fidx = torch.from_numpy(rng.integers(0, 4, n).astype(np.int32)).to(dev)
+    g = torch.Generator().manual_seed(0)
+    D, classes = 2048, (10,)
+    emb = torch.randn(n, D, generator=g).to(dev)
+    W, b = (torch.randn(10, D, generator=g) * 0.03).to(dev), torch.zeros(10, device=dev)
+    labels = torch.randint(0, 10, (n, 1), generator=g).to(dev)
+
+    def run(overlap):
+        hp = hotpath.HotPath(plan, classes, D, "CrossEntropyLoss", 0.0, device=dev)
+        outs = []
+        for _ in range(4):
+            bufs = hp.heads_step(emb, W, b, labels, train=True)
+            if overlap:
+                hp.mark_heads_done()
+            img = hp.preprocess(frames, boxes, fidx, overlap_previous=overlap)
+            outs.append((img.clone(), bufs.dW().clone(), bufs.loss.clone()))
+        torch.cuda.synchronize()
+        return outs, hp.cm.clone()
+
+    ref, cm_ref = run(False)
+    got, cm_got = run(True)
+    assert _lib.lib().nkbk_k1_overlap_previous(0) == 0          # the option was restored after every launch
+    for (ia, wa, la), (ib, wb, lb) in zip(ref, got):
+        assert torch.equal(ia, ib) and torch.equal(wa, wb) and torch.equal(la, lb)
+    assert torch.equal(cm_ref, cm_got)
