@@ -510,6 +510,25 @@ def pack_frames(frames: Sequence[np.ndarray], staging: Optional[torch.Tensor] = 
     return staging, total, torch.tensor(descs, dtype=torch.int64).reshape(-1, 4), sizes
 
 
+def validate_targets(target, classes, ignore_index: int = -100) -> None:
+    """Labels outside [0, C) that are not ``ignore_index`` would be silently IGNORED by the kernels (torch's loss
+    device-asserts on them): refuse them here, on the host, where a wrong class map or label column shows up for free."""
+    def check(t, n_classes, name):
+        if not isinstance(t, torch.Tensor) or t.numel() == 0 or t.is_cuda or t.dtype.is_floating_point:
+            return
+        lo, hi = int(t.min()), int(t.max())
+        if hi >= n_classes or (lo < 0 and bool(((t < 0) & (t != ignore_index)).any())):
+            raise ValueError(f"label outside [0, {n_classes}) for {name or 'the target'}: min {lo}, max {hi} "
+                             f"(only ignore_index = {ignore_index} may lie outside)")
+
+    if isinstance(target, dict) and isinstance(classes, dict):
+        for k, v in target.items():
+            if k in classes:
+                check(v, len(classes[k]), k)
+    elif isinstance(target, torch.Tensor) and isinstance(classes, (list, tuple)):
+        check(target, len(classes), "")
+
+
 def collate_targets(labels: list):
     """What default_collate makes of the reference's per-sample labels."""
     first = labels[0]
@@ -682,6 +701,7 @@ class DeviceCropLoader:
             slot.consumed.synchronize()          # K1 of the batch that used this slot last has read its sources
         slot.paths = set()                       # ... so that batch no longer pins anything in the frame cache
         ids, plist, raw_boxes, target = self.dataset.describe(indices)
+        validate_targets(target, getattr(self.dataset, "classes", None))
         n = len(ids)
         if self.sort_within_batch and n > 1:
             perm = np.argsort(ids, kind="stable")
@@ -862,6 +882,7 @@ class DeviceCropLoader:
         entries = [cache.get(p) for p in plist]
         if any(e is None for e in entries) or not isinstance(target, (dict, torch.Tensor)):
             return None
+        validate_targets(target, getattr(self.dataset, "classes", None))
         n, bs = len(ids), self.batch_size
         perm = None
         if self.sort_within_batch and n > 1:

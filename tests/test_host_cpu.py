@@ -254,3 +254,18 @@ def test_logger_and_metrics_reference_structure(golden_dir):
         assert Mx.balanced_accuracy_from_confusion(cm) == float(g[f"{n}.epoch_acc"])
     with pytest.raises(ValueError):
         Mx.compute_metrics(SimpleNamespace(task="other"), res)
+
+
+def test_loader_refuses_labels_outside_the_class_range():
+    """The kernels ignore labels outside [0, C) (torch would device-assert): the loader validates them on the host."""
+    import torch
+    from nkb_classification_b200.dataset import validate_targets
+    validate_targets(torch.tensor([0, 2, -100, 1]), ["a", "b", "c"])
+    validate_targets({"x": torch.tensor([0, 1]), "y": torch.tensor([3, -100])}, {"x": [0, 1], "y": [0, 1, 2, 3]})
+    validate_targets(["p0", "p1"], ["a"])                                  # inference: paths, nothing to check
+    with pytest.raises(ValueError):
+        validate_targets(torch.tensor([0, 3]), ["a", "b", "c"])
+    with pytest.raises(ValueError):
+        validate_targets(torch.tensor([0, -1]), ["a", "b", "c"])
+    with pytest.raises(ValueError):
+        validate_targets({"x": torch.tensor([0, 2])}, {"x": [0, 1]})
