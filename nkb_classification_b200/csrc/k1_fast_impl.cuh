@@ -192,7 +192,7 @@ k1_crop_resize_normalize_tma(const K1Params p) {
         for (int k = 0; k < pre; ++k) issue(k, ring0 + slot_stride * k, bar0 + 8u * k);
     }
 
-    const uint32_t sel0 = p.sel[0], sel1 = p.sel[1], sel2 = p.sel[2];
+    const uint32_t sel01 = (p.sel[0] & 0xFFu) | ((p.sel[1] & 0xFFu) << 8), sel2 = p.sel[2];
     const float m0f = p.m[0], m1f = p.m[1], m2f = p.m[2];
     const float d0f = p.d[0], d1f = p.d[1], d2f = p.d[2];
     const int64_t plane = (int64_t)p.out_h * p.out_w;
@@ -307,8 +307,10 @@ k1_crop_resize_normalize_tma(const K1Params p) {
             asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(w2) : "r"(a));
             const uint32_t lo = __funnelshift_r(w0, w1, sk8[j]);  // bytes o .. o+3
             const uint32_t hi = __funnelshift_r(w1, w2, sk8[j]);  // bytes o+4 .. o+7
-            H[j][0] = __dp2a_lo(cf[j], __byte_perm(lo, hi, sel0), 0u) >> 4;
-            H[j][1] = __dp2a_lo(cf[j], __byte_perm(lo, hi, sel1), 0u) >> 4;
+            // one PRMT pairs the taps of TWO channels (bytes 0,1 and 2,3); dp2a.lo / dp2a.hi pick the pair
+            const uint32_t t01 = __byte_perm(lo, hi, sel01);
+            H[j][0] = __dp2a_lo(cf[j], t01, 0u) >> 4;
+            H[j][1] = __dp2a_hi(cf[j], t01, 0u) >> 4;
             H[j][2] = __dp2a_lo(cf[j], __byte_perm(lo, hi, sel2), 0u) >> 4;
         }
         __syncwarp();  // every lane has read the slot before it is overwritten

@@ -46,8 +46,9 @@ __device__ __forceinline__ void convert_row(uint32_t (&H)[JMAX][3], const RawRow
         const uint32_t k8 = (xo[j] + R.mis) << 3;                    // shf.wrap uses the low 5 bits: (offset & 3) * 8
         const uint32_t lo = __funnelshift_r(R.w0[j], R.w1[j], k8);   // bytes o .. o+3
         const uint32_t hi = __funnelshift_r(R.w1[j], R.w2[j], k8);   // bytes o+4 .. o+7
-        H[j][0] = __dp2a_lo(cf[j], __byte_perm(lo, hi, sel0), 0u) >> 4;
-        H[j][1] = __dp2a_lo(cf[j], __byte_perm(lo, hi, sel1), 0u) >> 4;
+        const uint32_t t01 = __byte_perm(lo, hi, (sel0 & 0xFFu) | ((sel1 & 0xFFu) << 8));   // taps of channels 0 and 1
+        H[j][0] = __dp2a_lo(cf[j], t01, 0u) >> 4;
+        H[j][1] = __dp2a_hi(cf[j], t01, 0u) >> 4;
         H[j][2] = __dp2a_lo(cf[j], __byte_perm(lo, hi, sel2), 0u) >> 4;
     }
 }
