@@ -127,6 +127,11 @@ int nkbk_preprocess_crops_aug(const void* frames_base, const int64_t* frame_desc
  *   hsv_shift   fp64 [n][3] hue, sat, val shift draws (device)
  *   aug_flags   int32 [n] (device; as for nkbk_preprocess_crops_aug)
  *   out_lut     uint8 [n][3][256] (device): what nkbk_preprocess_crops_aug takes as aug_hsv_lut */
+/* Debug helper (host-synchronous): the per-CTA timeline of the calling process's last TMA-kernel K1 launch made with the
+ * environment variable NKBK_K1_TIMING set: out_host uint64 [n_ctas][3] = {SM id, %globaltimer ns at CTA entry, at the
+ * exit of its last warp}; returns the number of CTAs written (profiles/tools/k1_timeline.py). */
+int64_t nkbk_debug_k1_timeline(uint64_t* out_host, int64_t max_ctas);
+
 int nkbk_build_hsv_luts(const double* hsv_shift, const int32_t* aug_flags, int n, uint8_t* out_lut, void* stream);
 
 /* Host-only helper (no CUDA): the per-axis coefficient table K1 uses, for

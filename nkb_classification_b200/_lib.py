@@ -36,6 +36,7 @@ SYMBOLS = {
                                           c_int, POINTER(c_uint8), POINTER(c_float), POINTER(c_float), c_int,
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_int, POINTER(c_uint8), c_void_p,
                                           c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "nkbk_debug_k1_timeline": (c_int64, [c_void_p, c_int64]),
     "nkbk_build_hsv_luts": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "nkbk_debug_hsv_shift": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_void_p]),
     "nkbk_debug_brightness_contrast_lut": (c_int, [c_float, c_float, c_void_p]),

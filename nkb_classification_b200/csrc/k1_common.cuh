@@ -27,6 +27,7 @@ struct K1Params {
     int rows_per_warp;       // general kernel (<= 16)
     int rows_per_warp_fast;  // TMA kernel (<= 32)
     int fby_fast;            // TMA kernel: row blocks per crop; blockIdx.x = crop * fby_fast + row block (crop-major)
+    unsigned long long* timing;   // debug (NKBK_K1_TIMING=1): per CTA {SM id, %globaltimer at entry, at exit}, else NULL
     // ---- train-time augmentations on the resized (and padded) uint8 image, per crop (NULL = none) ----
     // applied in the reference's order: HorizontalFlip, VerticalFlip, RandomBrightnessContrast, CoarseDropout
     const int32_t* aug_flags;   // [n]  bit0 hflip, bit1 vflip, bit2 brightness/contrast, bits 8.. = number of holes

@@ -88,6 +88,25 @@ k1_crop_resize_normalize_tma(const K1Params p) {
     const int crop = blockIdx.x / p.fby_fast;
     const int yblk = blockIdx.x - crop * p.fby_fast;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    struct K1Stamp {   // debug timeline: entry stamp by thread 0, exit stamp = the latest warp exit (atomicMax)
+        unsigned long long* t;
+        __device__ static unsigned long long now() {
+            unsigned long long v;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+            return v;
+        }
+        __device__ K1Stamp(unsigned long long* base) : t(base) {
+            if (t != nullptr && threadIdx.x == 0) {
+                unsigned int sm;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+                t[0] = sm;
+                t[1] = now();
+            }
+        }
+        __device__ ~K1Stamp() {
+            if (t != nullptr && (threadIdx.x & 31) == 0) atomicMax(t + 2, now());
+        }
+    } stamp(p.timing == nullptr ? nullptr : p.timing + 3 * ((size_t)blockIdx.z * gridDim.x + blockIdx.x));
     const int band = yblk * K1_WARPS + warp;
     const int y_begin = band * p.rows_per_warp_fast;
     if (y_begin >= p.out_h) return;

@@ -122,6 +122,19 @@ static int k1_preprocess_impl(const void* frames_base, const int64_t* frame_desc
                               void* out, int out_dtype, uint8_t* out_u8, int32_t* bad_count, const K1AugArgs* aug,
                               void* stream);
 
+// debug timeline of the last TMA-kernel launch made with NKBK_K1_TIMING set (profiles/tools/k1_timeline.py)
+static unsigned long long* g_k1_timing = nullptr;
+static size_t g_k1_timing_cap = 0, g_k1_timing_n = 0;
+
+extern "C" int64_t nkbk_debug_k1_timeline(uint64_t* out_host, int64_t max_ctas) {
+    if (g_k1_timing == nullptr || out_host == nullptr) return 0;
+    const int64_t n = (int64_t)g_k1_timing_n < max_ctas ? (int64_t)g_k1_timing_n : max_ctas;
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpy(out_host, g_k1_timing, (size_t)n * 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return -1;
+    return n;
+}
+
 extern "C" int nkbk_preprocess_crops(const void* frames_base, const int64_t* frame_desc, int n_frames,
                                      const int32_t* boxes, const int32_t* frame_idx, int n, int mode, int out_h,
                                      int out_w, int max_size, const uint8_t* pad_value, const float* mean255,
@@ -218,6 +231,7 @@ static int k1_preprocess_impl(const void* frames_base, const int64_t* frame_desc
     const bool f32 = out_dtype == NKBK_F32;
     p.rows_per_warp_fast = p.rows_per_warp;
     p.fby_fast = 1;
+    p.timing = nullptr;
 
     // ---- fast path: A.Resize or LongestMaxSize + PadIfNeeded, output width a whole number of 32*J column tiles,
     // no uint8 side output; the train-time augmentations have their own instantiation (k1_fast_aug.cu) ----
@@ -247,6 +261,20 @@ static int k1_preprocess_impl(const void* frames_base, const int64_t* frame_desc
         p.fby_fast = fby;
         if (fj != 0 && cols / fj <= 65535 && (int64_t)n * fby < (int64_t(1) << 31)) {
             dim3 fgrid((unsigned)((int64_t)n * fby), 1u, (unsigned)(cols / fj));
+            static const bool want_timing = getenv("NKBK_K1_TIMING") != nullptr;   // debug: per-CTA timeline of the launch
+            if (want_timing) {
+                const size_t ctas = (size_t)fgrid.x * fgrid.z;
+                if (g_k1_timing_cap < ctas) {
+                    if (g_k1_timing) cudaFree(g_k1_timing);
+                    if (cudaMalloc(&g_k1_timing, ctas * 3 * sizeof(unsigned long long)) != cudaSuccess) g_k1_timing = nullptr;
+                    g_k1_timing_cap = g_k1_timing ? ctas : 0;
+                }
+                if (g_k1_timing) {
+                    cudaMemsetAsync(g_k1_timing, 0, ctas * 3 * sizeof(unsigned long long), st);
+                    p.timing = g_k1_timing;
+                    g_k1_timing_n = ctas;
+                }
+            }
             if (aug != nullptr ? launch_k1_fast_aug(p, fj, fgrid, st, f32) : launch_k1_fast(p, fj, fgrid, st, f32)) {
                 NKBK_CHECK_LAUNCH("k1_crop_resize_normalize_tma");
                 return NKBK_OK;   // crops the TMA path cannot take are produced in-kernel by the direct-load routine
