@@ -69,6 +69,7 @@ k1_crop_resize_normalize_tma(const K1Params p) {
     __shared__ __align__(128) uint8_t ring[K1_WARPS][K1F_RING_BYTES];
     __shared__ __align__(8) uint64_t bars[K1_WARPS][K1F_MAX_SLOTS];
     __shared__ int fetch_rows[K1_WARPS][64];
+    __shared__ uint32_t htab[2][JMAX][32];   // the CTA's horizontal tables: window offset (bit 31: valid), coefficients
     // HueSaturationValue: OpenCV's two division tables (built once per CTA) + per warp the current crop's 3 x 256 tables
     __shared__ int hsv_div_tab[AUG ? 512 : 1];
     __shared__ __align__(16) uint8_t hsv_lut_s[AUG ? K1_WARPS * 768 : 16];
@@ -109,8 +110,8 @@ k1_crop_resize_normalize_tma(const K1Params p) {
     } stamp(p.timing == nullptr ? nullptr : p.timing + 3 * ((size_t)blockIdx.z * gridDim.x + blockIdx.x));
     const int band = yblk * K1_WARPS + warp;
     const int y_begin = band * p.rows_per_warp_fast;
-    if (y_begin >= p.out_h) return;
-    const int nrows = min(p.rows_per_warp_fast, p.out_h - y_begin);   // <= 32: one output row per lane
+    const bool active = y_begin < p.out_h;   // (a warp past the last row still helps with the CTA's horizontal tables)
+    const int nrows = active ? min(p.rows_per_warp_fast, p.out_h - y_begin) : 0;   // <= 32: one output row per lane
     const int ox0 = blockIdx.z * (32 * JMAX) + lane;
 
     const CropGeom g = load_geom(p, crop);
@@ -119,51 +120,23 @@ k1_crop_resize_normalize_tma(const K1Params p) {
     int dw = p.out_w, dh = p.out_h, top = 0, left = 0;
     bool fast = fast_path_qualifies(p, g, seg_start, seg_bytes, slot_stride, nslot);
     if (LB && fast) fast = letterbox_geometry(g.bh, g.bw, p.max_size, p.out_h, p.out_w, dh, dw, top, left);
-    if (!fast) {
+    if (!fast) {   // (uniform over the CTA: it depends on the crop only)
         // unaligned frame rows, a box wider than the ring, an invalid box or a letterbox that does not fit: same
         // arithmetic, direct loads
-        k1_process_band<JMAX, OutT, true, false, AUG>(p, crop, g, y_begin, nrows, ox0,
-                                                      yblk == 0 && blockIdx.z == 0 && warp == 0,
-                                                      AUG ? hsv_div_tab : nullptr, AUG ? hsv_lut_s + warp * 768 : nullptr);
+        if (active)
+            k1_process_band<JMAX, OutT, true, false, AUG>(p, crop, g, y_begin, nrows, ox0,
+                                                          yblk == 0 && blockIdx.z == 0 && warp == 0,
+                                                          AUG ? hsv_div_tab : nullptr, AUG ? hsv_lut_s + warp * 768 : nullptr);
         return;
     }
 
     // ---- per-warp barriers ----
     const uint32_t bar0 = smem_u32(&bars[warp][0]);
     const uint32_t ring0 = smem_u32(&ring[warp][0]);
-    if (lane == 0) {
+    if (active && lane == 0) {
         for (int s = 0; s < nslot; ++s) mbar_init(bar0 + 8u * s, 1u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-
-    // ---- horizontal tables: smem byte offset of the window, funnel shift, packed coefficients ----
-    uint32_t soa[JMAX], sk8[JMAX], cf[JMAX];
-    uint32_t vmask = (1u << JMAX) - 1u;   // LB: columns of this lane that receive resized pixels (the rest is border)
-    {
-        const double sxs = axis_scale(dw, g.bw);
-        if (LB) vmask = 0;
-#pragma unroll
-        for (int j = 0; j < JMAX; ++j) {
-            int s = 0, c0 = 0, c1 = 0;
-            const int dx = ox0 + 32 * j - left;
-            const bool valid = !LB || (dx >= 0 && dx < dw);
-            if (valid) axis_coef(dx, sxs, g.bw, true, s, c0, c1);
-            int px = g.bx0 + s;
-            uint32_t c = uint32_t(c0) | (uint32_t(c1) << 16);
-            if (px + 1 >= g.fw) {  // window would leave the frame row: shift it left, weight moves to tap 1
-                px -= 1;
-                c = uint32_t(c0) << 16;
-            }
-            if (LB) {
-                vmask |= uint32_t(valid) << j;
-                if (!valid) c = 0u;   // border column: reads the box's first window, weights zero (value replaced below)
-            }
-            const uint32_t so = uint32_t(px) * 3u - seg_start;
-            soa[j] = so & ~3u;
-            sk8[j] = (so & 3u) * 8u;
-            cf[j] = c;
-        }
     }
 
     // ---- vertical tables: lane l holds output row y_begin + l ----
@@ -209,6 +182,46 @@ k1_crop_resize_normalize_tma(const K1Params p) {
     if (lane == 0) {
         const int pre = min(nslot, nfetch);
         for (int k = 0; k < pre; ++k) issue(k, ring0 + slot_stride * k, bar0 + 8u * k);
+    }
+
+    // (the first bulk copies are in flight: the horizontal tables below are computed under their latency -- the prologue's
+    // dependent chain geometry loads -> coefficient arithmetic -> first source row is what a CTA slot idles on, 2.6 us per
+    // band before this reordering)
+    // ---- horizontal tables: smem byte offset of the window, funnel shift, packed coefficients ----
+    // They depend on the crop and the column only, not on the band: the CTA's four warps share them -- warp w computes
+    // the columns j = w, w + 4 and everybody reads all of them back (two of seven double-precision coefficient sets per
+    // warp instead of seven: the prologue is what makes short bands expensive).
+    uint32_t soa[JMAX], sk8[JMAX], cf[JMAX];
+    uint32_t vmask = (1u << JMAX) - 1u;   // LB: columns of this lane that receive resized pixels (the rest is border)
+    {
+        const double sxs = axis_scale(dw, g.bw);
+        for (int j = warp; j < JMAX; j += K1_WARPS) {
+            int s = 0, c0 = 0, c1 = 0;
+            const int dx = ox0 + 32 * j - left;
+            const bool valid = !LB || (dx >= 0 && dx < dw);
+            if (valid) axis_coef(dx, sxs, g.bw, true, s, c0, c1);
+            int px = g.bx0 + s;
+            uint32_t c = uint32_t(c0) | (uint32_t(c1) << 16);
+            if (px + 1 >= g.fw) {  // window would leave the frame row: shift it left, weight moves to tap 1
+                px -= 1;
+                c = uint32_t(c0) << 16;
+            }
+            if (LB && !valid) c = 0u;   // border column: reads the box's first window, weights zero (value replaced below)
+            const uint32_t so = uint32_t(px) * 3u - seg_start;
+            htab[0][j][lane] = so | (uint32_t(valid) << 31);   // (so < the ring size)
+            htab[1][j][lane] = c;
+        }
+        __syncthreads();
+        if (!active) return;
+        if (LB) vmask = 0;
+#pragma unroll
+        for (int j = 0; j < JMAX; ++j) {
+            const uint32_t so = htab[0][j][lane];
+            if (LB) vmask |= (so >> 31) << j;
+            soa[j] = so & 0x7ffffffcu;
+            sk8[j] = (so & 3u) * 8u;
+            cf[j] = htab[1][j][lane];
+        }
     }
 
     const uint32_t sel01 = (p.sel[0] & 0xFFu) | ((p.sel[1] & 0xFFu) << 8), sel2 = p.sel[2];
