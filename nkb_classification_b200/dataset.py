@@ -506,7 +506,10 @@ def pack_frames(frames: Sequence[np.ndarray], staging: Optional[torch.Tensor] = 
             staging = staging.pin_memory()
     buf = staging.numpy()
     for f, (o, h, w, pitch) in zip(frames, descs):
-        buf[o: o + h * pitch].reshape(h, pitch)[:, : w * 3] = f.reshape(h, w * 3)
+        if pitch == w * 3 and f.flags.c_contiguous:       # rows already 16-byte multiples: one flat copy
+            buf[o: o + h * pitch] = f.reshape(-1)
+        else:
+            buf[o: o + h * pitch].reshape(h, pitch)[:, : w * 3] = f.reshape(h, w * 3)
     return staging, total, torch.tensor(descs, dtype=torch.int64).reshape(-1, 4), sizes
 
 
