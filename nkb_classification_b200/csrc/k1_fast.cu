@@ -51,12 +51,15 @@ static void launch_k1_kernel(Kern kern, const K1Params& p, dim3 grid, cudaStream
 
 template <int JMAX, bool AUG>
 static void launch_fast_j(const K1Params& p, dim3 grid, cudaStream_t st, bool f32) {
-    if (p.mode == NKBK_MODE_LETTERBOX) {
-        if (f32) launch_k1_kernel(k1_crop_resize_normalize_tma<JMAX, float, true, AUG>, p, grid, st);
-        else launch_k1_kernel(k1_crop_resize_normalize_tma<JMAX, __nv_bfloat16, true, AUG>, p, grid, st);
+    if (p.mode == NKBK_MODE_LETTERBOX && (p.padu[0] | p.padu[1] | p.padu[2]) == 0u) {   // PadIfNeeded(value = 0)
+        if (f32) launch_k1_kernel(k1_crop_resize_normalize_tma<JMAX, float, 2, AUG>, p, grid, st);
+        else launch_k1_kernel(k1_crop_resize_normalize_tma<JMAX, __nv_bfloat16, 2, AUG>, p, grid, st);
+    } else if (p.mode == NKBK_MODE_LETTERBOX) {
+        if (f32) launch_k1_kernel(k1_crop_resize_normalize_tma<JMAX, float, 1, AUG>, p, grid, st);
+        else launch_k1_kernel(k1_crop_resize_normalize_tma<JMAX, __nv_bfloat16, 1, AUG>, p, grid, st);
     } else {
-        if (f32) launch_k1_kernel(k1_crop_resize_normalize_tma<JMAX, float, false, AUG>, p, grid, st);
-        else launch_k1_kernel(k1_crop_resize_normalize_tma<JMAX, __nv_bfloat16, false, AUG>, p, grid, st);
+        if (f32) launch_k1_kernel(k1_crop_resize_normalize_tma<JMAX, float, 0, AUG>, p, grid, st);
+        else launch_k1_kernel(k1_crop_resize_normalize_tma<JMAX, __nv_bfloat16, 0, AUG>, p, grid, st);
     }
 }
 

@@ -63,9 +63,14 @@ __device__ __forceinline__ uint32_t vtap(uint32_t b0, uint32_t h0, uint32_t b1, 
 // AUG = true: the per-crop train-time augmentations (K1Params::aug_*) on the resized + padded uint8 pixel before
 // Normalize, exactly as in the general kernel (k1_general_impl.cuh): flips mirror the store address, brightness /
 // contrast and HueSaturationValue run per pixel, CoarseDropout holes become a per-row column mask.
-template <int JMAX, typename OutT, bool LB, bool AUG = false>
+// LBM = 0: A.Resize; 1: letterbox; 2: letterbox with PadIfNeeded(value = 0) -- every pipeline in the reference's configs:
+// border columns already carry zero weights, so their pixel comes out 0 = the pad value and the per-element select of
+// the pad value (two ALU instructions on the pipe this kernel loads most) is dropped.
+template <int JMAX, typename OutT, int LBM, bool AUG = false>
 __global__ void __launch_bounds__(K1_WARPS * 32, AUG ? K1F_MIN_BLOCKS_AUG : K1F_MIN_BLOCKS)
 k1_crop_resize_normalize_tma(const K1Params p) {
+    constexpr bool LB = LBM != 0;        // letterbox geometry
+    constexpr bool PADSEL = LBM == 1;    // border columns need the pad value selected in (it is not zero)
     __shared__ __align__(128) uint8_t ring[K1_WARPS][K1F_RING_BYTES];
     __shared__ __align__(8) uint64_t bars[K1_WARPS][K1F_MAX_SLOTS];
     __shared__ int fetch_rows[K1_WARPS][64];
@@ -390,7 +395,7 @@ k1_crop_resize_normalize_tma(const K1Params p) {
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
                         PA[j][c] = vtap(b0, Ht[j][c], b1, Hb[j][c]);
-                        if (LB && !(vmask >> j & 1)) PA[j][c] = p.padu[c];
+                        if (PADSEL && !(vmask >> j & 1)) PA[j][c] = p.padu[c];
                     }
                 return;
             }
@@ -403,10 +408,10 @@ k1_crop_resize_normalize_tma(const K1Params p) {
 #pragma unroll
                 for (int j = 0; j < JMAX; j += 2) {
                     uint32_t va = vtap(b0, Ht[j][c], b1, Hb[j][c]);
-                    if (LB && !(vmask >> j & 1)) va = p.padu[c];
+                    if (PADSEL && !(vmask >> j & 1)) va = p.padu[c];
                     if (j + 1 < JMAX) {
                         uint32_t vb = vtap(b0, Ht[j + 1][c], b1, Hb[j + 1][c]);
-                        if (LB && !(vmask >> (j + 1) & 1)) vb = p.padu[c];
+                        if (PADSEL && !(vmask >> (j + 1) & 1)) vb = p.padu[c];
                         float ra, rb;
                         normalize2((float)va, (float)vb, mf[c], df[c], ra, rb);
                         store_out<OutT>(oc + 32 * j, ra);
