@@ -157,7 +157,13 @@ class BaseLogger:
         # the whole training step of a crop on this path -- so `cfg.epoch_results_numpy = True` keeps the numpy arrays
         # (every consumer in the reference wraps the lists in np.array / passes them to sklearn anyway)
         as_np = bool(getattr(self.cfg, "epoch_results_numpy", False))
-        ls = (lambda a: np.ascontiguousarray(a)) if as_np else (lambda a: a.tolist())
+        # (floats as float64: what np.array() makes of the reference's lists of Python floats, so that downstream means /
+        # sklearn calls see the same dtype either way)
+        def as_array(a):
+            a = np.ascontiguousarray(a)
+            return a.astype(np.float64) if a.dtype.kind == "f" else a
+
+        ls = as_array if as_np else (lambda a: a.tolist())
         if names is None:
             res["running_loss"] = ls(loss[:, 0])
             res["confidences"] = ls(conf)

@@ -111,3 +111,37 @@ def test_pbar_update_loss_matches_reference_postfix(cuda_device):
     bar.update_loss(torch.tensor(1.5, device=cuda_device)); bar.update_loss(torch.tensor(1.5, device=cuda_device))
     assert bar.postfix == "Loss: 1.5000"            # engine.py:17
     bar.close()
+
+
+@pytest.mark.parametrize("task", ["single", "multi"])
+def test_epoch_results_as_numpy_give_the_same_metrics(cuda_device, task):
+    """cfg.epoch_results_numpy: the epoch results as numpy arrays instead of the reference's Python lists -- same
+    values, and compute_metrics (which wraps them in np.array / hands them to sklearn, as the reference's does) returns
+    the same numbers.  Second epochs run as resident epochs (the whole epoch planned at once)."""
+    from nkb_classification_b200 import engine, logging as LG, losses, metrics as MX
+    dev = cuda_device
+    loader, classes = make_loader(dev, task)
+    from nkb_classification_b200 import model as M
+    model = M.get_model({"task": task, "model": Stub(), "pretrained": False, "backbone_dropout": 0.0,
+                         "classifier_dropout": 0.0, "classifier_initialization": "kaiming_normal_"}, classes, dev)
+    crit = {"task": task, "type": "CrossEntropyLoss"}
+    cfg = SimpleNamespace(task=task, target_names=sorted(classes) if task == "multi" else None, target_column="label",
+                          enable_mixed_presicion=False, log_gradients=False, disable_tqdm=True, criterion=crit)
+    criterion = losses.get_loss(crit, dev)
+    out = {}
+    for as_np in (False, True, False):          # (first pass fills the frame cache; the other two are resident epochs)
+        cfg.epoch_results_numpy = as_np
+        torch.manual_seed(3)
+        res = engine.val_epoch(model, loader, criterion, dev, cfg, LG.BaseLogger(cfg, classes))
+        out[as_np] = (res, MX.compute_metrics(cfg, res))
+    assert loader.stats["resident_epochs"] == 2
+    (rl, ml), (rn, mn) = out[False], out[True]
+    pick = (lambda r, k: r[k]) if task == "single" else (lambda r, k: r[k]["color"])
+    assert isinstance(pick(rl, "predictions"), list) and isinstance(pick(rn, "predictions"), np.ndarray)
+    for k in ("predictions", "ground_truth", "confidences"):
+        assert np.array_equal(np.asarray(pick(rl, k)), pick(rn, k))
+    if task == "single":
+        assert ml["epoch_acc"] == mn["epoch_acc"] and ml["epoch_loss"] == mn["epoch_loss"]
+        assert np.array_equal(ml["epoch_roc_auc"], mn["epoch_roc_auc"], equal_nan=True)
+    else:
+        assert ml["epoch_acc"] == mn["epoch_acc"] and ml["color"]["epoch_acc"] == mn["color"]["epoch_acc"]
