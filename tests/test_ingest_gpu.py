@@ -172,3 +172,39 @@ def test_resident_epoch_plan_matches_streaming_path(cuda_device):
         assert t["a"].tolist() == [lab["a"][i] for i in idx] and t["b"].tolist() == [lab["b"][i] for i in idx]
         pos += img.shape[0]
     assert loader.stats["resident_epochs"] == 1 and pos == len(dm)
+
+
+def test_resident_epoch_with_train_pipeline_matches_streaming_path(cuda_device):
+    """Train pipelines (per-sample augmentation parameters) run as resident epochs too: the parameters are drawn batch
+    by batch inside the loop, exactly as the per-batch path draws them -- same `random.seed`, same shuffle, same tensors."""
+    import random
+    from nkb_classification_b200 import dataset as D, transforms as T
+    ds = make_dataset()
+    pipe = [T.Resize(224, 224), T.HorizontalFlip(p=0.5), T.VerticalFlip(p=0.5),
+            T.RandomBrightnessContrast(brightness_limit=(-0.2, 0.2), contrast_limit=(0.1, -0.5), p=0.5),
+            T.HueSaturationValue(hue_shift_limit=0, sat_shift_limit=10, val_shift_limit=50, p=0.5),
+            T.CoarseDropout(max_holes=4, min_holes=1, max_height=0.2, min_height=0.05, max_width=0.2, min_width=0.05,
+                            fill_value=[0, 0.5, 1], p=0.5),
+            T.Normalize((0.485, 0.456, 0.406), (0.229, 0.224, 0.225)), T.ToTensorV2()]
+    dt = D.InMemoryFrames(ds.frames, ds.frame_idx, ds.labels, boxes=ds.boxes, classes=list(range(5)),
+                          transform=D.Transforms(pipe))
+    res = D.DeviceCropLoader(dt, batch_size=32, shuffle=True, device=cuda_device, frame_cache_bytes=64 << 20)
+    stream = D.DeviceCropLoader(dt, batch_size=32, shuffle=True, device=cuda_device, frame_cache_bytes=64 << 20,
+                                resident_epochs=False)
+    for _ in res:          # first epochs fill the caches
+        pass
+    for _ in stream:
+        pass
+    outs = []
+    for loader in (res, stream):
+        torch.manual_seed(21)
+        random.seed(21)
+        outs.append([(img.clone(), t.clone()) for img, t in loader])
+    assert res.stats["resident_epochs"] == 1 and stream.stats["resident_epochs"] == 0
+    assert len(outs[0]) == len(outs[1]) == 4
+    for (ia, ta), (ib, tb) in zip(*outs):
+        assert torch.equal(ia, ib) and torch.equal(ta, tb)
+    torch.manual_seed(21)
+    random.seed(22)
+    again = [img.clone() for img, _ in res]
+    assert not all(torch.equal(a, b[0]) for a, b in zip(again, outs[0]))      # other parameters, other pixels
