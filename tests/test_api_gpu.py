@@ -518,3 +518,21 @@ def test_focal_loss_sum_and_none_match_reference_golden(cuda_device, golden_dir,
     assert "reduction='none'" in repr(losses.FocalLoss(reduction="none"))
     all_ignored = losses.FocalLoss(reduction="none").to(cuda_device)(z0, torch.full_like(y, -100))
     assert float(all_ignored) == 0.0
+
+
+def test_engine_sharded_epochs_equal_single_gpu_multi_gpu(cuda_device):
+    """engine.train_epoch / val_epoch with cfg.communicator over N GPUs (tests/engine_dist_check.py under torchrun):
+    parameters bit-identical on all ranks and equal to the single-GPU run, epoch results global and rank independent.
+    Needs >= 2 visible GPUs (gpurun --gpus 2)."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2 if n < 4 else 4
+    here = Path(__file__).resolve().parent
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29679", str(here / "engine_dist_check.py")],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "ENGINE_DIST_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
