@@ -89,8 +89,28 @@ def test_train_and_val_steps_do_not_sync(cuda_device, task):
     else:
         assert len(res["predictions"]["color"]) == n and len(res["running_loss"]["loss"]) == len(loader)
     assert "confusion" in res
-    vres = engine.val_epoch(model, SyncGuard(loader), criterion, dev, cfg, LG.BaseLogger(cfg, classes))
+    # the example images of the epoch (logging.py:283-285): the first batch, copied asynchronously through pinned memory
+    class First:
+        def __init__(self, inner):
+            self.inner, self.dataset, self.first = inner, inner.dataset, None
+
+        def __len__(self):
+            return len(self.inner)
+
+        def __iter__(self):
+            for i, (img, t) in enumerate(self.inner):
+                if i == 0:
+                    self.first = img.clone()
+                yield img, t
+
+    cfg.example_images = 5
+    keep = First(loader)
+    vres = engine.val_epoch(model, keep, criterion, dev, cfg, LG.BaseLogger(cfg, classes))
     assert "confusion" in vres
+    assert vres["images"].device.type == "cpu" and torch.equal(vres["images"], keep.first[:5].cpu())
+    cfg.example_images = None        # the reference's whole first batch
+    vres = engine.val_epoch(model, keep, criterion, dev, cfg, LG.BaseLogger(cfg, classes))
+    assert torch.equal(vres["images"], keep.first.cpu())
 
 
 def test_pbar_update_loss_matches_reference_postfix(cuda_device):
