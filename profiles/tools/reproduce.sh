@@ -48,3 +48,9 @@ python bench.py --workload cfg5_shard8 --steps 50 --warmup 5 --no-cpu-baseline -
 T="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29712"
 $T bench.py --gpus 8 --steps 50 --warmup 5 --no-e2e                                           # weak + strong + parity_check
 $T profiles/tools/k4_phases.py                                                                # exchange phases, NCCL beside it
+NKBK_K1_TIMING=1 python profiles/tools/k1_timeline.py --workload cfg5_1080p_64x64             # per-CTA timeline of one K1 launch
+NKBK_K1_TIMING=1 python profiles/tools/k1_timeline.py --workload cfg5_shard8
+python profiles/tools/epoch_profile.py                                                        # host time of a warm API epoch outside the loop
+T4="python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29712"
+$T4 bench.py --gpus 4 --steps 50 --warmup 5; $T4 profiles/tools/h2d_ceiling.py                # 4-GPU line + H2D ceiling
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29679 tests/engine_dist_check.py
