@@ -804,6 +804,7 @@ def run_b200(args, wl):
     if world == 1 and not args.no_variants:
         variants = {}
         vlist = [("cfg4_vit_5heads.bf16", WORKLOADS["cfg4_vit_5heads"], torch.bfloat16, torch.bfloat16, False),
+                 ("cfg1_single_224", WORKLOADS["cfg1_single_224"], torch.float32, torch.float32, False),
                  ("cfg2_multitask_256", WORKLOADS["cfg2_multitask_256"], torch.float32, torch.float32, False),
                  ("cfg3_1080p_20", WORKLOADS["cfg3_1080p_20"], torch.float32, torch.float32, False),
                  ("cfg5_1080p_64x64.letterbox", dataclasses.replace(wl, mode="letterbox"), out_dtype, emb_dtype, False),
