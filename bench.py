@@ -205,7 +205,9 @@ def workload_config(wl, out_dtype, n_gpus, transport="peer"):
         "timing": "value = the fastest of { serial: eager launches on one stream; graph: the same step replayed from a CUDA "
                   "graph; overlap: a CUDA graph whose two branches are K1 of batch i+1 and the heads step of batch i (no "
                   "dependency without the backbone); pdl / pdl_graph: ONE stream, the heads step of batch i then K1 of "
-                  "batch i+1 as its programmatic dependent (nkbk_k1_overlap_previous), eager / one graph per step } -- "
+                  "batch i+1 as its programmatic dependent (nkbk_k1_overlap_previous), eager / one graph per step; "
+                  "streams / streams_multi: eager launches on two streams, K1 of batch i+1 on one and the heads step of "
+                  "batch i on a higher-priority one, as one launch / as its separate kernels (nkbk_heads_one_launch(0)) } -- "
                   "`mode` says which; serial_value = eager; every figure is the "
                   "median of 3 repetitions of exactly K steps",
     }
@@ -383,6 +385,34 @@ def _measure_leg(leg, steps, barrier, world, dev, use_graph=True):
     except Exception as e:   # pragma: no cover
         sys.stderr.write(f"[bench] programmatic dependent launch failed ({e!r}); pdl numbers omitted\n")
     leg.hp._heads_done = None
+    # streams: eager launches on two streams -- K1 of batch i+1 on one, the heads step of batch i on a higher-priority one
+    # (round 1's pipelined form); streams_multi: the same with the heads step as its separate kernels (forward, dW,
+    # exchange + finalize), whose small CTAs slot in between K1's instead of waiting for whole SMs
+    cur = torch.cuda.current_stream(dev)
+    s_pre, s_heads = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev, priority=-1)
+
+    def two_streams():
+        s_pre.wait_stream(cur)
+        s_heads.wait_stream(cur)
+        for _ in range(steps):
+            with torch.cuda.stream(s_pre):
+                leg.k1()
+            with torch.cuda.stream(s_heads):
+                leg.heads()
+        cur.wait_stream(s_pre)
+        cur.wait_stream(s_heads)
+
+    for key, multi in (("streams", False), ("streams_multi", True)):
+        try:
+            leg.hp.one_launch = not multi           # (nkbk_heads_one_launch)
+            two_streams()
+            t_ms, t_all = _timed(two_streams, barrier, world, dev)
+            out.update({f"{key}_ms": t_ms / steps, f"{key}_all_ms": [t / steps for t in t_all]})
+        except Exception as e:   # pragma: no cover
+            sys.stderr.write(f"[bench] two-stream mode failed ({e!r}); {key} numbers omitted\n")
+        finally:
+            leg.hp.one_launch = True
+    leg.step()
     for key, overlap, pdl in (("graph", False, False), ("overlap", True, False), ("pdl_graph", False, True)):
         g = _capture(leg, dev, overlap, pdl) if use_graph else None
         if g is not None:
@@ -395,7 +425,8 @@ def _measure_leg(leg, steps, barrier, world, dev, use_graph=True):
             del g
     leg.hp._heads_done = None
     out["best_ms"], out["best_mode"] = min((out[k], k[:-3]) for k in ("serial_ms", "graph_ms", "overlap_ms", "pdl_ms",
-                                                                      "pdl_graph_ms") if k in out)
+                                                                      "pdl_graph_ms", "streams_ms", "streams_multi_ms")
+                                         if k in out)
     return out
 
 
@@ -693,7 +724,8 @@ def run_b200(args, wl):
         strong = {"global_batch": gb, "crops_per_rank": sleg.n, "value": gb / (s_ms * 1e-3), "ms_per_step": s_ms,
                   "serial_ms_per_step": sm_["serial_ms"], "graph_ms_per_step": sm_.get("graph_ms"),
                   "overlap_ms_per_step": sm_.get("overlap_ms"), "pdl_ms_per_step": sm_.get("pdl_ms"),
-                  "pdl_graph_ms_per_step": sm_.get("pdl_graph_ms"), "mode": sm_["best_mode"],
+                  "pdl_graph_ms_per_step": sm_.get("pdl_graph_ms"), "streams_ms_per_step": sm_.get("streams_ms"),
+                  "streams_multi_ms_per_step": sm_.get("streams_multi_ms"), "mode": sm_["best_mode"],
                   "k1_ms": sm_["k1_ms"], "n1_ms_per_step": float(t1.item()),
                   "speedup_vs_n1": float(t1.item()) / s_ms, "efficiency_vs_n1": float(t1.item()) / s_ms / world,
                   "heads_path": sm_["heads_path"], "gpu_launches_per_step": sm_["launches"] // steps,
@@ -858,17 +890,24 @@ def run_b200(args, wl):
         return
     if e2e is not None and e2e.get("resident"):
         e2e["resident"]["fraction_of_value"] = e2e["resident"]["value"] / value
+    config = workload_config(wl, args.out_dtype, world, transport)
+    if m["best_mode"] == "streams_multi":
+        config["launches_per_step"] = ("4: K1 on one stream; on the other the heads step as its separate kernels (forward + loss + "
+                                       "K3, dW/db, exchange + finalize) -- nkbk_heads_one_launch(0)")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
         "ms_per_step": best_ms, "serial_value": serial_value, "serial_ms_per_step": m["serial_ms"],
         "graph_ms_per_step": m.get("graph_ms"), "overlap_ms_per_step": m.get("overlap_ms"),
-        "pdl_ms_per_step": m.get("pdl_ms"), "pdl_graph_ms_per_step": m.get("pdl_graph_ms"), "mode": m["best_mode"],
+        "pdl_ms_per_step": m.get("pdl_ms"), "pdl_graph_ms_per_step": m.get("pdl_graph_ms"),
+        "streams_ms_per_step": m.get("streams_ms"), "streams_multi_ms_per_step": m.get("streams_multi_ms"),
+        "mode": m["best_mode"],
         "reps": REPS, "rep_ms_per_step": {"serial": m["serial_all_ms"], "graph": m.get("graph_all_ms"),
                                           "overlap": m.get("overlap_all_ms"), "pdl": m.get("pdl_all_ms"),
-                                          "pdl_graph": m.get("pdl_graph_all_ms")},
+                                          "pdl_graph": m.get("pdl_graph_all_ms"), "streams": m.get("streams_all_ms"),
+                                          "streams_multi": m.get("streams_multi_all_ms")},
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/int32->" + args.out_dtype + (", heads bf16 emb x f32 W -> f32" if args.emb_dtype == "bf16" else ", heads f32"),
-        "data": "synthetic", "config": workload_config(wl, args.out_dtype, world, transport),
+        "data": "synthetic", "config": config,
         "heads_path": m["heads_path"], "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": int(m["launches"]), "strong": strong, "parity_check": parity, "variants": variants, "api": api,
         "clocks": sampler.summary(),

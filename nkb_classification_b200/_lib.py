@@ -29,6 +29,7 @@ SYMBOLS = {
     "nkbk_last_error": (c_char_p, []),
     "nkbk_launch_count": (c_int64, []),
     "nkbk_k1_overlap_previous": (c_int, [c_int]),
+    "nkbk_heads_one_launch": (c_int, [c_int]),
     "nkbk_preprocess_crops": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                       POINTER(c_uint8), POINTER(c_float), POINTER(c_float), c_int, c_void_p, c_int,
                                       c_void_p, c_void_p, c_void_p]),

@@ -1015,7 +1015,7 @@ int launch_k2_fused(const K2FwdParams& f, int emb_dtype, float* reduce_buf, floa
                     int64_t* cm_total, int64_t n_cm, int mode, cudaStream_t st) {
     if (f.dlogits == nullptr) return 0;
     const char* off = getenv("NKBK_DISABLE_FUSED_HEADS");
-    if (off != nullptr && off[0] == '1') return 0;
+    if ((off != nullptr && off[0] == '1') || !heads_one_launch()) return 0;
     int dev = 0;
     NKBK_CHECK_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return 0;

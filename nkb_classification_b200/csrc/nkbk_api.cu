@@ -8,6 +8,7 @@ namespace nkbk {
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
 static thread_local int g_k1_overlap = 0;
+static thread_local int g_heads_one_launch = 1;
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -18,6 +19,7 @@ void set_error(const char* fmt, ...) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 bool k1_overlap_previous() { return g_k1_overlap != 0; }
+bool heads_one_launch() { return g_heads_one_launch != 0; }
 
 }  // namespace nkbk
 
@@ -27,5 +29,10 @@ extern "C" int64_t nkbk_launch_count(void) { return nkbk::g_launches.load(std::m
 extern "C" int nkbk_k1_overlap_previous(int enable) {
     const int prev = nkbk::g_k1_overlap;
     nkbk::g_k1_overlap = enable ? 1 : 0;
+    return prev;
+}
+extern "C" int nkbk_heads_one_launch(int enable) {
+    const int prev = nkbk::g_heads_one_launch;
+    nkbk::g_heads_one_launch = enable ? 1 : 0;
     return prev;
 }

@@ -12,7 +12,9 @@ namespace nkbk {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
-bool k1_overlap_previous();   // nkbk_k1_overlap_previous(): K1 launches as programmatic dependents
+bool k1_overlap_previous();
+bool heads_one_launch();      // nkbk_heads_one_launch(): may the heads calls use the one-launch persistent kernel?
+//   // nkbk_k1_overlap_previous(): K1 launches as programmatic dependents
 
 #define NKBK_CHECK_ARG(cond, ...)            \
     do {                                     \

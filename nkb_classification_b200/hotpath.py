@@ -43,6 +43,10 @@ class HotPath:
         self._pred: Dict[int, torch.Tensor] = {}
         self._desc = None
         self._heads_done: Optional[torch.cuda.Event] = None   # set by mark_heads_done() in overlapped loops
+        # False: the heads step as its separate kernels (nkbk_heads_one_launch(0)) -- the better partner for a K1 that
+        # runs on ANOTHER stream at a full batch per GPU: small CTAs slot in between K1's, and at world > 1 the wait for
+        # the other ranks does not hold SMs
+        self.one_launch = True
 
     def mark_heads_done(self):
         """Call right after heads_step in a loop that launches K1 with ``overlap_previous=True``."""
@@ -94,6 +98,14 @@ class HotPath:
         """One step of K2 + K3 + K4.  Returns the HeadsBuffers holding (after finalize) the global-mean
         dW/db, logits, probs, ``.loss`` [T+1] and ``.pred`` [B,T]; the epoch confusion totals are in ``self.cm``
         (already summed over ranks)."""
+        if not self.one_launch:
+            prev = _lib.lib().nkbk_heads_one_launch(0)
+            try:
+                self.one_launch = True
+                return self.heads_step(emb, W_cat, b_cat, labels, train, want_probs, want_pred, update_confusion)
+            finally:
+                self.one_launch = False
+                _lib.lib().nkbk_heads_one_launch(prev)
         B = emb.shape[0]
         bufs = self._buffers(B, train, want_probs)
         do_cm = update_confusion and labels is not None
