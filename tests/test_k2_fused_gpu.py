@@ -274,3 +274,31 @@ def test_k1_as_programmatic_dependent_of_the_heads_step(cuda_device):
     for (ia, wa, la), (ib, wb, lb) in zip(ref, got):
         assert torch.equal(ia, ib) and torch.equal(wa, wb) and torch.equal(la, lb)
     assert torch.equal(cm_ref, cm_got)
+
+
+def test_heads_one_launch_option_selects_the_separate_kernels(cuda_device):
+    """nkbk_heads_one_launch(0) / HotPath.one_launch = False: the heads step runs as its separate kernels (forward, dW,
+    finalize) instead of k2_fused_step -- same losses / gradients (1e-5), identical confusion counts and predictions,
+    nkbk_heads_last_path says which ran, and the thread's option is restored after every call."""
+    from nkb_classification_b200 import _lib, hotpath, ops, transforms as T
+    dev = cuda_device
+    plan = T.compile_pipeline([T.Resize(32, 32), T.Normalize(), T.ToTensorV2()])
+    g = torch.Generator().manual_seed(4)
+    B, D, classes = 700, 768, (2, 3, 4, 7, 14)
+    emb = torch.randn(B, D, generator=g).to(dev)
+    W, b = (torch.randn(sum(classes), D, generator=g) * 0.05).to(dev), torch.zeros(sum(classes), device=dev)
+    labels = torch.stack([torch.randint(0, c, (B,), generator=g) for c in classes], 1).contiguous().to(dev)
+    out = {}
+    for one in (True, False):
+        hp = hotpath.HotPath(plan, classes, D, "FocalLoss", 1.0, device=dev)
+        hp.one_launch = one
+        bufs = hp.heads_step(emb, W, b, labels, train=True)
+        path = ops.heads_last_path()
+        torch.cuda.synchronize()
+        out[one] = (bufs.loss.clone(), bufs.dW().clone(), bufs.db().clone(), hp.cm.clone(), bufs.pred.clone(), path)
+        assert _lib.lib().nkbk_heads_one_launch(1) == 1            # restored
+    assert out[True][5] == _lib.PATH_FUSED and out[False][5] == _lib.PATH_FFMA_FWD
+    rel = lambda a, e: float((a - e).abs().max() / e.abs().max().clamp_min(1e-30))
+    assert rel(out[False][0], out[True][0]) <= 1e-5 and rel(out[False][1], out[True][1]) <= 1e-5
+    assert rel(out[False][2], out[True][2]) <= 1e-5
+    assert torch.equal(out[False][3], out[True][3]) and torch.equal(out[False][4], out[True][4])
