@@ -7,7 +7,12 @@ from pinned host buffers (`e2e`), the dominant kernel against the HBM roofline
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
 
 N > 1 is launched by torchrun (one rank per GPU); per-GPU work is fixed (weak
-scaling): every rank owns its own frames, the only exchange is the K4 all-reduce.
+scaling): every rank owns its own frames, the only exchange is the sum of the head
+gradients and confusion counts (K4' over NVLink peer memory, or NCCL).  The same
+line also carries `strong` (N > 1: a FIXED global batch sharded over the ranks,
+with the one-GPU time of that batch measured in the same run), `parity_check`
+(sharded == single-GPU), and at N = 1 `variants` (the other named configurations)
+and `api` (crops/s through get_dataset -> train_epoch / inference).
 The backbone is out of scope for this path (timed separately by the caller):
 K2 consumes synthetic embeddings of the named width.
 """
